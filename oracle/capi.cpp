@@ -1,0 +1,228 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Not part of the product path.
+//
+// C entry points over the oracle so that tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference legs can drive it through ctypes.  Nothing under
+// zk-odst_b200/ may load this library.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include "blake2f_circuit.hpp"
+#include "curve.hpp"
+#include "mock_prover.hpp"
+#include "xorshift.hpp"
+
+using namespace zko;
+
+static void set_msg(char* msg, size_t len, const std::string& s) {
+  if (msg && len) {
+    snprintf(msg, len, "%s", s.c_str());
+  }
+}
+
+extern "C" {
+
+// ---- BLAKE2b -----------------------------------------------------------------------------
+int zko_blake2f_F(const uint8_t in[213], uint8_t out[64]) {
+  Blake2fInput x;
+  if (parse_eip152(in, x)) return -1;
+  uint64_t h[8];
+  memcpy(h, x.h, 64);
+  blake2b_F(h, x.m, x.t, x.f, x.rounds);
+  memcpy(out, h, 64);
+  return 0;
+}
+void zko_blake2b(const char* personal16, const uint8_t* data, size_t len, uint8_t out[64]) {
+  Blake2b st(personal16);
+  st.update(data, len);
+  st.finalize(out);
+}
+void zko_xorshift_u64(const uint8_t seed[16], size_t n, uint64_t* out) {
+  XorShiftRng rng(seed);
+  for (size_t i = 0; i < n; i++) out[i] = rng.next_u64();
+}
+
+// ---- fields (which: 0 = Fp, 1 = Fq); all elements are 4 x u64 Montgomery limbs ------------
+// consts layout: MOD, R, R2, R3, {INV,0,0,0}, GENERATOR, ROOT_OF_UNITY, DELTA, ZETA  (raw
+// canonical integers for GENERATOR.. so tests can compare against SURVEY Appendix A.1)
+void zko_field_consts(int which, uint64_t out[9 * 4]) {
+  auto fill = [&](auto tag) {
+    typedef decltype(tag) F;
+    const auto& c = F::C();
+    memset(out, 0, 9 * 32);
+    memcpy(out + 4, c.R.l, 32);
+    memcpy(out + 8, c.R2.l, 32);
+    memcpy(out + 12, c.R3.l, 32);
+    out[16] = c.inv;
+    c.generator.to_raw(out + 20);
+    c.root_of_unity.to_raw(out + 24);
+    c.delta.to_raw(out + 28);
+    c.zeta.to_raw(out + 32);
+  };
+  if (which == 0) {
+    memcpy(out, FpParams::MOD, 32);
+    uint64_t m[4];
+    memcpy(m, FpParams::MOD, 32);
+    fill(Fp());
+    memcpy(out, m, 32);
+  } else {
+    uint64_t m[4];
+    memcpy(m, FqParams::MOD, 32);
+    fill(Fq());
+    memcpy(out, m, 32);
+  }
+}
+// op: 0 mul, 1 add, 2 sub, 3 invert(a), 4 from_raw(a) (canonical -> Montgomery),
+//     5 to_raw(a), 6 sqrt(a) (returns 0/1 in rc)
+int zko_field_op(int which, int op, const uint64_t a[4], const uint64_t b[4], uint64_t out[4]) {
+  auto run = [&](auto tag) -> int {
+    typedef decltype(tag) F;
+    F x, y, r;
+    memcpy(x.l, a, 32);
+    if (b) memcpy(y.l, b, 32);
+    int rc = 0;
+    switch (op) {
+      case 0: r = x * y; break;
+      case 1: r = x + y; break;
+      case 2: r = x - y; break;
+      case 3: r = x.invert(); break;
+      case 4: r = F::from_raw(a); break;
+      case 5: x.to_raw(r.l); break;
+      case 6: rc = x.sqrt(r) ? 1 : 0; break;
+      default: return -1;
+    }
+    memcpy(out, r.l, 32);
+    return rc;
+  };
+  return which == 0 ? run(Fp()) : run(Fq());
+}
+void zko_field_from_u512(int which, const uint64_t v[8], uint64_t out[4]) {
+  if (which == 0) {
+    Fp r = Fp::from_u512(v);
+    memcpy(out, r.l, 32);
+  } else {
+    Fq r = Fq::from_u512(v);
+    memcpy(out, r.l, 32);
+  }
+}
+
+// ---- circuit ------------------------------------------------------------------------------
+uint64_t zko_rows_per_compression(uint32_t rounds) { return rows_per_compression(rounds); }
+
+uint32_t zko_spread16(uint32_t x) { return spread16(x); }
+uint32_t zko_get_tag(uint32_t x) { return get_tag(x); }
+uint32_t zko_even_bits32(uint32_t x) { return even_bits32(x); }
+uint32_t zko_odd_bits32(uint32_t x) { return odd_bits32(x); }
+
+static int parse_inputs(const uint8_t* inputs213, size_t n, std::vector<Blake2fInput>& v,
+                        uint32_t rounds) {
+  v.resize(n);
+  for (size_t i = 0; i < n; i++) {
+    if (parse_eip152(inputs213 + 213 * i, v[i])) return -1;
+    if (v[i].rounds != rounds) return -2;
+  }
+  return 0;
+}
+
+// Witness generation (Circuit::synthesize).  advice_mont: 12 * n * 4 u64 (column-major by
+// halo2 column index, 32-byte Montgomery Fp per cell) or NULL; advice_raw: 12 * n u64 or
+// NULL; digests: n_compressions * 8 u64 or NULL.
+int zko_blake2f_witness(int k, uint32_t rounds, const uint8_t* inputs213, size_t n_compressions,
+                        uint64_t* advice_mont, uint64_t* advice_raw, uint64_t* digests) {
+  try {
+    std::vector<Blake2fInput> in;
+    int rc = parse_inputs(inputs213, n_compressions, in, rounds);
+    if (rc) return rc;
+    ConstraintSystem cs;
+    blake2f_configure(cs);
+    Blake2fAssignment as;
+    as.want_shape = false;
+    blake2f_synthesize(as, k, rounds, in.data(), n_compressions, cs.blinding_factors());
+    size_t n = as.n;
+    for (int c = 0; c < NUM_ADVICE; c++)
+      for (size_t r = 0; r < n; r++) {
+        if (advice_raw) advice_raw[c * n + r] = as.advice[c][r];
+        if (advice_mont) {
+          Fp v = Fp::from_u64(as.advice[c][r]);
+          memcpy(advice_mont + (c * n + r) * 4, v.l, 32);
+        }
+      }
+    if (digests)
+      for (size_t j = 0; j < n_compressions; j++) memcpy(digests + 8 * j, as.outputs[j].data(), 64);
+    return 0;
+  } catch (std::exception& e) {
+    fprintf(stderr, "zko_blake2f_witness: %s\n", e.what());
+    return -3;
+  }
+}
+
+// MockProver-equivalent over an advice matrix given as integers (12 * n u64, column-major).
+int zko_mock_verify_raw(int k, uint32_t rounds, size_t n_compressions, const uint64_t* advice_raw,
+                        char* msg, size_t msg_len) {
+  try {
+    CircuitShape sh;
+    build_shape(sh, k, rounds, n_compressions);
+    std::vector<std::vector<uint64_t>> adv(NUM_ADVICE, std::vector<uint64_t>(sh.n));
+    for (int c = 0; c < NUM_ADVICE; c++) memcpy(adv[c].data(), advice_raw + c * sh.n, 8 * sh.n);
+    MockFailure f = mock_verify(sh, adv);
+    set_msg(msg, msg_len, f.what);
+    return f.ok ? 0 : 1;
+  } catch (std::exception& e) {
+    set_msg(msg, msg_len, e.what());
+    return -3;
+  }
+}
+// Same, over Montgomery-form cells (what the CUDA path emits).  Any cell >= 2^64 fails.
+int zko_mock_verify_mont(int k, uint32_t rounds, size_t n_compressions,
+                         const uint64_t* advice_mont, char* msg, size_t msg_len) {
+  size_t n = (size_t)1 << k;
+  std::vector<uint64_t> raw(NUM_ADVICE * n);
+  for (size_t i = 0; i < NUM_ADVICE * n; i++) {
+    Fp v;
+    memcpy(v.l, advice_mont + 4 * i, 32);
+    if (!raw_geq(FpParams::MOD, v.l) || raw_geq(v.l, FpParams::MOD)) {
+      set_msg(msg, msg_len, "non-canonical Montgomery limb");
+      return 2;
+    }
+    u64 r[4];
+    v.to_raw(r);
+    if (r[1] | r[2] | r[3]) {
+      set_msg(msg, msg_len, "cell value >= 2^64 at index " + std::to_string(i));
+      return 2;
+    }
+    raw[i] = r[0];
+  }
+  return zko_mock_verify_raw(k, rounds, n_compressions, raw.data(), msg, msg_len);
+}
+
+// Circuit description for cross-checking the product's hard-wired tables.
+// Writes "col,rot;" lists etc. as text.
+int zko_describe_circuit(int k, uint32_t rounds, size_t n_compressions, char* out, size_t out_len) {
+  try {
+    CircuitShape sh;
+    build_shape(sh, k, rounds, n_compressions);
+    std::ostringstream os;
+    os << "degree=" << sh.cs.degree() << "\nblinding_factors=" << sh.blinding_factors
+       << "\nnum_fixed=" << sh.cs.num_fixed_columns << "\nnum_advice=" << sh.cs.num_advice_columns
+       << "\nadvice_queries=";
+    for (auto& q : sh.cs.advice_queries) os << q.column << "," << q.rotation << ";";
+    os << "\nfixed_queries=";
+    for (auto& q : sh.cs.fixed_queries) os << q.column << "," << q.rotation << ";";
+    os << "\npermutation_columns=";
+    for (int c : sh.cs.permutation_columns) os << c << ";";
+    os << "\nselectors=";
+    for (auto& a : sh.selector_assignments)
+      os << a.selector << ":" << a.fixed_column << ":" << a.assigned_root << ":" << a.combination_len
+         << ";";
+    os << "\nn_copies=" << sh.copies.size() << "\nn_polys=";
+    size_t np = 0;
+    for (auto& g : sh.cs.gates) np += g.polys.size();
+    os << np << "\n";
+    set_msg(out, out_len, os.str());
+    return 0;
+  } catch (std::exception& e) {
+    set_msg(out, out_len, e.what());
+    return -3;
+  }
+}
+
+}  // extern "C"
