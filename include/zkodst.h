@@ -1,0 +1,109 @@
+/*
+ * zkodst.h — C ABI of the B200-native prover backend for zk-odst's BLAKE2f Table16 circuit.
+ *
+ * This is the drop-in boundary: the entry points a Rust `extern "C"` block
+ * (rust/zkodst-sys) binds in place of the CPU work the reference reaches
+ * through halo2_proofs 0.3.0.  Plain pointers and sizes only; every call returns an
+ * int32_t status (0 = ZK_OK, negative = ZK_E_*); nothing unwinds across the boundary.
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with
+ * ZK_E_CUDA.
+ *
+ * Each declaration cites the reference interface it replaces (paths relative to the
+ * reference repository root).
+ */
+#ifndef ZKODST_H
+#define ZKODST_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZK_OK 0
+#define ZK_E_INVALID (-1)   /* bad argument (NULL pointer, k out of range, malformed input) */
+#define ZK_E_CUDA (-2)      /* CUDA runtime / driver error, or no device */
+#define ZK_E_NOMEM (-3)     /* host or device allocation failed */
+#define ZK_E_ROWS (-4)      /* circuit does not fit 2^k rows (halo2 Error::NotEnoughRowsAvailable) */
+#define ZK_E_INPUT (-5)     /* EIP-152 input rejected (f not in {0,1}, rounds mismatch) */
+#define ZK_E_STATE (-6)     /* call order violated (e.g. prove before params/keygen) */
+#define ZK_E_VERIFY (-7)    /* proof rejected / constraint not satisfied */
+#define ZK_E_BUFFER (-8)    /* caller buffer too small; required size written back */
+
+#define ZK_BLAKE2F_INPUT_BYTES 213 /* EIP-152: rounds(4 BE) h(64) m(128) t(16) f(1) */
+#define ZK_FIELD_BYTES 32          /* Fp / Fq element: 4 x u64 LE limbs, Montgomery form */
+#define ZK_POINT_BYTES 64          /* Vesta affine point: x, y (Montgomery Fq) */
+#define ZK_NUM_ADVICE 12           /* table16.rs:281-310 + spread_table.rs:435-441 */
+
+typedef struct zk_ctx zk_ctx;
+
+/* ---- context ------------------------------------------------------------------------- */
+
+/* One context per (host thread, device).  Owns all device memory it allocates and a private
+ * CUDA stream.  Replaces nothing in the reference (which has no device); it is the handle
+ * the Rust shim keeps inside its `Table16Chip` backend state. */
+int32_t zk_ctx_create(int32_t device_id, zk_ctx** out);
+void zk_ctx_destroy(zk_ctx* ctx);
+/* Last error text for this context (valid until the next call on the context). */
+const char* zk_last_error(const zk_ctx* ctx);
+/* Run the context's work on an externally owned CUDA stream (cudaStream_t as void*);
+ * NULL restores the private stream. */
+int32_t zk_ctx_set_stream(zk_ctx* ctx, void* cuda_stream);
+int32_t zk_ctx_synchronize(zk_ctx* ctx);
+/* Number of kernels this context has launched so far (bench.py `gpu_launches`). */
+uint64_t zk_ctx_launch_count(const zk_ctx* ctx);
+/* Milliseconds the most recent launch of the named kernel class took, measured with CUDA
+ * events on the context's stream.  which: 0 = witness kernel. */
+int32_t zk_ctx_last_kernel_ms(zk_ctx* ctx, int32_t which, float* ms);
+int32_t zk_ctx_enable_timing(zk_ctx* ctx, int32_t on);
+
+/* Integer-pipe micro-benchmark (the compute roofline of the field-arithmetic kernels;
+ * SURVEY.md §6 asks for it because no INT32 peak was measured by the driver).
+ * mode 0 = mad.lo.u32, 1 = mad.wide.u32, 2 = mad.lo.cc/madc.hi.cc chain.  Writes issued
+ * instructions per second over the whole device. */
+int32_t zk_bench_int_pipe(zk_ctx* ctx, int32_t mode, uint32_t iters, double* instr_per_sec);
+
+/* ---- circuit shape ------------------------------------------------------------------- */
+
+/* Rows one compression region occupies (292 + 392 * rounds, docs/CIRCUIT.md).  Replaces the
+ * row arithmetic of compression/compression_util.rs:32-43,112-205 (dead code upstream). */
+int32_t zk_blake2f_rows_per_compression(uint32_t rounds, uint64_t* rows);
+/* Smallest k such that n_compressions regions plus the 2^16-row spread table plus the
+ * blinding rows fit (reference default k = 17: spread_table.rs:759, benches/blake2f.rs:149). */
+int32_t zk_blake2f_min_k(uint32_t rounds, uint64_t n_compressions, int32_t* k);
+
+/* FNV-1a digests of one region's copy constraints (as LE u32 quadruples left col, left row,
+ * right col, right row in `copy_advice` call order) and selector activations ([12][R] bytes),
+ * so that a host-only test can compare the layout with an independent implementation. */
+int32_t zk_blake2f_layout_hash(uint32_t rounds, uint64_t* copies_hash, uint64_t* selectors_hash,
+                               uint64_t* n_copies);
+
+/* ---- K1: batched witness generation ------------------------------------------------------
+ * Replaces `Circuit::synthesize` for the BLAKE2f circuit: Table16Chip::compress
+ * (blake2f-circuit/src/blake2f/table16.rs:361-373, `todo!()` upstream),
+ * CompressionConfig::{initialize_with_iv, compress, digest} (table16/compression.rs:1078-1149),
+ * SpreadVar::with_lookup (table16/spread_table.rs:257-285) and AssignedBits::assign_bits
+ * (table16.rs:136-166), i.e. every `region.assign_advice` the chip performs.
+ *
+ * inputs: n_compressions x 213-byte EIP-152 records, all with the same `rounds`.
+ * advice: ZK_NUM_ADVICE columns x 2^k rows x 32 bytes, column-major by halo2 advice column
+ *         index, each cell a Montgomery-form pallas::Base — the in-memory image of halo2's
+ *         `Vec<Polynomial<Fp, LagrangeCoeff>>` before blinding.  Compression j occupies rows
+ *         [j*R, (j+1)*R).  All other cells are zero.
+ * digests: n_compressions x 8 u64 (the F outputs h'), or NULL.
+ *
+ * Host-buffer form: copies inputs H2D, runs the kernels, copies results D2H. */
+int32_t zk_blake2f_witness_batch(zk_ctx* ctx, int32_t k, uint32_t rounds,
+                                 const uint8_t* inputs, uint64_t n_compressions,
+                                 void* advice_out, uint64_t* digests_out);
+/* Device-buffer form: all three pointers are device memory on the context's device; runs
+ * asynchronously on the context's stream. */
+int32_t zk_blake2f_witness_batch_device(zk_ctx* ctx, int32_t k, uint32_t rounds,
+                                        const uint8_t* d_inputs, uint64_t n_compressions,
+                                        void* d_advice, uint64_t* d_digests);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKODST_H */

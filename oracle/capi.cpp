@@ -194,6 +194,41 @@ int zko_mock_verify_mont(int k, uint32_t rounds, size_t n_compressions,
   return zko_mock_verify_raw(k, rounds, n_compressions, raw.data(), msg, msg_len);
 }
 
+static uint64_t fnv1a(uint64_t h, const void* data, size_t len) {
+  const uint8_t* p = (const uint8_t*)data;
+  for (size_t i = 0; i < len; i++) {
+    h ^= p[i];
+    h *= 0x100000001b3ULL;
+  }
+  return h;
+}
+// FNV-1a digests of one region's copy constraints and selector activations (same definition
+// as zk_blake2f_layout_hash in include/zkodst.h), from the oracle's own synthesize.
+int zko_layout_hash(uint32_t rounds, uint64_t* copies_hash, uint64_t* selectors_hash,
+                    uint64_t* n_copies) {
+  try {
+    Blake2fAssignment as;
+    as.want_witness = false;
+    int k = 17;
+    while (rows_per_compression(rounds) + 6 > ((size_t)1 << k)) k++;
+    blake2f_synthesize(as, k, rounds, nullptr, 1, 5);
+    size_t R = rows_per_compression(rounds);
+    uint64_t h = 0xcbf29ce484222325ULL;
+    for (auto& c : as.copies) {
+      uint32_t rec[4] = {(uint32_t)c.lc, (uint32_t)c.lr, (uint32_t)c.rc, (uint32_t)c.rr};
+      h = fnv1a(h, rec, sizeof rec);
+    }
+    *copies_hash = h;
+    uint64_t hs = 0xcbf29ce484222325ULL;
+    for (int s = 0; s < NUM_SEL; s++) hs = fnv1a(hs, as.selectors[s].data(), R);
+    *selectors_hash = hs;
+    *n_copies = as.copies.size();
+    return 0;
+  } catch (std::exception& e) {
+    return -3;
+  }
+}
+
 // Circuit description for cross-checking the product's hard-wired tables.
 // Writes "col,rot;" lists etc. as text.
 int zko_describe_circuit(int k, uint32_t rounds, size_t n_compressions, char* out, size_t out_len) {

@@ -1,0 +1,136 @@
+"""ctypes wrapper of the CPU oracle (oracle/libzkoracle.so).  Test infrastructure only."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ODIR = os.path.join(ROOT, "oracle")
+_L = None
+
+
+def build():
+    subprocess.run(["make", "-C", ODIR, "-s"], check=True)
+    return os.path.join(ODIR, "libzkoracle.so")
+
+
+class Oracle:
+    def __init__(self, lib):
+        self.lib = lib
+        c = ctypes
+        vp, u64, u32, sz = c.c_void_p, c.c_uint64, c.c_uint32, c.c_size_t
+        lib.zko_blake2f_F.argtypes = [c.c_char_p, c.c_char_p]
+        lib.zko_blake2b.argtypes = [c.c_char_p, c.c_char_p, sz, c.c_char_p]
+        lib.zko_xorshift_u64.argtypes = [c.c_char_p, sz, vp]
+        lib.zko_field_consts.argtypes = [c.c_int, vp]
+        lib.zko_field_op.argtypes = [c.c_int, c.c_int, vp, vp, vp]
+        lib.zko_field_from_u512.argtypes = [c.c_int, vp, vp]
+        lib.zko_rows_per_compression.restype = u64
+        lib.zko_rows_per_compression.argtypes = [u32]
+        for f in ("zko_spread16", "zko_get_tag", "zko_even_bits32", "zko_odd_bits32"):
+            getattr(lib, f).restype = u32
+            getattr(lib, f).argtypes = [u32]
+        lib.zko_blake2f_witness.argtypes = [c.c_int, u32, c.c_char_p, sz, vp, vp, vp]
+        lib.zko_mock_verify_raw.argtypes = [c.c_int, u32, sz, vp, c.c_char_p, sz]
+        lib.zko_mock_verify_mont.argtypes = [c.c_int, u32, sz, vp, c.c_char_p, sz]
+        lib.zko_layout_hash.argtypes = [u32, c.POINTER(u64), c.POINTER(u64), c.POINTER(u64)]
+        lib.zko_describe_circuit.argtypes = [c.c_int, u32, sz, c.c_char_p, sz]
+
+    # -- BLAKE2 ---------------------------------------------------------------------------
+    def blake2f(self, record):
+        out = ctypes.create_string_buffer(64)
+        rc = self.lib.zko_blake2f_F(record, out)
+        return rc, out.raw
+
+    def blake2b(self, personal, data):
+        out = ctypes.create_string_buffer(64)
+        self.lib.zko_blake2b(personal, data, len(data), out)
+        return out.raw
+
+    def xorshift(self, seed, n):
+        out = np.zeros(n, dtype=np.uint64)
+        self.lib.zko_xorshift_u64(seed, n, out.ctypes.data)
+        return out
+
+    # -- fields ---------------------------------------------------------------------------
+    @staticmethod
+    def _limbs(v):
+        return np.array([(v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
+
+    @staticmethod
+    def _int(a):
+        return sum(int(a[i]) << (64 * i) for i in range(len(a)))
+
+    def consts(self, which):
+        out = np.zeros(36, dtype=np.uint64)
+        self.lib.zko_field_consts(which, out.ctypes.data)
+        names = ["MOD", "R", "R2", "R3", "INV", "GENERATOR", "ROOT_OF_UNITY", "DELTA", "ZETA"]
+        return {n: self._int(out[4 * i:4 * i + 4]) for i, n in enumerate(names)}
+
+    def field_op(self, which, op, a, b=0):
+        out = np.zeros(4, dtype=np.uint64)
+        la, lb = self._limbs(a), self._limbs(b)
+        rc = self.lib.zko_field_op(which, op, la.ctypes.data, lb.ctypes.data, out.ctypes.data)
+        return rc, self._int(out)
+
+    def from_u512(self, which, v):
+        out = np.zeros(4, dtype=np.uint64)
+        lv = np.array([(v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(8)], dtype=np.uint64)
+        self.lib.zko_field_from_u512(which, lv.ctypes.data, out.ctypes.data)
+        return self._int(out)
+
+    # -- circuit --------------------------------------------------------------------------
+    def rows_per_compression(self, rounds):
+        return self.lib.zko_rows_per_compression(rounds)
+
+    def witness(self, k, rounds, inputs, n, mont=True, raw=False):
+        nrows = 1 << k
+        a_m = np.zeros((12, nrows, 4), dtype=np.uint64) if mont else None
+        a_r = np.zeros((12, nrows), dtype=np.uint64) if raw else None
+        dig = np.zeros((n, 8), dtype=np.uint64)
+        rc = self.lib.zko_blake2f_witness(
+            k, rounds, inputs, n, a_m.ctypes.data if mont else None,
+            a_r.ctypes.data if raw else None, dig.ctypes.data)
+        if rc:
+            raise RuntimeError(f"zko_blake2f_witness rc={rc}")
+        return a_m, a_r, dig
+
+    def mock_verify_raw(self, k, rounds, n, advice_raw):
+        msg = ctypes.create_string_buffer(512)
+        rc = self.lib.zko_mock_verify_raw(k, rounds, n, advice_raw.ctypes.data, msg, 512)
+        return rc, msg.value.decode()
+
+    def mock_verify_mont(self, k, rounds, n, advice_mont):
+        msg = ctypes.create_string_buffer(512)
+        rc = self.lib.zko_mock_verify_mont(k, rounds, n, advice_mont.ctypes.data, msg, 512)
+        return rc, msg.value.decode()
+
+    def layout_hash(self, rounds):
+        a, b, n = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+        rc = self.lib.zko_layout_hash(rounds, ctypes.byref(a), ctypes.byref(b), ctypes.byref(n))
+        assert rc == 0
+        return a.value, b.value, n.value
+
+    def describe(self, k, rounds, n):
+        buf = ctypes.create_string_buffer(1 << 16)
+        rc = self.lib.zko_describe_circuit(k, rounds, n, buf, 1 << 16)
+        assert rc == 0, buf.value
+        return dict(line.split("=", 1) for line in buf.value.decode().strip().split("\n"))
+
+
+def load():
+    global _L
+    if _L is None:
+        path = os.path.join(ODIR, "libzkoracle.so")
+        if not os.path.exists(path) or any(
+            os.path.getmtime(os.path.join(ODIR, f)) > os.path.getmtime(path)
+            for f in os.listdir(ODIR) if f.endswith((".hpp", ".cpp"))
+        ):
+            try:
+                build()
+            except Exception:
+                if not os.path.exists(path):
+                    raise
+        _L = Oracle(ctypes.CDLL(path))
+    return _L

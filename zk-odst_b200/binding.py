@@ -1,0 +1,157 @@
+"""ctypes binding of include/zkodst.h."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+ERRORS = {
+    -1: "ZK_E_INVALID", -2: "ZK_E_CUDA", -3: "ZK_E_NOMEM", -4: "ZK_E_ROWS", -5: "ZK_E_INPUT",
+    -6: "ZK_E_STATE", -7: "ZK_E_VERIFY", -8: "ZK_E_BUFFER",
+}
+
+
+class ZkError(RuntimeError):
+    def __init__(self, code, msg=""):
+        super().__init__(f"{ERRORS.get(code, code)}: {msg}")
+        self.code = code
+
+
+def library_path():
+    return os.path.join(_HERE, "libzkodst.so")
+
+
+def load_library():
+    """Loads libzkodst.so; fails loudly if it has not been built (no fallback)."""
+    global _LIB
+    if _LIB is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise ZkError(-6, f"{path} is missing: run `python zk-odst_b200/build.py` "
+                              "(or __graft_entry__.build()); there is no CPU fallback")
+        lib = ctypes.CDLL(path)
+        c = ctypes
+        vp, u64, i32, u32 = c.c_void_p, c.c_uint64, c.c_int32, c.c_uint32
+        sigs = {
+            "zk_ctx_create": (i32, [i32, c.POINTER(vp)]),
+            "zk_ctx_destroy": (None, [vp]),
+            "zk_last_error": (c.c_char_p, [vp]),
+            "zk_ctx_set_stream": (i32, [vp, vp]),
+            "zk_ctx_synchronize": (i32, [vp]),
+            "zk_ctx_launch_count": (u64, [vp]),
+            "zk_ctx_last_kernel_ms": (i32, [vp, i32, c.POINTER(c.c_float)]),
+            "zk_ctx_enable_timing": (i32, [vp, i32]),
+            "zk_bench_int_pipe": (i32, [vp, i32, u32, c.POINTER(c.c_double)]),
+            "zk_blake2f_rows_per_compression": (i32, [u32, c.POINTER(u64)]),
+            "zk_blake2f_min_k": (i32, [u32, u64, c.POINTER(i32)]),
+            "zk_blake2f_layout_hash": (i32, [u32, c.POINTER(u64), c.POINTER(u64), c.POINTER(u64)]),
+            "zk_blake2f_witness_batch": (i32, [vp, i32, u32, vp, u64, vp, vp]),
+            "zk_blake2f_witness_batch_device": (i32, [vp, i32, u32, vp, u64, vp, vp]),
+        }
+        for name, (res, args) in sigs.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = lib
+    return _LIB
+
+
+def rows_per_compression(rounds):
+    out = ctypes.c_uint64()
+    rc = load_library().zk_blake2f_rows_per_compression(rounds, ctypes.byref(out))
+    if rc:
+        raise ZkError(rc)
+    return out.value
+
+
+def min_k(rounds, n_compressions):
+    out = ctypes.c_int32()
+    rc = load_library().zk_blake2f_min_k(rounds, n_compressions, ctypes.byref(out))
+    if rc:
+        raise ZkError(rc)
+    return out.value
+
+
+def layout_hash(rounds):
+    a, b, n = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+    rc = load_library().zk_blake2f_layout_hash(rounds, ctypes.byref(a), ctypes.byref(b), ctypes.byref(n))
+    if rc:
+        raise ZkError(rc)
+    return a.value, b.value, n.value
+
+
+def _ptr(x):
+    """Address of a bytes / numpy array / torch tensor / int."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if isinstance(x, (bytes, bytearray)):
+        return ctypes.cast(ctypes.c_char_p(bytes(x)), ctypes.c_void_p).value
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    if hasattr(x, "ctypes"):
+        return x.ctypes.data
+    raise TypeError(type(x))
+
+
+class Context:
+    """`zk_ctx`: one per (host thread, device)."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = ctypes.c_void_p()
+        rc = self.lib.zk_ctx_create(device, ctypes.byref(h))
+        if rc:
+            raise ZkError(rc, "zk_ctx_create failed (no CUDA device? there is no CPU fallback)")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if self.h:
+            self.lib.zk_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            raise ZkError(rc, self.lib.zk_last_error(self.h).decode())
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self.lib.zk_ctx_set_stream(self.h, cuda_stream_ptr))
+
+    def synchronize(self):
+        self._check(self.lib.zk_ctx_synchronize(self.h))
+
+    def launch_count(self):
+        return self.lib.zk_ctx_launch_count(self.h)
+
+    def enable_timing(self, on=True):
+        self._check(self.lib.zk_ctx_enable_timing(self.h, 1 if on else 0))
+
+    def last_kernel_ms(self, which=0):
+        ms = ctypes.c_float()
+        self._check(self.lib.zk_ctx_last_kernel_ms(self.h, which, ctypes.byref(ms)))
+        return ms.value
+
+    def bench_int_pipe(self, mode, iters=20000):
+        out = ctypes.c_double()
+        self._check(self.lib.zk_bench_int_pipe(self.h, mode, iters, ctypes.byref(out)))
+        return out.value
+
+    # ---- K1 ------------------------------------------------------------------------------
+    def witness_batch(self, k, rounds, inputs, n_compressions, advice_out, digests_out=None):
+        """Host buffers in, host buffers out (numpy arrays / pinned torch tensors)."""
+        keep = bytes(inputs) if isinstance(inputs, (bytes, bytearray)) else inputs
+        self._check(self.lib.zk_blake2f_witness_batch(
+            self.h, k, rounds, _ptr(keep), n_compressions, _ptr(advice_out), _ptr(digests_out)))
+
+    def witness_batch_device(self, k, rounds, d_inputs, n_compressions, d_advice, d_digests=None):
+        """Device buffers (torch CUDA tensors or raw device addresses); asynchronous."""
+        self._check(self.lib.zk_blake2f_witness_batch_device(
+            self.h, k, rounds, _ptr(d_inputs), n_compressions, _ptr(d_advice), _ptr(d_digests)))

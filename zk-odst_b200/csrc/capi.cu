@@ -1,0 +1,227 @@
+// extern "C" entry points of include/zkodst.h: context management and the K1 witness path.
+#include <cstring>
+#include <new>
+
+#include "zk_ctx.h"
+
+namespace zkodst {
+
+int32_t set_error(zk_ctx* ctx, int32_t code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+int32_t check_cuda(zk_ctx* ctx, cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return ZK_OK;
+  std::string msg = std::string(what) + ": " + cudaGetErrorString(e);
+  return set_error(ctx, e == cudaErrorMemoryAllocation ? ZK_E_NOMEM : ZK_E_CUDA, msg);
+}
+
+int32_t ensure_buf(zk_ctx* ctx, DevBuf& b, size_t bytes) {
+  if (b.cap >= bytes) return ZK_OK;
+  if (b.ptr) {
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZK_CUDA(ctx, cudaFree(b.ptr));
+    b.ptr = nullptr;
+    b.cap = 0;
+  }
+  ZK_CUDA(ctx, cudaMalloc(&b.ptr, bytes));
+  b.cap = bytes;
+  return ZK_OK;
+}
+
+int32_t get_layout(zk_ctx* ctx, uint32_t rounds, DeviceRegionLayout** out) {
+  auto it = ctx->layouts.find(rounds);
+  if (it == ctx->layouts.end()) {
+    DeviceRegionLayout L;
+    try {
+      build_region_layout(rounds, L.host);
+    } catch (std::exception& e) {
+      return set_error(ctx, ZK_E_INVALID, e.what());
+    }
+    size_t bytes = L.host.desc.size() * sizeof(uint32_t);
+    ZK_CUDA(ctx, cudaMalloc((void**)&L.d_desc, bytes));
+    ZK_CUDA(ctx, cudaMemcpyAsync(L.d_desc, L.host.desc.data(), bytes, cudaMemcpyHostToDevice,
+                                 ctx->stream));
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    it = ctx->layouts.emplace(rounds, std::move(L)).first;
+  }
+  *out = &it->second;
+  return ZK_OK;
+}
+
+}  // namespace zkodst
+
+using namespace zkodst;
+
+extern "C" {
+
+int32_t zk_ctx_create(int32_t device_id, zk_ctx** out) {
+  if (!out) return ZK_E_INVALID;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return ZK_E_CUDA;
+  if (device_id < 0 || device_id >= count) return ZK_E_INVALID;
+  zk_ctx* ctx = new (std::nothrow) zk_ctx();
+  if (!ctx) return ZK_E_NOMEM;
+  ctx->device = device_id;
+  if (cudaSetDevice(device_id) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return ZK_E_CUDA;
+  }
+  ctx->stream = ctx->own_stream;
+  for (auto& e : ctx->ev) cudaEventCreate(&e);
+  cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device_id);
+  if (cudaMalloc((void**)&ctx->d_status, sizeof(int)) != cudaSuccess ||
+      cudaMemset(ctx->d_status, 0, sizeof(int)) != cudaSuccess) {
+    zk_ctx_destroy(ctx);
+    return ZK_E_CUDA;
+  }
+  *out = ctx;
+  return ZK_OK;
+}
+
+void zk_ctx_destroy(zk_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& kv : ctx->layouts) cudaFree(kv.second.d_desc);
+  cudaFree(ctx->scratch_inputs.ptr);
+  cudaFree(ctx->scratch_advice.ptr);
+  cudaFree(ctx->scratch_digests.ptr);
+  cudaFree(ctx->d_status);
+  for (auto& e : ctx->ev)
+    if (e) cudaEventDestroy(e);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+const char* zk_last_error(const zk_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int32_t zk_ctx_set_stream(zk_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return ZK_E_INVALID;
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return ZK_OK;
+}
+
+int32_t zk_ctx_synchronize(zk_ctx* ctx) {
+  if (!ctx) return ZK_E_INVALID;
+  ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+  ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  int st = 0;
+  ZK_CUDA(ctx, cudaMemcpy(&st, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost));
+  if (st) {
+    cudaMemset(ctx->d_status, 0, sizeof(int));
+    return set_error(ctx, ZK_E_INPUT, "a kernel rejected an EIP-152 record (f or rounds)");
+  }
+  return ZK_OK;
+}
+
+uint64_t zk_ctx_launch_count(const zk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int32_t zk_ctx_enable_timing(zk_ctx* ctx, int32_t on) {
+  if (!ctx) return ZK_E_INVALID;
+  ctx->timing = on != 0;
+  return ZK_OK;
+}
+
+int32_t zk_ctx_last_kernel_ms(zk_ctx* ctx, int32_t which, float* ms) {
+  if (!ctx || !ms || which < 0 || which >= KC_COUNT) return ZK_E_INVALID;
+  if (!ctx->ev_valid[which]) return set_error(ctx, ZK_E_STATE, "kernel class not timed yet");
+  ZK_CUDA(ctx, cudaEventSynchronize(ctx->ev[2 * which + 1]));
+  ZK_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev[2 * which], ctx->ev[2 * which + 1]));
+  return ZK_OK;
+}
+
+int32_t zk_blake2f_rows_per_compression(uint32_t rounds, uint64_t* rows) {
+  if (!rows) return ZK_E_INVALID;
+  *rows = region_rows(rounds);
+  return ZK_OK;
+}
+
+int32_t zk_blake2f_min_k(uint32_t rounds, uint64_t n_compressions, int32_t* k) {
+  if (!k) return ZK_E_INVALID;
+  unsigned __int128 need = (unsigned __int128)region_rows(rounds) * n_compressions;
+  for (int kk = 17; kk <= 28; kk++) {
+    if (need <= (((unsigned __int128)1 << kk) - 6)) {
+      *k = kk;
+      return ZK_OK;
+    }
+  }
+  return ZK_E_ROWS;
+}
+
+static uint64_t fnv1a(uint64_t h, const void* data, size_t len) {
+  const uint8_t* p = (const uint8_t*)data;
+  for (size_t i = 0; i < len; i++) {
+    h ^= p[i];
+    h *= 0x100000001b3ULL;
+  }
+  return h;
+}
+
+int32_t zk_blake2f_layout_hash(uint32_t rounds, uint64_t* copies_hash, uint64_t* selectors_hash,
+                               uint64_t* n_copies) {
+  if (!copies_hash || !selectors_hash || !n_copies) return ZK_E_INVALID;
+  RegionLayout L;
+  try {
+    build_region_layout(rounds, L);
+  } catch (std::exception&) {
+    return ZK_E_INVALID;
+  }
+  uint64_t h = 0xcbf29ce484222325ULL;
+  for (auto& c : L.copies) {
+    uint32_t rec[4] = {c.left_col, c.left_row, c.right_col, c.right_row};
+    h = fnv1a(h, rec, sizeof rec);
+  }
+  *copies_hash = h;
+  *selectors_hash = fnv1a(0xcbf29ce484222325ULL, L.selectors.data(), L.selectors.size());
+  *n_copies = L.copies.size();
+  return ZK_OK;
+}
+
+int32_t zk_blake2f_witness_batch_device(zk_ctx* ctx, int32_t k, uint32_t rounds,
+                                        const uint8_t* d_inputs, uint64_t n_compressions,
+                                        void* d_advice, uint64_t* d_digests) {
+  if (!ctx) return ZK_E_INVALID;
+  ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+  return launch_witness(ctx, k, rounds, d_inputs, n_compressions, d_advice, d_digests);
+}
+
+int32_t zk_blake2f_witness_batch(zk_ctx* ctx, int32_t k, uint32_t rounds, const uint8_t* inputs,
+                                 uint64_t n_compressions, void* advice_out, uint64_t* digests_out) {
+  if (!ctx) return ZK_E_INVALID;
+  if (k < 17 || k > 28) return set_error(ctx, ZK_E_INVALID, "k out of range [17, 28]");
+  if (!inputs && n_compressions) return set_error(ctx, ZK_E_INVALID, "null inputs");
+  // EIP-152 rejection cases, checked before any device work
+  for (uint64_t i = 0; i < n_compressions; i++) {
+    const uint8_t* r = inputs + i * ZK_BLAKE2F_INPUT_BYTES;
+    uint32_t rr = ((uint32_t)r[0] << 24) | ((uint32_t)r[1] << 16) | ((uint32_t)r[2] << 8) | r[3];
+    if (r[212] > 1) return set_error(ctx, ZK_E_INPUT, "final-block flag must be 0 or 1");
+    if (rr != rounds) return set_error(ctx, ZK_E_INPUT, "record rounds differ from circuit rounds");
+  }
+  ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+  const uint64_t n = 1ull << k;
+  const size_t advice_bytes = (size_t)ZK_NUM_ADVICE * n * ZK_FIELD_BYTES;
+  int32_t rc;
+  if ((rc = ensure_buf(ctx, ctx->scratch_inputs, n_compressions * ZK_BLAKE2F_INPUT_BYTES + 16))) return rc;
+  if ((rc = ensure_buf(ctx, ctx->scratch_advice, advice_bytes))) return rc;
+  if ((rc = ensure_buf(ctx, ctx->scratch_digests, n_compressions * 64 + 16))) return rc;
+  if (n_compressions)
+    ZK_CUDA(ctx, cudaMemcpyAsync(ctx->scratch_inputs.ptr, inputs,
+                                 n_compressions * ZK_BLAKE2F_INPUT_BYTES, cudaMemcpyHostToDevice,
+                                 ctx->stream));
+  rc = launch_witness(ctx, k, rounds, (const uint8_t*)ctx->scratch_inputs.ptr, n_compressions,
+                      ctx->scratch_advice.ptr, (uint64_t*)ctx->scratch_digests.ptr);
+  if (rc) return rc;
+  if (advice_out)
+    ZK_CUDA(ctx, cudaMemcpyAsync(advice_out, ctx->scratch_advice.ptr, advice_bytes,
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+  if (digests_out && n_compressions)
+    ZK_CUDA(ctx, cudaMemcpyAsync(digests_out, ctx->scratch_digests.ptr, n_compressions * 64,
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+  return zk_ctx_synchronize(ctx);
+}
+
+}  // extern "C"

@@ -1,0 +1,91 @@
+// Integer-pipe micro-benchmark: measured peak of the 32x32-bit multiply-add forms that
+// Montgomery arithmetic is built from.  Its result is the compute roofline for the MSM / NTT
+// kernels ("the builder must add an IMAD micro-benchmark").
+//   mode 0: mad.lo.u32                    (IMAD,      1 result word per instruction)
+//   mode 1: mad.wide.u32                  (IMAD.WIDE, full 64-bit product + 64-bit add)
+//   mode 2: mad.lo.cc.u32 + madc.hi.cc.u32 (carry-chained pair = one 32x32->64 MAC)
+// Reports instructions/s; a "MAC" (32x32->64 multiply-accumulate) is 1 instruction in mode 1
+// and 2 instructions in mode 2.
+#include "zk_ctx.h"
+
+namespace zkodst {
+namespace {
+
+template <int MODE>
+__global__ void __launch_bounds__(256) imad_kernel(uint32_t* out, uint32_t iters, uint32_t seed) {
+  uint32_t a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
+  uint32_t r0 = 1, r1 = 2, r2 = 3, r3 = 4, r4 = 5, r5 = 6, r6 = 7, r7 = 8;
+  uint64_t w0 = 1, w1 = 2, w2 = 3, w3 = 4, w4 = 5, w5 = 6, w6 = 7, w7 = 8;
+  for (uint32_t i = 0; i < iters; i++) {
+    if (MODE == 0) {
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        asm volatile("mad.lo.u32 %0, %8, %9, %0;\n\tmad.lo.u32 %1, %8, %9, %1;\n\t"
+                     "mad.lo.u32 %2, %8, %9, %2;\n\tmad.lo.u32 %3, %8, %9, %3;\n\t"
+                     "mad.lo.u32 %4, %8, %9, %4;\n\tmad.lo.u32 %5, %8, %9, %5;\n\t"
+                     "mad.lo.u32 %6, %8, %9, %6;\n\tmad.lo.u32 %7, %8, %9, %7;"
+                     : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "+r"(r4), "+r"(r5), "+r"(r6), "+r"(r7)
+                     : "r"(a), "r"(b));
+      }
+    } else if (MODE == 1) {
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        asm volatile("mad.wide.u32 %0, %8, %9, %0;\n\tmad.wide.u32 %1, %8, %9, %1;\n\t"
+                     "mad.wide.u32 %2, %8, %9, %2;\n\tmad.wide.u32 %3, %8, %9, %3;\n\t"
+                     "mad.wide.u32 %4, %8, %9, %4;\n\tmad.wide.u32 %5, %8, %9, %5;\n\t"
+                     "mad.wide.u32 %6, %8, %9, %6;\n\tmad.wide.u32 %7, %8, %9, %7;"
+                     : "+l"(w0), "+l"(w1), "+l"(w2), "+l"(w3), "+l"(w4), "+l"(w5), "+l"(w6), "+l"(w7)
+                     : "r"(a), "r"(b));
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        asm volatile("mad.lo.cc.u32 %0, %8, %9, %0;\n\tmadc.hi.cc.u32 %1, %8, %9, %1;\n\t"
+                     "madc.lo.cc.u32 %2, %8, %9, %2;\n\tmadc.hi.cc.u32 %3, %8, %9, %3;\n\t"
+                     "madc.lo.cc.u32 %4, %8, %9, %4;\n\tmadc.hi.cc.u32 %5, %8, %9, %5;\n\t"
+                     "madc.lo.cc.u32 %6, %8, %9, %6;\n\tmadc.hi.u32 %7, %8, %9, %7;"
+                     : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "+r"(r4), "+r"(r5), "+r"(r6), "+r"(r7)
+                     : "r"(a), "r"(b));
+      }
+    }
+  }
+  uint32_t acc = r0 ^ r1 ^ r2 ^ r3 ^ r4 ^ r5 ^ r6 ^ r7;
+  uint64_t wacc = w0 ^ w1 ^ w2 ^ w3 ^ w4 ^ w5 ^ w6 ^ w7;
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc ^ (uint32_t)wacc ^ (uint32_t)(wacc >> 32);
+}
+
+}  // namespace
+}  // namespace zkodst
+
+using namespace zkodst;
+
+extern "C" int32_t zk_bench_int_pipe(zk_ctx* ctx, int32_t mode, uint32_t iters,
+                                     double* instr_per_sec) {
+  if (!ctx || !instr_per_sec || mode < 0 || mode > 2) return ZK_E_INVALID;
+  ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int blocks = ctx->sm_count * 8, threads = 256;
+  int32_t rc = ensure_buf(ctx, ctx->scratch_digests, (size_t)blocks * threads * 4);
+  if (rc) return rc;
+  uint32_t* out = (uint32_t*)ctx->scratch_digests.ptr;
+  cudaEvent_t e0, e1;
+  ZK_CUDA(ctx, cudaEventCreate(&e0));
+  ZK_CUDA(ctx, cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; rep++) {
+    ZK_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+    if (mode == 0) imad_kernel<0><<<blocks, threads, 0, ctx->stream>>>(out, iters, 12345u + rep);
+    if (mode == 1) imad_kernel<1><<<blocks, threads, 0, ctx->stream>>>(out, iters, 12345u + rep);
+    if (mode == 2) imad_kernel<2><<<blocks, threads, 0, ctx->stream>>>(out, iters, 12345u + rep);
+    ctx->launches++;
+    ZK_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+    ZK_CUDA(ctx, cudaEventSynchronize(e1));
+    float ms = 0;
+    ZK_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  double instr = (double)blocks * threads * (double)iters * 64.0;
+  *instr_per_sec = instr / (best * 1e-3);
+  return ZK_OK;
+}

@@ -1,0 +1,258 @@
+// K1 — batched BLAKE2f witness generation.
+//
+// One thread block per compression region.  Phase 1: four lanes run the 12-round G mixing
+// schedule (blake2f-circuit/src/README.md "Function Mix"; SIGMA = table16.rs:32-44, IV =
+// table16.rs:47-56) and record every intermediate word — sums with their carries, XORs with
+// their AND companions — in a shared-memory trace.  Phase 2: all threads walk the region's
+// rows; each cell's descriptor (blake2f_layout.h) selects a bit-piece of a trace word and
+// whether the cell carries its dense value, spread form (table16/util.rs:61-75 `spread_bits`)
+// or range tag (spread_table.rs:213-222 `get_tag`); the value is converted to a
+// Montgomery-form pallas::Base (table16.rs:93-98) and written with 128-bit stores to the
+// column-major advice buffer, consecutive threads writing consecutive rows of a column.
+//
+// Roofline: HBM store-bound.  Algorithmic bytes per compression = R * 12 * 32 written
+// + 213 read; integer work per cell is ~30 ALU ops.
+#include "zk_ctx.h"
+
+namespace zkodst {
+
+namespace {
+
+__constant__ uint8_t c_sigma[10][16] = {
+    {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15},
+    {14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3},
+    {11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4},
+    {7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8},
+    {9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13},
+    {2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9},
+    {12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11},
+    {13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10},
+    {6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5},
+    {10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0}};
+
+__constant__ uint64_t c_iv[8] = {
+    0x6a09e667f3bcc908ULL, 0xbb67ae8584caa73bULL, 0x3c6ef372fe94f82bULL, 0xa54ff53a5f1d36f1ULL,
+    0x510e527fade682d1ULL, 0x9b05688c2b3e6c1fULL, 0x1f83d9abfb41bd6bULL, 0x5be0cd19137e2179ULL};
+
+// pallas::Base modulus p = 2^254 + t
+constexpr uint64_t P0 = 0x992d30ed00000001ULL, P1 = 0x224698fc094cf91bULL, P3 = 0x4000000000000000ULL;
+// 2^256 = 4p - 4t  =>  R = 2^256 mod p = p - 4t, and for 0 < v < 2^64:  v*R mod p = p - 4t*v
+// (4t*v < 2^192 < p).  4t as two 64-bit words:
+constexpr uint64_t C0 = P0 << 2, C1 = (P1 << 2) | (P0 >> 62);
+
+__device__ __forceinline__ uint64_t rotr64(uint64_t x, uint32_t n) {
+  return (x >> (n & 63)) | (x << ((64 - n) & 63));
+}
+
+// interleave_u16_with_zeros (spread_table.rs:729-736 in the commented test) == spread_bits
+__device__ __forceinline__ uint32_t spread16(uint32_t x) {
+  x = (x | (x << 8)) & 0x00ff00ffu;
+  x = (x | (x << 4)) & 0x0f0f0f0fu;
+  x = (x | (x << 2)) & 0x33333333u;
+  x = (x | (x << 1)) & 0x55555555u;
+  return x;
+}
+
+// integer < 2^64 -> Montgomery-form Fp, as two 16-byte halves
+__device__ __forceinline__ void to_montgomery(uint64_t v, uint4& lo, uint4& hi) {
+  if (v == 0) {
+    lo = make_uint4(0, 0, 0, 0);
+    hi = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  // prod = (C1:C0) * v, 192 bits
+  uint64_t m0 = C0 * v, h0 = __umul64hi(C0, v);
+  uint64_t m1 = C1 * v, h1 = __umul64hi(C1, v);
+  uint64_t q0 = m0;
+  uint64_t q1 = h0 + m1;
+  uint64_t q2 = h1 + (q1 < m1 ? 1 : 0);
+  // r = p - prod
+  uint64_t r0 = P0 - q0;
+  uint64_t b0 = P0 < q0;
+  uint64_t r1 = P1 - q1 - b0;
+  uint64_t b1 = (P1 < q1) | ((P1 == q1) & b0);
+  uint64_t r2 = 0 - q2 - b1;
+  uint64_t b2 = (q2 != 0) | b1;
+  uint64_t r3 = P3 - b2;
+  lo = make_uint4((uint32_t)r0, (uint32_t)(r0 >> 32), (uint32_t)r1, (uint32_t)(r1 >> 32));
+  hi = make_uint4((uint32_t)r2, (uint32_t)(r2 >> 32), (uint32_t)r3, (uint32_t)(r3 >> 32));
+}
+
+__device__ __forceinline__ uint64_t eval_cell(uint32_t d, const uint64_t* __restrict__ trace) {
+  uint64_t w = trace[d >> 14];
+  uint32_t rot = (d >> 8) & 63, len = ((d >> 2) & 63) + 1, kind = d & 3;
+  uint64_t x = rotr64(w, rot);
+  if (len < 64) x &= (1ull << len) - 1;
+  if (kind == CK_DENSE) return x;
+  if (kind == CK_SPREAD) return spread16((uint32_t)x);
+  return x < 256 ? 0 : (x < 32768 ? 1 : 2);  // CK_TAG
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+blake2f_witness_kernel(const uint8_t* __restrict__ inputs, uint32_t rounds, uint32_t R,
+                       const uint32_t* __restrict__ desc, uint4* __restrict__ advice, uint64_t n,
+                       uint64_t* __restrict__ digests, uint64_t n_compressions,
+                       const uint32_t digest_word0, int* __restrict__ status) {
+  extern __shared__ uint64_t trace[];  // trace_words
+  __shared__ uint64_t v[16];
+  __shared__ uint8_t rec[216];
+
+  for (uint64_t comp = blockIdx.x; comp < n_compressions; comp += gridDim.x) {
+    // ---- load and parse the 213-byte EIP-152 record ---------------------------------------
+    for (int i = threadIdx.x; i < 213; i += THREADS) rec[i] = inputs[comp * 213 + i];
+    __syncthreads();
+    if (threadIdx.x < 26) {
+      uint64_t w = 0;
+      const uint8_t* p = rec + 4 + 8 * threadIdx.x;
+#pragma unroll
+      for (int b = 0; b < 8; b++) w |= (uint64_t)p[b] << (8 * b);
+      // words 0..7 = h, 8..23 = m, 24,25 = t
+      int dst = threadIdx.x < 8 ? TR_H + threadIdx.x
+                                : (threadIdx.x < 24 ? TR_M + (threadIdx.x - 8)
+                                                    : TR_T0 + (threadIdx.x - 24));
+      trace[dst] = w;
+    } else if (threadIdx.x < 34) {
+      trace[TR_IV + (threadIdx.x - 26)] = c_iv[threadIdx.x - 26];
+    } else if (threadIdx.x == 34) {
+      uint32_t rr = ((uint32_t)rec[0] << 24) | ((uint32_t)rec[1] << 16) | ((uint32_t)rec[2] << 8) |
+                    rec[3];
+      if (rec[212] > 1 || rr != rounds) atomicExch(status, 1);
+      trace[TR_FMASK] = rec[212] == 1 ? ~0ull : 0ull;
+    }
+    __syncthreads();
+
+    // ---- phase 1: the mixing schedule, four lanes = the four independent G of a half-round --
+    if (threadIdx.x < 32) {
+      const int lane = threadIdx.x;
+      if (lane < 16) v[lane] = lane < 8 ? trace[TR_H + lane] : c_iv[lane - 8];
+      __syncwarp();
+      if (lane < 3) {  // v12 ^= t0, v13 ^= t1, v14 ^= fmask   (ops 0..2)
+        uint64_t x = c_iv[4 + lane], y = trace[TR_T0 + lane];
+        trace[TR_OPS + 2 * lane] = x ^ y;
+        trace[TR_OPS + 2 * lane + 1] = x & y;
+        v[12 + lane] = x ^ y;
+      }
+      __syncwarp();
+      for (uint32_t round = 0; round < rounds; round++) {
+        const uint8_t* s = c_sigma[round % 10];
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+          if (lane < 4) {
+            int g = half * 4 + lane;
+            int ia = lane, ib = 4 + ((lane + half) & 3), ic = 8 + ((lane + 2 * half) & 3),
+                id = 12 + ((lane + 3 * half) & 3);
+            uint64_t a = v[ia], b = v[ib], c = v[ic], d = v[id];
+            uint64_t x = trace[TR_M + s[2 * g]], y = trace[TR_M + s[2 * g + 1]];
+            uint64_t* t = trace + TR_OPS + 2 * (3 + (round * 8 + g) * 8);
+            uint64_t s1 = a + b, c1 = s1 < a;
+            uint64_t s2 = s1 + x;
+            c1 += s2 < s1;
+            t[0] = s2; t[1] = c1; a = s2;                        // a1 = a + b + x
+            t[2] = d ^ a; t[3] = d & a; d = rotr64(d ^ a, 32);   // d1
+            s1 = c + d;
+            t[4] = s1; t[5] = s1 < c; c = s1;                    // c1
+            t[6] = b ^ c; t[7] = b & c; b = rotr64(b ^ c, 24);   // b1
+            s1 = a + b; c1 = s1 < a;
+            s2 = s1 + y;
+            c1 += s2 < s1;
+            t[8] = s2; t[9] = c1; a = s2;                        // a2 = a1 + b1 + y
+            t[10] = d ^ a; t[11] = d & a; d = rotr64(d ^ a, 16); // d2
+            s1 = c + d;
+            t[12] = s1; t[13] = s1 < c; c = s1;                  // c2
+            t[14] = b ^ c; t[15] = b & c; b = rotr64(b ^ c, 63); // b2
+            v[ia] = a; v[ib] = b; v[ic] = c; v[id] = d;
+          }
+          __syncwarp();
+        }
+      }
+      if (lane < 8) {  // h'_i = (h_i ^ v_i) ^ v_{i+8}
+        uint64_t* t = trace + TR_OPS + 2 * (3 + rounds * 64 + 2 * lane);
+        uint64_t hh = trace[TR_H + lane], lo = v[lane], hi = v[lane + 8];
+        uint64_t e = hh ^ lo;
+        t[0] = e; t[1] = hh & lo;
+        t[2] = e ^ hi; t[3] = e & hi;
+        if (digests) digests[comp * 8 + lane] = e ^ hi;
+      }
+    }
+    __syncthreads();
+
+    // ---- phase 2: emit the region's cells -------------------------------------------------
+    const uint64_t base = comp * (uint64_t)R;
+    for (uint32_t row = threadIdx.x; row < R; row += THREADS) {
+#pragma unroll
+      for (int c = 0; c < NUM_USED_COLUMNS; c++) {
+        uint32_t d = __ldg(desc + (size_t)c * R + row);
+        uint4 lo, hi;
+        if (d == 0) {
+          lo = make_uint4(0, 0, 0, 0);
+          hi = lo;
+        } else {
+          to_montgomery(eval_cell(d, trace), lo, hi);
+        }
+        uint4* dst = advice + ((uint64_t)c * n + base + row) * 2;
+        dst[0] = lo;
+        dst[1] = hi;
+      }
+#pragma unroll
+      for (int c = NUM_USED_COLUMNS; c < NUM_ADVICE_COLUMNS; c++) {
+        uint4* dst = advice + ((uint64_t)c * n + base + row) * 2;
+        dst[0] = make_uint4(0, 0, 0, 0);
+        dst[1] = make_uint4(0, 0, 0, 0);
+      }
+    }
+    __syncthreads();
+  }
+  (void)digest_word0;
+}
+
+// rows [first_row, n) of every advice column := 0
+__global__ void advice_tail_zero_kernel(uint4* __restrict__ advice, uint64_t n, uint64_t first_row) {
+  uint64_t per_col = (n - first_row) * 2;  // uint4 units
+  uint64_t total = per_col * NUM_ADVICE_COLUMNS;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t c = i / per_col, off = i % per_col;
+    advice[(c * n + first_row) * 2 + off] = make_uint4(0, 0, 0, 0);
+  }
+}
+
+}  // namespace
+
+int32_t launch_witness(zk_ctx* ctx, int32_t k, uint32_t rounds, const uint8_t* d_inputs,
+                       uint64_t n_compressions, void* d_advice, uint64_t* d_digests) {
+  if (k < 17 || k > 28) return set_error(ctx, ZK_E_INVALID, "k out of range [17, 28]");
+  if (!d_advice || (!d_inputs && n_compressions)) return set_error(ctx, ZK_E_INVALID, "null buffer");
+  DeviceRegionLayout* L = nullptr;
+  int32_t rc = get_layout(ctx, rounds, &L);
+  if (rc) return rc;
+  const uint64_t n = 1ull << k, R = L->host.rows;
+  const uint64_t usable = n - 6;  // blinding_factors 5 + 1 (docs/CIRCUIT.md)
+  if (n_compressions * R > usable)
+    return set_error(ctx, ZK_E_ROWS, "compressions do not fit in 2^k rows");
+  const size_t smem = (size_t)L->host.trace_words * 8;
+  constexpr int THREADS = 256;
+  if (smem > 200 * 1024) return set_error(ctx, ZK_E_INVALID, "rounds too large for the trace buffer");
+  if (smem > 48 * 1024)
+    ZK_CUDA(ctx, cudaFuncSetAttribute(blake2f_witness_kernel<THREADS>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (n_compressions) {
+    unsigned grid = (unsigned)(n_compressions < 65535ull * 16 ? n_compressions : 65535ull * 16);
+    KernelTimer timer(ctx, KC_WITNESS);
+    blake2f_witness_kernel<THREADS><<<grid, THREADS, smem, ctx->stream>>>(
+        d_inputs, rounds, (uint32_t)R, L->d_desc, (uint4*)d_advice, n, d_digests, n_compressions,
+        L->host.digest_word[0], ctx->d_status);
+    ctx->launches++;
+  }
+  ZK_CUDA(ctx, cudaGetLastError());
+  {
+    uint64_t first = n_compressions * R;
+    unsigned grid = (unsigned)(ctx->sm_count * 8);
+    advice_tail_zero_kernel<<<grid, 256, 0, ctx->stream>>>((uint4*)d_advice, n, first);
+    ctx->launches++;
+  }
+  ZK_CUDA(ctx, cudaGetLastError());
+  return ZK_OK;
+}
+
+}  // namespace zkodst

@@ -1,0 +1,76 @@
+// Context object behind the opaque `zk_ctx*` of include/zkodst.h.  Product code.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/zkodst.h"
+#include "blake2f_layout.h"
+
+namespace zkodst {
+
+struct DeviceRegionLayout {
+  RegionLayout host;
+  uint32_t* d_desc = nullptr;  // [NUM_USED_COLUMNS][rows]
+};
+
+struct DevBuf {  // grow-only device scratch buffer
+  void* ptr = nullptr;
+  size_t cap = 0;
+};
+
+enum KernelClass { KC_WITNESS = 0, KC_COUNT = 8 };
+
+}  // namespace zkodst
+
+struct zk_ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+  bool timing = false;
+  cudaEvent_t ev[2 * zkodst::KC_COUNT] = {};
+  bool ev_valid[zkodst::KC_COUNT] = {};
+  std::map<uint32_t, zkodst::DeviceRegionLayout> layouts;
+  zkodst::DevBuf scratch_inputs, scratch_advice, scratch_digests;
+  int* d_status = nullptr;  // device-side error flag (bad EIP-152 record seen by a kernel)
+  int sm_count = 148;
+};
+
+namespace zkodst {
+
+int32_t set_error(zk_ctx* ctx, int32_t code, const std::string& msg);
+int32_t check_cuda(zk_ctx* ctx, cudaError_t e, const char* what);
+int32_t ensure_buf(zk_ctx* ctx, DevBuf& b, size_t bytes);
+int32_t get_layout(zk_ctx* ctx, uint32_t rounds, DeviceRegionLayout** out);
+
+struct KernelTimer {  // CUDA-event bracket on the context's stream, only when timing is on
+  zk_ctx* ctx;
+  int which;
+  KernelTimer(zk_ctx* c, int w) : ctx(c), which(w) {
+    if (ctx->timing) cudaEventRecord(ctx->ev[2 * which], ctx->stream);
+  }
+  ~KernelTimer() {
+    if (ctx->timing) {
+      cudaEventRecord(ctx->ev[2 * which + 1], ctx->stream);
+      ctx->ev_valid[which] = true;
+    }
+  }
+};
+
+#define ZK_CUDA(ctx, call)                                        \
+  do {                                                            \
+    int32_t _rc = zkodst::check_cuda((ctx), (call), #call);       \
+    if (_rc) return _rc;                                          \
+  } while (0)
+
+// witness.cu
+int32_t launch_witness(zk_ctx* ctx, int32_t k, uint32_t rounds, const uint8_t* d_inputs,
+                       uint64_t n_compressions, void* d_advice, uint64_t* d_digests);
+
+}  // namespace zkodst
