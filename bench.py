@@ -158,7 +158,8 @@ def main():
     nrows = 1 << k
     inputs = zk.synthetic_inputs(n, stream=rank)  # independent batch per rank (weak scaling)
     ctx = zk.Context(local_rank)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # a real (non-legacy) stream: events and kernels share it
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     ctx.enable_timing(True)
 

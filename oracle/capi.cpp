@@ -9,6 +9,7 @@
 #include "blake2f_circuit.hpp"
 #include "curve.hpp"
 #include "mock_prover.hpp"
+#include "plonk.hpp"
 #include "xorshift.hpp"
 
 using namespace zko;
@@ -257,6 +258,147 @@ int zko_describe_circuit(int k, uint32_t rounds, size_t n_compressions, char* ou
   } catch (std::exception& e) {
     set_msg(out, out_len, e.what());
     return -3;
+  }
+}
+
+
+// ---- params / keygen / prove / verify ----------------------------------------------------------
+struct OracleProver {
+  Params params;
+  ProvingKey pk;
+  bool has_pk = false;
+  ProverTrace trace;
+};
+
+void* zko_prover_new_substitute(int k, const uint8_t seed[16]) {
+  try {
+    auto* p = new OracleProver();
+    p->params = Params::generate_substitute(k, seed);
+    return p;
+  } catch (std::exception& e) {
+    fprintf(stderr, "zko_prover_new_substitute: %s\n", e.what());
+    return nullptr;
+  }
+}
+void* zko_prover_new_from_params(const uint8_t* bytes, size_t len) {
+  try {
+    auto* p = new OracleProver();
+    p->params = Params::read(bytes, len);
+    return p;
+  } catch (std::exception& e) {
+    fprintf(stderr, "zko_prover_new_from_params: %s\n", e.what());
+    return nullptr;
+  }
+}
+void zko_prover_free(void* h) { delete (OracleProver*)h; }
+// halo2 Params::write format; returns the size, writes if out != NULL
+size_t zko_params_write(void* h, uint8_t* out, size_t cap) {
+  auto* p = (OracleProver*)h;
+  size_t need = 4 + (2 * p->params.n + 2) * 32;
+  if (out && cap >= need) {
+    std::vector<uint8_t> v;
+    p->params.write(v);
+    memcpy(out, v.data(), need);
+  }
+  return need;
+}
+// raw affine points (Montgomery x, y; 64 bytes each): which 0 = g, 1 = g_lagrange, 2 = {w, u}
+void zko_params_points(void* h, int which, uint64_t* out) {
+  auto* p = (OracleProver*)h;
+  const std::vector<Affine>* v = which == 0 ? &p->params.g : &p->params.g_lagrange;
+  if (which == 2) {
+    memcpy(out, &p->params.w, 64);
+    memcpy(out + 8, &p->params.u, 64);
+    return;
+  }
+  memcpy(out, v->data(), v->size() * 64);
+}
+int zko_keygen(void* h, uint32_t rounds, size_t n_compressions) {
+  auto* p = (OracleProver*)h;
+  try {
+    keygen(p->params, rounds, n_compressions, p->pk);
+    p->has_pk = true;
+    return 0;
+  } catch (std::exception& e) {
+    fprintf(stderr, "zko_keygen: %s\n", e.what());
+    return -3;
+  }
+}
+// vk pieces for comparison: fixed commitments then permutation commitments (compressed, 32 B each),
+// then transcript_repr (32 B repr).  Returns the number of bytes.
+size_t zko_vk_bytes(void* h, uint8_t* out, size_t cap) {
+  auto* p = (OracleProver*)h;
+  const VerifyingKey& vk = p->pk.vk;
+  size_t need = (vk.fixed_commitments.size() + vk.permutation_commitments.size() + 1) * 32;
+  if (!out || cap < need) return need;
+  size_t off = 0;
+  for (auto& c : vk.fixed_commitments) { c.to_bytes(out + off); off += 32; }
+  for (auto& c : vk.permutation_commitments) { c.to_bytes(out + off); off += 32; }
+  vk.transcript_repr.to_repr(out + off);
+  return need;
+}
+int zko_create_proof(void* h, const uint8_t* inputs213, size_t n_compressions, const uint8_t seed[16],
+                     uint8_t* proof_out, size_t* proof_len) {
+  auto* p = (OracleProver*)h;
+  try {
+    if (!p->has_pk) return -6;
+    uint32_t rounds = p->pk.vk.shape.rounds;
+    if (n_compressions != p->pk.vk.shape.n_compressions) return -1;
+    std::vector<Blake2fInput> in;
+    int rc = parse_inputs(inputs213, n_compressions, in, rounds);
+    if (rc) return rc;
+    Blake2fAssignment as;
+    as.want_shape = false;
+    blake2f_synthesize(as, p->params.k, rounds, in.data(), n_compressions,
+                       p->pk.vk.shape.blinding_factors);
+    XorShiftRng rng(seed);
+    std::vector<uint8_t> proof = create_proof(p->params, p->pk, as.advice, rng, &p->trace);
+    if (*proof_len < proof.size()) {
+      *proof_len = proof.size();
+      return -8;
+    }
+    memcpy(proof_out, proof.data(), proof.size());
+    *proof_len = proof.size();
+    return 0;
+  } catch (std::exception& e) {
+    fprintf(stderr, "zko_create_proof: %s\n", e.what());
+    return -3;
+  }
+}
+int zko_verify_proof(void* h, const uint8_t* proof, size_t len, char* msg, size_t msg_len) {
+  auto* p = (OracleProver*)h;
+  if (!p->has_pk) return -6;
+  std::string why;
+  bool ok = verify_proof(p->params, p->pk.vk, proof, len, &why);
+  set_msg(msg, msg_len, why);
+  return ok ? 0 : 1;
+}
+// MSM / NTT primitives for kernel-level parity tests
+void zko_msm(const uint64_t* scalars_mont, const uint64_t* bases_affine_mont, size_t n,
+             uint64_t out_affine[8]) {
+  Jac r = msm((const Fp*)scalars_mont, (const Affine*)bases_affine_mont, n);
+  Affine a = r.to_affine();
+  memcpy(out_affine, &a, 64);
+}
+// in-place: inverse = 0 -> coeff->lagrange (omega), 1 -> lagrange->coeff (omega^-1, scaled)
+void zko_ntt(uint64_t* data_mont, int log_n, int inverse) {
+  Domain d(2, log_n);
+  Poly a((Fp*)data_mont, (Fp*)data_mont + ((size_t)1 << log_n));
+  a = inverse ? d.lagrange_to_coeff(a) : d.coeff_to_lagrange(a);
+  memcpy(data_mont, a.data(), a.size() * 32);
+}
+// coeffs (n) -> extended coset evaluations (4n for this circuit's degree)
+void zko_coeff_to_extended(const uint64_t* coeffs_mont, int k, int cs_degree, uint64_t* out) {
+  Domain d(cs_degree, k);
+  Poly a((const Fp*)coeffs_mont, (const Fp*)coeffs_mont + d.n);
+  Poly e = d.coeff_to_extended(a);
+  memcpy(out, e.data(), e.size() * 32);
+}
+void zko_random_fields(const uint8_t seed[16], size_t n, uint64_t* out_mont) {
+  XorShiftRng rng(seed);
+  for (size_t i = 0; i < n; i++) {
+    Fp v = rng.random_field<Fp>();
+    memcpy(out_mont + 4 * i, v.l, 32);
   }
 }
 

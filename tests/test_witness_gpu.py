@@ -75,7 +75,9 @@ def test_full_size_properties(ctx, oracle, zk):
     d_in = torch.frombuffer(bytearray(inputs), dtype=torch.uint8).cuda()
     d_adv = torch.empty((12, 1 << k, 4), dtype=torch.int64, device="cuda")
     d_dig = torch.empty((n, 8), dtype=torch.int64, device="cuda")
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    stream = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    ctx.set_stream(stream.cuda_stream)
     ctx.witness_batch_device(k, 12, d_in, n, d_adv, d_dig)
     ctx.synchronize()
     ctx.set_stream(None)

@@ -88,17 +88,56 @@ __device__ __forceinline__ uint64_t eval_cell(uint32_t d, const uint64_t* __rest
   return x < 256 ? 0 : (x < 32768 ? 1 : 2);  // CK_TAG
 }
 
+__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
+  uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src);
+  uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
+  return ((uint64_t)hi << 32) | lo;
+}
+
+// One G (README.md "Function Mix"), recording the 8 primary/secondary trace word pairs.
+__device__ __forceinline__ void mix_g(uint64_t& a, uint64_t& b, uint64_t& c, uint64_t& d,
+                                      uint64_t x, uint64_t y, uint64_t* t, bool write) {
+  uint64_t w[16];
+  uint64_t s1 = a + b, c1 = s1 < a;
+  uint64_t s2 = s1 + x;
+  c1 += s2 < s1;
+  w[0] = s2; w[1] = c1; a = s2;                         // a1 = a + b + x
+  w[2] = d ^ a; w[3] = d & a; d = rotr64(d ^ a, 32);    // d1
+  s1 = c + d;
+  w[4] = s1; w[5] = s1 < c; c = s1;                     // c1
+  w[6] = b ^ c; w[7] = b & c; b = rotr64(b ^ c, 24);    // b1
+  s1 = a + b; c1 = s1 < a;
+  s2 = s1 + y;
+  c1 += s2 < s1;
+  w[8] = s2; w[9] = c1; a = s2;                         // a2 = a1 + b1 + y
+  w[10] = d ^ a; w[11] = d & a; d = rotr64(d ^ a, 16);  // d2
+  s1 = c + d;
+  w[12] = s1; w[13] = s1 < c; c = s1;                   // c2
+  w[14] = b ^ c; w[15] = b & c; b = rotr64(b ^ c, 63);  // b2
+  if (write) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) t[i] = w[i];
+  }
+}
+
+// Grid: n_compressions * slices blocks.  Block (comp, slice) rebuilds the compression's trace
+// (cheap, and it keeps every block independent) and emits rows
+// [slice * rows_per_slice, (slice + 1) * rows_per_slice) of that region.  Lane pairs share a
+// row: lane 2m writes the low 16 bytes of a cell, lane 2m+1 the high 16 bytes, so every
+// 128-bit store instruction covers 512 contiguous bytes of one column.
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 blake2f_witness_kernel(const uint8_t* __restrict__ inputs, uint32_t rounds, uint32_t R,
                        const uint32_t* __restrict__ desc, uint4* __restrict__ advice, uint64_t n,
-                       uint64_t* __restrict__ digests, uint64_t n_compressions,
-                       const uint32_t digest_word0, int* __restrict__ status) {
+                       uint64_t* __restrict__ digests, uint64_t n_compressions, uint32_t slices,
+                       uint32_t rows_per_slice, int* __restrict__ status) {
   extern __shared__ uint64_t trace[];  // trace_words
-  __shared__ uint64_t v[16];
   __shared__ uint8_t rec[216];
 
-  for (uint64_t comp = blockIdx.x; comp < n_compressions; comp += gridDim.x) {
+  const uint64_t total = n_compressions * slices;
+  for (uint64_t blk = blockIdx.x; blk < total; blk += gridDim.x) {
+    const uint64_t comp = blk / slices;
+    const uint32_t slice = (uint32_t)(blk % slices);
     // ---- load and parse the 213-byte EIP-152 record ---------------------------------------
     for (int i = threadIdx.x; i < 213; i += THREADS) rec[i] = inputs[comp * 213 + i];
     __syncthreads();
@@ -122,64 +161,55 @@ blake2f_witness_kernel(const uint8_t* __restrict__ inputs, uint32_t rounds, uint
     }
     __syncthreads();
 
-    // ---- phase 1: the mixing schedule, four lanes = the four independent G of a half-round --
+    // ---- phase 1: the mixing schedule.  Lane l of warp 0 owns column l of the 4x4 state
+    // (a, b, c, d) = (v[l], v[4+l], v[8+l], v[12+l]); the diagonal step rotates b, c, d across
+    // lanes with shuffles.  Four lanes = the four independent G of each half-round.
     if (threadIdx.x < 32) {
-      const int lane = threadIdx.x;
-      if (lane < 16) v[lane] = lane < 8 ? trace[TR_H + lane] : c_iv[lane - 8];
-      __syncwarp();
-      if (lane < 3) {  // v12 ^= t0, v13 ^= t1, v14 ^= fmask   (ops 0..2)
-        uint64_t x = c_iv[4 + lane], y = trace[TR_T0 + lane];
-        trace[TR_OPS + 2 * lane] = x ^ y;
-        trace[TR_OPS + 2 * lane + 1] = x & y;
-        v[12 + lane] = x ^ y;
+      const int lane = threadIdx.x, l = lane & 3;
+      const bool w = lane < 4;
+      uint64_t a = trace[TR_H + l], b = trace[TR_H + 4 + l], c = c_iv[l], d = c_iv[4 + l];
+      {  // v12 ^= t0, v13 ^= t1, v14 ^= fmask   (ops 0..2)
+        uint64_t y = l < 3 ? trace[TR_T0 + l] : 0;
+        if (lane < 3) {
+          trace[TR_OPS + 2 * lane] = d ^ y;
+          trace[TR_OPS + 2 * lane + 1] = d & y;
+        }
+        d ^= y;
       }
-      __syncwarp();
       for (uint32_t round = 0; round < rounds; round++) {
         const uint8_t* s = c_sigma[round % 10];
-#pragma unroll
-        for (int half = 0; half < 2; half++) {
-          if (lane < 4) {
-            int g = half * 4 + lane;
-            int ia = lane, ib = 4 + ((lane + half) & 3), ic = 8 + ((lane + 2 * half) & 3),
-                id = 12 + ((lane + 3 * half) & 3);
-            uint64_t a = v[ia], b = v[ib], c = v[ic], d = v[id];
-            uint64_t x = trace[TR_M + s[2 * g]], y = trace[TR_M + s[2 * g + 1]];
-            uint64_t* t = trace + TR_OPS + 2 * (3 + (round * 8 + g) * 8);
-            uint64_t s1 = a + b, c1 = s1 < a;
-            uint64_t s2 = s1 + x;
-            c1 += s2 < s1;
-            t[0] = s2; t[1] = c1; a = s2;                        // a1 = a + b + x
-            t[2] = d ^ a; t[3] = d & a; d = rotr64(d ^ a, 32);   // d1
-            s1 = c + d;
-            t[4] = s1; t[5] = s1 < c; c = s1;                    // c1
-            t[6] = b ^ c; t[7] = b & c; b = rotr64(b ^ c, 24);   // b1
-            s1 = a + b; c1 = s1 < a;
-            s2 = s1 + y;
-            c1 += s2 < s1;
-            t[8] = s2; t[9] = c1; a = s2;                        // a2 = a1 + b1 + y
-            t[10] = d ^ a; t[11] = d & a; d = rotr64(d ^ a, 16); // d2
-            s1 = c + d;
-            t[12] = s1; t[13] = s1 < c; c = s1;                  // c2
-            t[14] = b ^ c; t[15] = b & c; b = rotr64(b ^ c, 63); // b2
-            v[ia] = a; v[ib] = b; v[ic] = c; v[id] = d;
-          }
-          __syncwarp();
-        }
+        uint64_t* t = trace + TR_OPS + 2 * (3 + (round * 8 + l) * 8);
+        mix_g(a, b, c, d, trace[TR_M + s[2 * l]], trace[TR_M + s[2 * l + 1]], t, w);
+        b = shfl64(b, (lane + 1) & 3);
+        c = shfl64(c, (lane + 2) & 3);
+        d = shfl64(d, (lane + 3) & 3);
+        mix_g(a, b, c, d, trace[TR_M + s[8 + 2 * l]], trace[TR_M + s[8 + 2 * l + 1]], t + 64, w);
+        b = shfl64(b, (lane + 3) & 3);
+        c = shfl64(c, (lane + 2) & 3);
+        d = shfl64(d, (lane + 1) & 3);
       }
-      if (lane < 8) {  // h'_i = (h_i ^ v_i) ^ v_{i+8}
-        uint64_t* t = trace + TR_OPS + 2 * (3 + rounds * 64 + 2 * lane);
-        uint64_t hh = trace[TR_H + lane], lo = v[lane], hi = v[lane + 8];
-        uint64_t e = hh ^ lo;
-        t[0] = e; t[1] = hh & lo;
-        t[2] = e ^ hi; t[3] = e & hi;
-        if (digests) digests[comp * 8 + lane] = e ^ hi;
+      if (w) {  // h'_i = (h_i ^ v_i) ^ v_{i+8} for i = l and i = 4 + l
+        uint64_t* t = trace + TR_OPS + 2 * (3 + rounds * 64);
+        uint64_t h0 = trace[TR_H + l], h1 = trace[TR_H + 4 + l];
+        uint64_t e0 = h0 ^ a, e1 = h1 ^ b;
+        t[4 * l + 0] = e0;      t[4 * l + 1] = h0 & a;
+        t[4 * l + 2] = e0 ^ c;  t[4 * l + 3] = e0 & c;
+        t[4 * (4 + l) + 0] = e1;      t[4 * (4 + l) + 1] = h1 & b;
+        t[4 * (4 + l) + 2] = e1 ^ d;  t[4 * (4 + l) + 3] = e1 & d;
+        if (digests && slice == 0) {
+          digests[comp * 8 + l] = e0 ^ c;
+          digests[comp * 8 + 4 + l] = e1 ^ d;
+        }
       }
     }
     __syncthreads();
 
-    // ---- phase 2: emit the region's cells -------------------------------------------------
+    // ---- phase 2: emit this slice's cells ---------------------------------------------------
     const uint64_t base = comp * (uint64_t)R;
-    for (uint32_t row = threadIdx.x; row < R; row += THREADS) {
+    const uint32_t row_begin = slice * rows_per_slice;
+    const uint32_t row_end = min(R, row_begin + rows_per_slice);
+    const uint32_t half = threadIdx.x & 1;
+    for (uint32_t row = row_begin + (threadIdx.x >> 1); row < row_end; row += THREADS / 2) {
 #pragma unroll
       for (int c = 0; c < NUM_USED_COLUMNS; c++) {
         uint32_t d = __ldg(desc + (size_t)c * R + row);
@@ -190,20 +220,14 @@ blake2f_witness_kernel(const uint8_t* __restrict__ inputs, uint32_t rounds, uint
         } else {
           to_montgomery(eval_cell(d, trace), lo, hi);
         }
-        uint4* dst = advice + ((uint64_t)c * n + base + row) * 2;
-        dst[0] = lo;
-        dst[1] = hi;
+        advice[((uint64_t)c * n + base + row) * 2 + half] = half ? hi : lo;
       }
 #pragma unroll
-      for (int c = NUM_USED_COLUMNS; c < NUM_ADVICE_COLUMNS; c++) {
-        uint4* dst = advice + ((uint64_t)c * n + base + row) * 2;
-        dst[0] = make_uint4(0, 0, 0, 0);
-        dst[1] = make_uint4(0, 0, 0, 0);
-      }
+      for (int c = NUM_USED_COLUMNS; c < NUM_ADVICE_COLUMNS; c++)
+        advice[((uint64_t)c * n + base + row) * 2 + half] = make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
   }
-  (void)digest_word0;
 }
 
 // rows [first_row, n) of every advice column := 0
@@ -237,11 +261,21 @@ int32_t launch_witness(zk_ctx* ctx, int32_t k, uint32_t rounds, const uint8_t* d
     ZK_CUDA(ctx, cudaFuncSetAttribute(blake2f_witness_kernel<THREADS>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (n_compressions) {
-    unsigned grid = (unsigned)(n_compressions < 65535ull * 16 ? n_compressions : 65535ull * 16);
+    // aim for >= 8 resident blocks per SM; a slice is never smaller than 256 rows
+    uint64_t want = (uint64_t)ctx->sm_count * 8;
+    uint32_t slices = (uint32_t)((want + n_compressions - 1) / n_compressions);
+    uint32_t max_slices = (uint32_t)((R + 255) / 256);
+    if (slices > max_slices) slices = max_slices;
+    if (slices < 1) slices = 1;
+    uint32_t rows_per_slice = (uint32_t)((R + slices - 1) / slices);
+    rows_per_slice = (rows_per_slice + 127) / 128 * 128;  // whole passes of the thread block
+    slices = (uint32_t)((R + rows_per_slice - 1) / rows_per_slice);
+    uint64_t total = n_compressions * slices;
+    unsigned grid = (unsigned)(total < (1ull << 22) ? total : (1ull << 22));
     KernelTimer timer(ctx, KC_WITNESS);
     blake2f_witness_kernel<THREADS><<<grid, THREADS, smem, ctx->stream>>>(
         d_inputs, rounds, (uint32_t)R, L->d_desc, (uint4*)d_advice, n, d_digests, n_compressions,
-        L->host.digest_word[0], ctx->d_status);
+        slices, rows_per_slice, ctx->d_status);
     ctx->launches++;
   }
   ZK_CUDA(ctx, cudaGetLastError());
