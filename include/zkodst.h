@@ -103,6 +103,23 @@ int32_t zk_blake2f_witness_batch_device(zk_ctx* ctx, int32_t k, uint32_t rounds,
                                         const uint8_t* d_inputs, uint64_t n_compressions,
                                         void* d_advice, uint64_t* d_digests);
 
+/* ---- K2/K3: multi-scalar multiplication over Vesta --------------------------------------
+ * Replaces halo2_proofs 0.3.0 `best_multiexp` as reached from `Params::commit_lagrange` /
+ * `Params::commit` (blake2f-circuit/benches/blake2f.rs:125 `create_proof`; :85 `Params`).
+ * scalars: n Montgomery-form Fp (32 B each); bases: n affine points (x, y Montgomery Fq,
+ * 64 B each, identity = all zero); out_affine: 64 B.  on_device != 0: both arrays are device
+ * pointers on the context's device. */
+int32_t zk_msm_vesta(zk_ctx* ctx, const void* scalars, const void* bases, uint64_t n,
+                     int32_t on_device, void* out_affine);
+
+/* ---- K4/K5: NTT over Fp -----------------------------------------------------------------
+ * Replaces halo2_proofs 0.3.0 `best_fft` behind `EvaluationDomain::lagrange_to_coeff` /
+ * `coeff_to_lagrange` (reached from `create_proof`, blake2f-circuit/benches/blake2f.rs:125).
+ * data: 2^log_n Montgomery-form Fp, natural order, transformed in place.
+ * inverse = 0: coefficients -> evaluations over <omega_n>; 1: evaluations -> coefficients
+ * (scaled by 1/n).  omega_n = ROOT_OF_UNITY^(2^(32 - log_n)). */
+int32_t zk_ntt_fp(zk_ctx* ctx, void* data, int32_t log_n, int32_t inverse, int32_t on_device);
+
 #ifdef __cplusplus
 }
 #endif

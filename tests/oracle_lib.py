@@ -134,3 +134,99 @@ def load():
                     raise
         _L = Oracle(ctypes.CDLL(path))
     return _L
+
+
+# ---- prover-level helpers (appended) ----------------------------------------------------------
+def _setup_prover_api(lib):
+    c = ctypes
+    vp, sz, u32 = c.c_void_p, c.c_size_t, c.c_uint32
+    lib.zko_prover_new_substitute.restype = vp
+    lib.zko_prover_new_substitute.argtypes = [c.c_int, c.c_char_p]
+    lib.zko_prover_new_from_params.restype = vp
+    lib.zko_prover_new_from_params.argtypes = [c.c_char_p, sz]
+    lib.zko_prover_free.argtypes = [vp]
+    lib.zko_params_write.restype = sz
+    lib.zko_params_write.argtypes = [vp, vp, sz]
+    lib.zko_params_points.argtypes = [vp, c.c_int, vp]
+    lib.zko_keygen.argtypes = [vp, u32, sz]
+    lib.zko_vk_bytes.restype = sz
+    lib.zko_vk_bytes.argtypes = [vp, vp, sz]
+    lib.zko_create_proof.argtypes = [vp, c.c_char_p, sz, c.c_char_p, vp, c.POINTER(sz)]
+    lib.zko_verify_proof.argtypes = [vp, c.c_char_p, sz, c.c_char_p, sz]
+    lib.zko_msm.argtypes = [vp, vp, sz, vp]
+    lib.zko_ntt.argtypes = [vp, c.c_int, c.c_int]
+    lib.zko_coeff_to_extended.argtypes = [vp, c.c_int, c.c_int, vp]
+    lib.zko_random_fields.argtypes = [c.c_char_p, sz, vp]
+
+
+class OracleProver:
+    """Params + keygen + create_proof + verify_proof of the CPU oracle."""
+
+    def __init__(self, oracle, k=None, seed=None, params_bytes=None):
+        self.o = oracle
+        _setup_prover_api(oracle.lib)
+        if params_bytes is not None:
+            self.h = oracle.lib.zko_prover_new_from_params(params_bytes, len(params_bytes))
+        else:
+            self.h = oracle.lib.zko_prover_new_substitute(k, seed)
+        assert self.h
+        self.k = k
+
+    def close(self):
+        if self.h:
+            self.o.lib.zko_prover_free(self.h)
+            self.h = None
+
+    def params_bytes(self):
+        need = self.o.lib.zko_params_write(self.h, None, 0)
+        buf = np.zeros(need, dtype=np.uint8)
+        self.o.lib.zko_params_write(self.h, buf.ctypes.data, need)
+        return buf.tobytes()
+
+    def points(self, which, n):
+        out = np.zeros((2 if which == 2 else n, 8), dtype=np.uint64)
+        self.o.lib.zko_params_points(self.h, which, out.ctypes.data)
+        return out
+
+    def keygen(self, rounds, n_compressions):
+        rc = self.o.lib.zko_keygen(self.h, rounds, n_compressions)
+        assert rc == 0, rc
+
+    def vk_bytes(self):
+        need = self.o.lib.zko_vk_bytes(self.h, None, 0)
+        buf = np.zeros(need, dtype=np.uint8)
+        self.o.lib.zko_vk_bytes(self.h, buf.ctypes.data, need)
+        return buf.tobytes()
+
+    def create_proof(self, inputs, n, seed):
+        buf = np.zeros(1 << 16, dtype=np.uint8)
+        ln = ctypes.c_size_t(buf.size)
+        rc = self.o.lib.zko_create_proof(self.h, inputs, n, seed, buf.ctypes.data, ctypes.byref(ln))
+        assert rc == 0, rc
+        return buf[:ln.value].tobytes()
+
+    def verify(self, proof):
+        msg = ctypes.create_string_buffer(256)
+        rc = self.o.lib.zko_verify_proof(self.h, proof, len(proof), msg, 256)
+        return rc, msg.value.decode()
+
+
+def random_fields(oracle, seed, n):
+    _setup_prover_api(oracle.lib)
+    out = np.zeros((n, 4), dtype=np.uint64)
+    oracle.lib.zko_random_fields(seed, n, out.ctypes.data)
+    return out
+
+
+def msm(oracle, scalars, bases):
+    _setup_prover_api(oracle.lib)
+    out = np.zeros(8, dtype=np.uint64)
+    oracle.lib.zko_msm(scalars.ctypes.data, bases.ctypes.data, len(scalars), out.ctypes.data)
+    return out
+
+
+def ntt(oracle, data, log_n, inverse):
+    _setup_prover_api(oracle.lib)
+    d = np.ascontiguousarray(data).copy()
+    oracle.lib.zko_ntt(d.ctypes.data, log_n, 1 if inverse else 0)
+    return d

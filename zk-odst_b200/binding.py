@@ -45,6 +45,8 @@ def load_library():
             "zk_blake2f_rows_per_compression": (i32, [u32, c.POINTER(u64)]),
             "zk_blake2f_min_k": (i32, [u32, u64, c.POINTER(i32)]),
             "zk_blake2f_layout_hash": (i32, [u32, c.POINTER(u64), c.POINTER(u64), c.POINTER(u64)]),
+            "zk_msm_vesta": (i32, [vp, vp, vp, u64, i32, vp]),
+            "zk_ntt_fp": (i32, [vp, vp, i32, i32, i32]),
             "zk_blake2f_witness_batch": (i32, [vp, i32, u32, vp, u64, vp, vp]),
             "zk_blake2f_witness_batch_device": (i32, [vp, i32, u32, vp, u64, vp, vp]),
         }
@@ -143,6 +145,15 @@ class Context:
         out = ctypes.c_double()
         self._check(self.lib.zk_bench_int_pipe(self.h, mode, iters, ctypes.byref(out)))
         return out.value
+
+    # ---- K2/K3, K4/K5 ------------------------------------------------------------------
+    def msm(self, scalars, bases, n, out_affine, on_device=False):
+        self._check(self.lib.zk_msm_vesta(self.h, _ptr(scalars), _ptr(bases), n,
+                                          1 if on_device else 0, _ptr(out_affine)))
+
+    def ntt(self, data, log_n, inverse=False, on_device=False):
+        self._check(self.lib.zk_ntt_fp(self.h, _ptr(data), log_n, 1 if inverse else 0,
+                                       1 if on_device else 0))
 
     # ---- K1 ------------------------------------------------------------------------------
     def witness_batch(self, k, rounds, inputs, n_compressions, advice_out, digests_out=None):

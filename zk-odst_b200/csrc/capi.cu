@@ -90,6 +90,15 @@ void zk_ctx_destroy(zk_ctx* ctx) {
   cudaFree(ctx->scratch_inputs.ptr);
   cudaFree(ctx->scratch_advice.ptr);
   cudaFree(ctx->scratch_digests.ptr);
+  cudaFree(ctx->scratch_a.ptr);
+  cudaFree(ctx->scratch_b.ptr);
+  cudaFree(ctx->msm_ws.ptr);
+  cudaFree(ctx->msm_out.ptr);
+  cudaFree(ctx->ntt_tmp.ptr);
+  for (auto& kv : ctx->ntt_tables) {
+    cudaFree(kv.second.tw_fwd);
+    cudaFree(kv.second.tw_inv);
+  }
   cudaFree(ctx->d_status);
   for (auto& e : ctx->ev)
     if (e) cudaEventDestroy(e);

@@ -1,0 +1,105 @@
+// Vesta group law (y^2 = x^3 + 5 over Fq) for host and device.  Product code.
+//
+// Replaces pasta_curves 0.5.1 `vesta::{Affine, Point}` as used by `Params<EqAffine>`
+// (blake2f-circuit/benches/blake2f.rs:3,85).  Accumulators use extended Jacobian "XYZZ"
+// coordinates (x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2; EFD shortw/xyzz, a = 0): mixed addition is
+// 8M + 2S, the cheapest form for bucket accumulation.  Only affine results leave the library,
+// so the coordinate system is not observable.
+#pragma once
+#include "field.cuh"
+
+namespace zkodst {
+
+struct Affine {  // 64 bytes; identity = (0, 0) as in pasta_curves
+  Fq x, y;
+  ZK_HD bool is_identity() const { return x.is_zero() && y.is_zero(); }
+  ZK_HD static Affine identity() { return Affine{Fq::zero(), Fq::zero()}; }
+  ZK_HD Affine neg() const { return is_identity() ? *this : Affine{x, y.neg()}; }
+};
+
+struct XYZZ {  // 128 bytes; identity has zz == 0
+  Fq x, y, zz, zzz;
+  ZK_HD static XYZZ identity() { return XYZZ{Fq::zero(), Fq::zero(), Fq::zero(), Fq::zero()}; }
+  ZK_HD bool is_identity() const { return zz.is_zero(); }
+  ZK_HD static XYZZ from_affine(const Affine& p) {
+    if (p.is_identity()) return identity();
+    return XYZZ{p.x, p.y, Fq::one(), Fq::one()};
+  }
+  ZK_HD XYZZ neg() const { return XYZZ{x, y.neg(), zz, zzz}; }
+
+  // 2 * (affine point)                                             [mdbl-2008-s-1]
+  ZK_HD static XYZZ dbl_affine(const Affine& p) {
+    if (p.is_identity()) return identity();
+    Fq u = p.y.dbl();
+    Fq v = u.sqr();
+    Fq w = u * v;
+    Fq s = p.x * v;
+    Fq xx = p.x.sqr();
+    Fq m = xx.dbl() + xx;
+    Fq x3 = m.sqr() - s.dbl();
+    Fq y3 = m * (s - x3) - w * p.y;
+    return XYZZ{x3, y3, v, w};
+  }
+  //                                                                  [dbl-2008-s-1]
+  ZK_HD XYZZ dbl() const {
+    if (is_identity()) return *this;
+    Fq u = y.dbl();
+    Fq v = u.sqr();
+    Fq w = u * v;
+    Fq s = x * v;
+    Fq xx = x.sqr();
+    Fq m = xx.dbl() + xx;
+    Fq x3 = m.sqr() - s.dbl();
+    Fq y3 = m * (s - x3) - w * y;
+    return XYZZ{x3, y3, v * zz, w * zzz};
+  }
+  // this + affine                                                    [madd-2008-s]
+  ZK_HD XYZZ add_affine(const Affine& p) const {
+    if (p.is_identity()) return *this;
+    if (is_identity()) return from_affine(p);
+    Fq u2 = p.x * zz;
+    Fq s2 = p.y * zzz;
+    Fq pp_ = u2 - x;
+    Fq r = s2 - y;
+    if (pp_.is_zero()) {
+      if (r.is_zero()) return dbl_affine(p);
+      return identity();
+    }
+    Fq pp = pp_.sqr();
+    Fq ppp = pp_ * pp;
+    Fq q = x * pp;
+    Fq x3 = r.sqr() - ppp - q.dbl();
+    Fq y3 = r * (q - x3) - y * ppp;
+    return XYZZ{x3, y3, zz * pp, zzz * ppp};
+  }
+  // this + other                                                     [add-2008-s]
+  ZK_HD XYZZ add(const XYZZ& o) const {
+    if (o.is_identity()) return *this;
+    if (is_identity()) return o;
+    Fq u1 = x * o.zz;
+    Fq u2 = o.x * zz;
+    Fq s1 = y * o.zzz;
+    Fq s2 = o.y * zzz;
+    Fq pp_ = u2 - u1;
+    Fq r = s2 - s1;
+    if (pp_.is_zero()) {
+      if (r.is_zero()) return dbl();
+      return identity();
+    }
+    Fq pp = pp_.sqr();
+    Fq ppp = pp_ * pp;
+    Fq q = u1 * pp;
+    Fq x3 = r.sqr() - ppp - q.dbl();
+    Fq y3 = r * (q - x3) - s1 * ppp;
+    return XYZZ{x3, y3, zz * o.zz * pp, zzz * o.zzz * ppp};
+  }
+  // host-side normalisation (one inversion)
+  ZK_HD Affine to_affine() const {
+    if (is_identity()) return Affine::identity();
+    Fq zi = zzz.inv();          // 1 / ZZZ
+    Fq zz_inv = zi.sqr() * zz * zz;  // ZZ^2 / ZZZ^2 = ZZ^2 / ZZ^3 = 1 / ZZ
+    return Affine{x * zz_inv, y * zi};
+  }
+};
+
+}  // namespace zkodst

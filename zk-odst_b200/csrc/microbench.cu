@@ -6,6 +6,7 @@
 //   mode 2: mad.lo.cc.u32 + madc.hi.cc.u32 (carry-chained pair = one 32x32->64 MAC)
 // Reports instructions/s; a "MAC" (32x32->64 multiply-accumulate) is 1 instruction in mode 1
 // and 2 instructions in mode 2.
+#include "ec.cuh"
 #include "zk_ctx.h"
 
 namespace zkodst {
@@ -54,6 +55,30 @@ __global__ void __launch_bounds__(256) imad_kernel(uint32_t* out, uint32_t iters
   out[blockIdx.x * blockDim.x + threadIdx.x] = acc ^ (uint32_t)wacc ^ (uint32_t)(wacc >> 32);
 }
 
+// mode 3: Fq Montgomery multiplications (4 independent chains per thread);
+// mode 4: XYZZ mixed additions (the MSM inner loop)
+__global__ void __launch_bounds__(128) fieldmul_kernel(uint64_t* out, uint32_t iters, uint64_t seed) {
+  Fq a{{seed + threadIdx.x, 2, 3, 4}}, b{{5, seed ^ blockIdx.x, 7, 8}}, c{{9, 10, seed, 12}}, d{{13, 14, 15, 1}};
+  Fq m{{seed | 1, 77, 99, 1234}};
+  for (uint32_t i = 0; i < iters; i++) {
+    a = a * m;
+    b = b * m;
+    c = c * m;
+    d = d * m;
+  }
+  Fq r = a + b + c + d;
+  out[blockIdx.x * blockDim.x + threadIdx.x] = r.l[0] ^ r.l[3];
+}
+__global__ void __launch_bounds__(128) madd_kernel(uint64_t* out, uint32_t iters, uint64_t seed) {
+  Affine p{Fq{{seed + threadIdx.x, 2, 3, 4}}, Fq{{5, seed ^ blockIdx.x, 7, 8}}};
+  XYZZ acc = XYZZ::from_affine(Affine{Fq{{11, 12, 13, 14}}, Fq{{1, 2, 3, 5}}});
+  for (uint32_t i = 0; i < iters; i++) {
+    acc = acc.add_affine(p);
+    p.x.l[0] += i;
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc.x.l[0] ^ acc.zzz.l[3];
+}
+
 }  // namespace
 }  // namespace zkodst
 
@@ -61,10 +86,10 @@ using namespace zkodst;
 
 extern "C" int32_t zk_bench_int_pipe(zk_ctx* ctx, int32_t mode, uint32_t iters,
                                      double* instr_per_sec) {
-  if (!ctx || !instr_per_sec || mode < 0 || mode > 2) return ZK_E_INVALID;
+  if (!ctx || !instr_per_sec || mode < 0 || mode > 4) return ZK_E_INVALID;
   ZK_CUDA(ctx, cudaSetDevice(ctx->device));
-  const int blocks = ctx->sm_count * 8, threads = 256;
-  int32_t rc = ensure_buf(ctx, ctx->scratch_digests, (size_t)blocks * threads * 4);
+  const int blocks = ctx->sm_count * 8, threads = mode >= 3 ? 128 : 256;
+  int32_t rc = ensure_buf(ctx, ctx->scratch_digests, (size_t)blocks * threads * 8);
   if (rc) return rc;
   uint32_t* out = (uint32_t*)ctx->scratch_digests.ptr;
   cudaEvent_t e0, e1;
@@ -76,6 +101,8 @@ extern "C" int32_t zk_bench_int_pipe(zk_ctx* ctx, int32_t mode, uint32_t iters,
     if (mode == 0) imad_kernel<0><<<blocks, threads, 0, ctx->stream>>>(out, iters, 12345u + rep);
     if (mode == 1) imad_kernel<1><<<blocks, threads, 0, ctx->stream>>>(out, iters, 12345u + rep);
     if (mode == 2) imad_kernel<2><<<blocks, threads, 0, ctx->stream>>>(out, iters, 12345u + rep);
+    if (mode == 3) fieldmul_kernel<<<blocks, threads, 0, ctx->stream>>>((uint64_t*)out, iters, 12345u + rep);
+    if (mode == 4) madd_kernel<<<blocks, threads, 0, ctx->stream>>>((uint64_t*)out, iters, 12345u + rep);
     ctx->launches++;
     ZK_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
     ZK_CUDA(ctx, cudaEventSynchronize(e1));
@@ -85,7 +112,8 @@ extern "C" int32_t zk_bench_int_pipe(zk_ctx* ctx, int32_t mode, uint32_t iters,
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
-  double instr = (double)blocks * threads * (double)iters * 64.0;
+  double per_iter = mode == 3 ? 4.0 : (mode == 4 ? 1.0 : 64.0);  // field mults / madds / instructions
+  double instr = (double)blocks * threads * (double)iters * per_iter;
   *instr_per_sec = instr / (best * 1e-3);
   return ZK_OK;
 }

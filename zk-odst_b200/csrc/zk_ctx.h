@@ -10,6 +10,7 @@
 
 #include "../../include/zkodst.h"
 #include "blake2f_layout.h"
+#include "field.cuh"
 
 namespace zkodst {
 
@@ -23,7 +24,14 @@ struct DevBuf {  // grow-only device scratch buffer
   size_t cap = 0;
 };
 
-enum KernelClass { KC_WITNESS = 0, KC_COUNT = 8 };
+struct NttTables {  // per-domain twiddle tables (device) and host constants
+  int log_n = 0;
+  Fp omega, omega_inv, n_inv;
+  Fp* tw_fwd = nullptr;  // omega^i, i < N/2
+  Fp* tw_inv = nullptr;  // omega^-i
+};
+
+enum KernelClass { KC_WITNESS = 0, KC_MSM = 1, KC_NTT = 2, KC_QUOTIENT = 3, KC_COUNT = 8 };
 
 }  // namespace zkodst
 
@@ -38,6 +46,8 @@ struct zk_ctx {
   bool ev_valid[zkodst::KC_COUNT] = {};
   std::map<uint32_t, zkodst::DeviceRegionLayout> layouts;
   zkodst::DevBuf scratch_inputs, scratch_advice, scratch_digests;
+  zkodst::DevBuf scratch_a, scratch_b, msm_ws, msm_out, ntt_tmp;
+  std::map<int, zkodst::NttTables> ntt_tables;
   int* d_status = nullptr;  // device-side error flag (bad EIP-152 record seen by a kernel)
   int sm_count = 148;
 };
