@@ -120,6 +120,34 @@ int32_t zk_msm_vesta(zk_ctx* ctx, const void* scalars, const void* bases, uint64
  * (scaled by 1/n).  omega_n = ROOT_OF_UNITY^(2^(32 - log_n)). */
 int32_t zk_ntt_fp(zk_ctx* ctx, void* data, int32_t log_n, int32_t inverse, int32_t on_device);
 
+/* ---- params, keys, proofs ---------------------------------------------------------------
+ * Replace the reference's prove sequence (blake2f-circuit/benches/blake2f.rs:83-142):
+ *   Params::<EqAffine>::new / read / write  ->  zk_params_generate_substitute / _load / _write
+ *   keygen_vk + keygen_pk                    ->  zk_blake2f_keygen
+ *   create_proof(.., rng, &mut transcript); transcript.finalize()  ->  zk_create_proof
+ * All state lives inside the context (device memory); one params set and one key set at a time. */
+
+/* Substitute URS with known discrete logs (benchmark / parity use only; Params::new's
+ * hash-to-curve cannot be reproduced offline): g_i = [s_i] G with s_i from XorShiftRng(seed). */
+int32_t zk_params_generate_substitute(zk_ctx* ctx, int32_t k, const uint8_t seed[16]);
+/* halo2 params file format (Params::write): k u32 LE | n x g | n x g_lagrange | w | u, 32 B
+ * compressed points. */
+int32_t zk_params_load(zk_ctx* ctx, const uint8_t* bytes, uint64_t len);
+int32_t zk_params_write(zk_ctx* ctx, uint8_t* out, uint64_t* len);
+/* Keys for a circuit of n_compressions regions of `rounds` rounds at the params' k. */
+int32_t zk_blake2f_keygen(zk_ctx* ctx, uint32_t rounds, uint64_t n_compressions);
+/* 10 fixed + 8 permutation commitments (32 B compressed each) followed by vk.transcript_repr. */
+int32_t zk_vk_bytes(zk_ctx* ctx, uint8_t* out, uint64_t* len);
+/* Inject a genuine halo2 `vk.transcript_repr` (32 B canonical LE) in place of the substitute
+ * hash (the Rust `{:?}` rendering of vk.pinned() is not reproducible here). */
+int32_t zk_vk_repr_override(zk_ctx* ctx, const uint8_t repr[32]);
+/* inputs: n_compressions x 213 B (host).  seed: 16-byte XorShiftRng seed (the reference harness
+ * seeds its prover RNG the same way, benchmarking/src/blake2f_circuit_bench.rs:41-44).
+ * proof_out / proof_len: caller buffer and its capacity; the proof length is written back
+ * (ZK_E_BUFFER if too small). */
+int32_t zk_create_proof(zk_ctx* ctx, const uint8_t* inputs, uint64_t n_compressions,
+                        const uint8_t seed[16], uint8_t* proof_out, uint64_t* proof_len);
+
 #ifdef __cplusplus
 }
 #endif

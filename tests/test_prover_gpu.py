@@ -1,0 +1,82 @@
+"""Full proving path through the C ABI vs the oracle: params, keys and proof bytes bit-exact;
+the oracle verifier accepts GPU proofs and rejects tampered ones."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+VECS = json.load(open(os.path.join(G, "eip152.json")))
+
+
+def first_diff(a, b):
+    n = min(len(a), len(b))
+    for i in range(0, n, 32):
+        if a[i:i + 32] != b[i:i + 32]:
+            return i // 32
+    return None if len(a) == len(b) else n // 32
+
+
+@pytest.fixture(scope="module")
+def setup17(ctx, oracle, zk):
+    seed = zk.REFERENCE_SEED
+    ctx.params_generate_substitute(17, seed)
+    op = oracle_lib.OracleProver(oracle, k=17, seed=seed)
+    yield ctx, op, seed
+    op.close()
+
+
+def test_params_match_oracle_and_roundtrip(setup17):
+    ctx, op, _ = setup17
+    mine = ctx.params_write()
+    ref = op.params_bytes()
+    assert len(mine) == len(ref)
+    assert first_diff(mine[4:], ref[4:]) is None and mine[:4] == ref[:4]
+    # halo2 params format round trip through the loader (point decompression on the device)
+    ctx.params_load(ref)
+    assert ctx.params_write() == ref
+
+
+def test_keygen_matches_oracle(setup17):
+    ctx, op, _ = setup17
+    ctx.keygen(12, 2)
+    op.keygen(12, 2)
+    mine, ref = ctx.vk_bytes(), op.vk_bytes()
+    assert first_diff(mine, ref) is None, "vk chunk %s differs" % first_diff(mine, ref)
+
+
+def test_proof_bytes_match_oracle(setup17, zk):
+    ctx, op, seed = setup17
+    inputs = zk.synthetic_inputs(2)
+    ctx.keygen(12, 2)
+    op.keygen(12, 2)
+    proof = ctx.create_proof(inputs, 2, seed)
+    ref = op.create_proof(inputs, 2, seed)
+    assert len(proof) == len(ref) == 4000
+    assert first_diff(proof, ref) is None, "proof chunk %s differs" % first_diff(proof, ref)
+    rc, msg = op.verify(proof)
+    assert rc == 0, msg
+    bad = bytearray(proof)
+    bad[1000] ^= 1
+    assert op.verify(bytes(bad))[0] != 0
+    # a different prover seed gives a different, still valid proof
+    other = ctx.create_proof(inputs, 2, bytes(range(16)))
+    assert other != proof and op.verify(other)[0] == 0
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2, 3])
+def test_eip152_sweep_proofs(setup17, idx):
+    """Config 2: rounds 0 / 12 / 12 (f = false) / 1, one compression each, proof bytes equal."""
+    ctx, op, seed = setup17
+    rec = bytes.fromhex(VECS[idx]["input"])
+    rounds = int.from_bytes(rec[:4], "big")
+    ctx.keygen(rounds, 1)
+    op.keygen(rounds, 1)
+    proof = ctx.create_proof(rec, 1, seed)
+    ref = op.create_proof(rec, 1, seed)
+    assert first_diff(proof, ref) is None, "proof chunk %s differs" % first_diff(proof, ref)
+    assert op.verify(proof)[0] == 0

@@ -45,6 +45,13 @@ def load_library():
             "zk_blake2f_rows_per_compression": (i32, [u32, c.POINTER(u64)]),
             "zk_blake2f_min_k": (i32, [u32, u64, c.POINTER(i32)]),
             "zk_blake2f_layout_hash": (i32, [u32, c.POINTER(u64), c.POINTER(u64), c.POINTER(u64)]),
+            "zk_params_generate_substitute": (i32, [vp, i32, c.c_char_p]),
+            "zk_params_load": (i32, [vp, vp, u64]),
+            "zk_params_write": (i32, [vp, vp, c.POINTER(u64)]),
+            "zk_blake2f_keygen": (i32, [vp, u32, u64]),
+            "zk_vk_bytes": (i32, [vp, vp, c.POINTER(u64)]),
+            "zk_vk_repr_override": (i32, [vp, c.c_char_p]),
+            "zk_create_proof": (i32, [vp, vp, u64, c.c_char_p, vp, c.POINTER(u64)]),
             "zk_msm_vesta": (i32, [vp, vp, vp, u64, i32, vp]),
             "zk_ntt_fp": (i32, [vp, vp, i32, i32, i32]),
             "zk_blake2f_witness_batch": (i32, [vp, i32, u32, vp, u64, vp, vp]),
@@ -145,6 +152,39 @@ class Context:
         out = ctypes.c_double()
         self._check(self.lib.zk_bench_int_pipe(self.h, mode, iters, ctypes.byref(out)))
         return out.value
+
+    # ---- params / keygen / prove ---------------------------------------------------------
+    def params_generate_substitute(self, k, seed):
+        self._check(self.lib.zk_params_generate_substitute(self.h, k, bytes(seed)))
+
+    def params_load(self, data):
+        keep = bytes(data)
+        self._check(self.lib.zk_params_load(self.h, _ptr(keep), len(keep)))
+
+    def params_write(self):
+        ln = ctypes.c_uint64(0)
+        self.lib.zk_params_write(self.h, None, ctypes.byref(ln))
+        buf = ctypes.create_string_buffer(ln.value)
+        self._check(self.lib.zk_params_write(self.h, ctypes.cast(buf, ctypes.c_void_p), ctypes.byref(ln)))
+        return buf.raw[:ln.value]
+
+    def keygen(self, rounds, n_compressions):
+        self._check(self.lib.zk_blake2f_keygen(self.h, rounds, n_compressions))
+
+    def vk_bytes(self):
+        ln = ctypes.c_uint64(0)
+        self.lib.zk_vk_bytes(self.h, None, ctypes.byref(ln))
+        buf = ctypes.create_string_buffer(ln.value)
+        self._check(self.lib.zk_vk_bytes(self.h, ctypes.cast(buf, ctypes.c_void_p), ctypes.byref(ln)))
+        return buf.raw[:ln.value]
+
+    def create_proof(self, inputs, n_compressions, seed):
+        keep = bytes(inputs) if isinstance(inputs, (bytes, bytearray)) else inputs
+        buf = ctypes.create_string_buffer(1 << 16)
+        ln = ctypes.c_uint64(len(buf))
+        self._check(self.lib.zk_create_proof(self.h, _ptr(keep), n_compressions, bytes(seed),
+                                             ctypes.cast(buf, ctypes.c_void_p), ctypes.byref(ln)))
+        return buf.raw[:ln.value]
 
     # ---- K2/K3, K4/K5 ------------------------------------------------------------------
     def msm(self, scalars, bases, n, out_affine, on_device=False):

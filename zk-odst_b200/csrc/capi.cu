@@ -95,6 +95,10 @@ void zk_ctx_destroy(zk_ctx* ctx) {
   cudaFree(ctx->msm_ws.ptr);
   cudaFree(ctx->msm_out.ptr);
   cudaFree(ctx->ntt_tmp.ptr);
+  cudaFree(ctx->scan_ws.ptr);
+  cudaFree(ctx->eval_ws.ptr);
+  cudaFree(ctx->misc_ws.ptr);
+  if (ctx->prover_state && ctx->prover_state_free) ctx->prover_state_free(ctx->prover_state);
   for (auto& kv : ctx->ntt_tables) {
     cudaFree(kv.second.tw_fwd);
     cudaFree(kv.second.tw_inv);

@@ -35,12 +35,18 @@ struct HeavyItem {
 };
 
 // -------- step 1: digits + histogram ---------------------------------------------------------
-__global__ void msm_digits_kernel(const Fp* __restrict__ scalars, uint32_t n, int c, int nwin,
-                                  int32_t* __restrict__ digits, uint32_t* __restrict__ counts) {
+// `extra` (optional) supplies one more scalar, logically scalars[n - 1], so that a commitment's
+// blinding term [r] W rides in the same MSM (the bases array carries W after the n - 1 points).
+__global__ void msm_digits_kernel(const Fp* __restrict__ scalars, const Fp* __restrict__ extra, uint32_t n,
+                                  int c, int nwin, int32_t* __restrict__ digits,
+                                  uint32_t* __restrict__ counts) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint64_t s[4];
-  scalars[i].to_canonical(s);
+  if (extra && i == n - 1)
+    extra->to_canonical(s);
+  else
+    scalars[i].to_canonical(s);
   const uint32_t B = 1u << (c - 1);
   uint32_t carry = 0;
   for (int w = 0; w < nwin; w++) {
@@ -271,7 +277,7 @@ int msm_window_bits(uint64_t n) {
 }
 
 // Runs the device part of an MSM; writes nwin window sums (XYZZ) to d_window_sums.
-int32_t msm_device(zk_ctx* ctx, const Fp* d_scalars, const Affine* d_bases, uint64_t n64, int c,
+int32_t msm_device(zk_ctx* ctx, const Fp* d_scalars, const Fp* d_extra, const Affine* d_bases, uint64_t n64, int c,
                    int* nwin_out, XYZZ* d_window_sums) {
   const uint32_t n = (uint32_t)n64;
   const int nwin = (255 + c - 1) / c + ((255 % c) == 0 ? 1 : 0);
@@ -316,7 +322,7 @@ int32_t msm_device(zk_ctx* ctx, const Fp* d_scalars, const Affine* d_bases, uint
   ZK_CUDA(ctx, cudaMemsetAsync(hcount, 0, 16, st));
   KernelTimer timer(ctx, KC_MSM);
   const int T = 256;
-  msm_digits_kernel<<<(n + T - 1) / T, T, 0, st>>>(d_scalars, n, c, nwin, digits, counts);
+  msm_digits_kernel<<<(n + T - 1) / T, T, 0, st>>>(d_scalars, d_extra, n, c, nwin, digits, counts);
   scan_tiles_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(counts, offsets, tiles, nbuckets);
   scan_sums_kernel<<<1, 1024, 0, st>>>(tiles, ntiles);
   scan_add_kernel<<<(nbuckets + T - 1) / T, T, 0, st>>>(offsets, tiles, nbuckets);
@@ -357,7 +363,9 @@ int32_t msm_device(zk_ctx* ctx, const Fp* d_scalars, const Affine* d_bases, uint
 }
 
 // Full MSM: device pipeline + host Horner over the window sums.
-int32_t msm_run(zk_ctx* ctx, const Fp* d_scalars, const Affine* d_bases, uint64_t n, XYZZ* result) {
+// n counts the extra scalar when d_extra != nullptr (bases has n entries either way).
+int32_t msm_run(zk_ctx* ctx, const Fp* d_scalars, const Affine* d_bases, uint64_t n, XYZZ* result,
+                const Fp* d_extra) {
   if (n == 0) {
     *result = XYZZ::identity();
     return ZK_OK;
@@ -365,9 +373,9 @@ int32_t msm_run(zk_ctx* ctx, const Fp* d_scalars, const Affine* d_bases, uint64_
   if (n > 0x7fffffffull) return set_error(ctx, ZK_E_INVALID, "msm: n too large");
   const int c = msm_window_bits(n);
   int nwin = 0;
-  int32_t rc = ensure_buf(ctx, ctx->msm_out, 32 * sizeof(XYZZ));
+  int32_t rc = ensure_buf(ctx, ctx->msm_out, 64 * sizeof(XYZZ));
   if (rc) return rc;
-  rc = msm_device(ctx, d_scalars, d_bases, n, c, &nwin, (XYZZ*)ctx->msm_out.ptr);
+  rc = msm_device(ctx, d_scalars, d_extra, d_bases, n, c, &nwin, (XYZZ*)ctx->msm_out.ptr);
   if (rc) return rc;
   XYZZ sums[48];
   ZK_CUDA(ctx, cudaMemcpyAsync(sums, ctx->msm_out.ptr, (size_t)nwin * sizeof(XYZZ),
@@ -403,7 +411,7 @@ extern "C" int32_t zk_msm_vesta(zk_ctx* ctx, const void* scalars, const void* ba
     d_b = (const Affine*)ctx->scratch_b.ptr;
   }
   XYZZ r;
-  int32_t rc = msm_run(ctx, d_s, d_b, n, &r);
+  int32_t rc = msm_run(ctx, d_s, d_b, n, &r, nullptr);
   if (rc) return rc;
   Affine a = r.to_affine();
   memcpy(out_affine, &a, sizeof a);

@@ -1,0 +1,819 @@
+// create_proof on the device.
+//
+// Replaces halo2_proofs 0.3.0 `plonk::create_proof` (Pasta / IPA) as the reference calls it:
+//   create_proof(&params, &pk, &[circuit], &[&[]], rng, &mut Blake2bWrite<_, _, Challenge255<_>>)
+// (blake2f-circuit/benches/blake2f.rs:124-127).  The host keeps only the byte-serial parts —
+// the BLAKE2b transcript, challenge derivation and the seeded RNG stream — and drives kernels
+// for everything else: witness (K1), commitments (K2/K3), NTTs (K4/K5), lookup permutation
+// (K7), grand products (K8), the quotient (K6), evaluations (K9), multiopen (K10) and the inner
+// product argument (K11).  The order of transcript writes, challenge squeezes and RNG draws is
+// halo2's; proof bytes are compared with the CPU oracle byte for byte in tests/.
+#include <atomic>
+#include <thread>
+
+#include "polyops.cuh"
+#include "prover_state.h"
+#include "quotient.h"
+#include "transcript.h"
+
+namespace zkodst {
+
+// ---- device buffers of one proof ---------------------------------------------------------------------
+struct ProofWorkspace {
+  uint64_t n = 0, en = 0;
+  uint8_t* inputs = nullptr;
+  uint64_t* digests = nullptr;
+  Fp* advice_values = nullptr;  // [12][n]
+  Fp* advice_polys = nullptr;   // [12][n]
+  Fp* advice_cosets = nullptr;  // [12][en]
+  Fp *cin = nullptr, *ctab = nullptr, *pin = nullptr, *ptab = nullptr;  // lookup, n each
+  Fp *pin_poly = nullptr, *ptab_poly = nullptr, *zl_poly = nullptr;
+  Fp *pin_coset = nullptr, *ptab_coset = nullptr, *zl_coset = nullptr;
+  Fp* z_poly[NUM_SETS] = {};
+  Fp* z_coset[NUM_SETS] = {};
+  Fp *tmp_a = nullptr, *tmp_b = nullptr, *tmp_c = nullptr;  // n each
+  Fp *h = nullptr, *h_coeffs = nullptr;                      // en each
+  Fp *random_poly = nullptr, *s_poly = nullptr, *q_prime = nullptr, *p_poly = nullptr, *b_vec = nullptr;
+  Fp* q_polys[8] = {};
+  Fp* h_poly = nullptr;
+  Affine* g_fold = nullptr;  // n
+  uint64_t* raw = nullptr;   // n * 8 words of RNG output
+  // lookup permutation tables
+  Fp* table_vals = nullptr;      // 65536 compressed table values
+  Fp* table_sorted = nullptr;    // ascending
+  uint32_t* rank_of = nullptr;   // dense index -> rank
+  uint32_t* counts = nullptr;    // per rank: number of input rows
+  uint32_t* offsets = nullptr;   // exclusive scan of counts
+  uint32_t* left_cnt = nullptr;  // per rank: leftover table multiplicity
+  uint32_t* left_off = nullptr;  // exclusive scan of left_cnt
+  uint32_t* first_flag_scan = nullptr;  // n: number of first-occurrence positions before p
+  uint32_t* left_rank = nullptr;        // n: leftover list (rank per entry), ascending
+  std::vector<void*> all;
+};
+
+void free_workspace(void* p) {
+  ProofWorkspace* W = (ProofWorkspace*)p;
+  for (void* q : W->all) cudaFree(q);
+  delete W;
+}
+
+namespace {
+
+template <class T>
+int32_t dalloc(zk_ctx* ctx, ProofWorkspace* W, T** p, size_t count) {
+  ZK_CUDA(ctx, cudaMalloc((void**)p, count * sizeof(T)));
+  W->all.push_back(*p);
+  return ZK_OK;
+}
+
+int32_t get_workspace(zk_ctx* ctx, DeviceKeys& K, ProofWorkspace** out) {
+  if (!K.workspace) {
+    ProofWorkspace* W = new ProofWorkspace();
+    K.workspace = W;
+    const uint64_t n = K.n, en = K.en;
+    W->n = n;
+    W->en = en;
+    int32_t rc = 0;
+#define A(p, cnt) if ((rc = dalloc(ctx, W, &W->p, (cnt)))) return rc
+    A(inputs, K.n_compressions * 213 + 16);
+    A(digests, K.n_compressions * 8 + 8);
+    A(advice_values, 12 * n);
+    A(advice_polys, 12 * n);
+    A(advice_cosets, 12 * en);
+    A(cin, n); A(ctab, n); A(pin, n); A(ptab, n);
+    A(pin_poly, n); A(ptab_poly, n); A(zl_poly, n);
+    A(pin_coset, en); A(ptab_coset, en); A(zl_coset, en);
+    for (int s = 0; s < NUM_SETS; s++) {
+      A(z_poly[s], n);
+      A(z_coset[s], en);
+    }
+    A(tmp_a, n); A(tmp_b, n); A(tmp_c, n);
+    A(h, en); A(h_coeffs, en);
+    A(random_poly, n); A(s_poly, n); A(q_prime, n); A(p_poly, n); A(b_vec, n); A(h_poly, n);
+    for (int s = 0; s < 8; s++) A(q_polys[s], n);
+    A(g_fold, n);
+    A(raw, n * 8);
+    A(table_vals, 65536); A(table_sorted, 65536);
+    A(rank_of, 65536); A(counts, 65536 + 8); A(offsets, 65536 + 8); A(left_cnt, 65536 + 8); A(left_off, 65536 + 8);
+    A(first_flag_scan, n + 8); A(left_rank, n + 8);
+#undef A
+  }
+  *out = (ProofWorkspace*)K.workspace;
+  return ZK_OK;
+}
+
+// ---- RNG tape: the whole XorShift stream of one proof, produced by a worker thread -----------------
+class RandomTape {
+ public:
+  RandomTape(const uint8_t seed[16], size_t total_fields) : words_(total_fields * 8), ready_(0), pos_(0) {
+    memcpy(seed_, seed, 16);
+    worker_ = std::thread([this] {
+      XorShift rng(seed_);
+      const size_t total = words_.size();
+      for (size_t i = 0; i < total; i += 8) {
+        rng.next_wide(&words_[i]);
+        if ((i & 0xfff8) == 0xfff8 || i + 8 >= total) ready_.store(i + 8, std::memory_order_release);
+      }
+    });
+  }
+  ~RandomTape() {
+    if (worker_.joinable()) worker_.join();
+  }
+  // raw words of the next `count` field elements
+  const uint64_t* take(size_t count) {
+    size_t need = (pos_ + count) * 8;
+    if (need > words_.size()) throw std::runtime_error("RNG tape exhausted");
+    while (ready_.load(std::memory_order_acquire) < need) std::this_thread::yield();
+    const uint64_t* p = &words_[pos_ * 8];
+    pos_ += count;
+    return p;
+  }
+  Fp next() { return Fp::from_u512(take(1)); }
+
+ private:
+  std::vector<uint64_t> words_;
+  std::atomic<size_t> ready_;
+  size_t pos_;
+  uint8_t seed_[16];
+  std::thread worker_;
+};
+
+__global__ void from_u512_kernel2(const uint64_t* __restrict__ raw, uint64_t n, Fp* __restrict__ out) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t w[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) w[j] = raw[8 * i + j];
+  out[i] = Fp::from_u512(w);
+}
+
+// n random field elements from the tape -> device
+int32_t random_poly_to_device(zk_ctx* ctx, ProofWorkspace* W, RandomTape& tape, uint64_t n, Fp* out) {
+  const uint64_t* raw = tape.take(n);
+  ZK_CUDA(ctx, cudaMemcpyAsync(W->raw, raw, n * 64, cudaMemcpyHostToDevice, ctx->stream));
+  from_u512_kernel2<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(W->raw, n, out);
+  ctx->launches++;
+  ZK_CUDA(ctx, cudaGetLastError());
+  return ZK_OK;
+}
+
+int32_t upload_fp(zk_ctx* ctx, Fp* dst, const Fp* src, size_t count) {
+  ZK_CUDA(ctx, cudaMemcpyAsync(dst, src, count * sizeof(Fp), cudaMemcpyHostToDevice, ctx->stream));
+  return ZK_OK;
+}
+
+// ---- lookup argument helpers (A.5 permute_expression_pair, specialised to this circuit) ------------
+// The lookup inputs are (tag, dense, spread) triples; a valid row equals table row `dense`, so the
+// theta-compressed input of a row is table_vals[dense].  Sorting the inputs therefore reduces to a
+// counting sort on the rank of that table value, and the permuted table follows from per-rank
+// multiplicities.  Rows whose triple is not a table row raise the error flag
+// (halo2: Error::ConstraintSystemFailure).
+__global__ void lookup_compress_kernel(const Fp* __restrict__ c0, const Fp* __restrict__ c1,
+                                       const Fp* __restrict__ c2, Fp theta, uint64_t n, Fp* __restrict__ out) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (c0[i] * theta + c1[i]) * theta + c2[i];
+}
+__global__ void lookup_count_kernel(const Fp* __restrict__ dense_col, const Fp* __restrict__ cin,
+                                    const Fp* __restrict__ table_vals, const uint32_t* __restrict__ rank_of,
+                                    uint64_t usable, uint32_t* __restrict__ counts, int* __restrict__ status) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= usable) return;
+  uint64_t d[4];
+  dense_col[i].to_canonical(d);
+  if ((d[1] | d[2] | d[3]) || d[0] >= 65536 || cin[i] != table_vals[d[0]]) {
+    atomicExch(status, 2);
+    return;
+  }
+  atomicAdd(&counts[rank_of[d[0]]], 1u);
+}
+// per rank: leftover multiplicity = table multiplicity - [rank used by an input]
+__global__ void lookup_leftover_kernel(const uint32_t* __restrict__ counts, uint32_t zero_rank,
+                                       uint32_t zero_mult, uint32_t* __restrict__ left_cnt) {
+  uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= 65536) return;
+  uint32_t mult = r == zero_rank ? zero_mult : 1;
+  left_cnt[r] = mult - (counts[r] ? 1 : 0);
+}
+// permuted input: run of counts[r] copies of table_sorted[r]; first flags for the table pass
+__global__ void lookup_fill_input_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
+                                         const Fp* __restrict__ table_sorted, Fp* __restrict__ pin,
+                                         uint32_t* __restrict__ first_flag) {
+  uint32_t r = blockIdx.x;
+  uint32_t cnt = counts[r], off = offsets[r];
+  Fp v = table_sorted[r];
+  for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) {
+    pin[off + j] = v;
+    first_flag[off + j] = j == 0 ? 1 : 0;
+  }
+}
+// leftover list: rank r occupies [left_off[r], left_off[r] + left_cnt[r])
+__global__ void lookup_fill_leftover_kernel(const uint32_t* __restrict__ left_cnt,
+                                            const uint32_t* __restrict__ left_off,
+                                            uint32_t* __restrict__ left_rank) {
+  uint32_t r = blockIdx.x;
+  uint32_t cnt = left_cnt[r], off = left_off[r];
+  for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) left_rank[off + j] = r;
+}
+// permuted table: first occurrences take the input value; the m-th repeated row (ascending)
+// takes leftover[total - 1 - m]  (BTreeMap ascending order popped onto the highest rows first)
+__global__ void lookup_fill_table_kernel(const Fp* __restrict__ pin, const uint32_t* __restrict__ first_flag,
+                                         const uint32_t* __restrict__ first_scan,
+                                         const uint32_t* __restrict__ left_rank,
+                                         const Fp* __restrict__ table_sorted, uint64_t usable,
+                                         uint32_t n_repeated, Fp* __restrict__ ptab) {
+  uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (p >= usable) return;
+  if (first_flag[p]) {
+    ptab[p] = pin[p];
+  } else {
+    uint32_t m = (uint32_t)p - first_scan[p];  // repeated rows before p
+    ptab[p] = table_sorted[left_rank[n_repeated - 1 - m]];
+  }
+}
+
+// u32 exclusive scan (single block, up to a few million entries) used by the lookup pass
+__global__ void scan_u32_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n,
+                                uint32_t* __restrict__ total) {
+  __shared__ uint32_t ws[32];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (uint32_t base = 0; base < n; base += blockDim.x * 4) {
+    uint32_t i0 = base + threadIdx.x * 4;
+    uint32_t v[4], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      v[k] = i0 + k < n ? in[i0 + k] : 0;
+      sum += v[k];
+    }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) ws[warp] = incl;
+    __syncthreads();
+    uint32_t off = carry;
+    for (int w = 0; w < warp; w++) off += ws[w];
+    uint32_t excl = off + incl - sum;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (i0 + k < n) out[i0 + k] = excl;
+      excl += v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = off + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && total) *total = carry;
+}
+
+// ---- IPA helpers ---------------------------------------------------------------------------------------
+// G'_i <- affine(G_lo_i + [u] G_hi_i): shared scalar, one thread per point
+struct ScalarBits {
+  uint64_t v[4];
+};
+__global__ void __launch_bounds__(128)
+generator_collapse_kernel(Affine* __restrict__ g, uint64_t half, ScalarBits u) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= half) return;
+  const Affine hi = g[i + half];
+  XYZZ acc = XYZZ::identity();
+  for (int bit = 254; bit >= 0; bit--) {
+    acc = acc.dbl();
+    if ((u.v[bit >> 6] >> (bit & 63)) & 1) acc = acc.add_affine(hi);
+  }
+  acc = acc.add_affine(g[i]);
+  g[i] = acc.to_affine();
+}
+
+}  // namespace
+
+// ---- the prover ------------------------------------------------------------------------------------------
+static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, uint64_t n_compressions,
+                                 const uint8_t seed[16], std::vector<uint8_t>& proof_out) {
+  ProverState* S = prover_state(ctx);
+  if (!S->has_params || !S->has_keys) return set_error(ctx, ZK_E_STATE, "create_proof before params/keygen");
+  DeviceKeys& K = S->keys;
+  const DeviceParams& P = S->params;
+  if (n_compressions != K.n_compressions) return set_error(ctx, ZK_E_INVALID, "batch size differs from keygen");
+  for (uint64_t i = 0; i < n_compressions; i++) {
+    const uint8_t* r = inputs + i * ZK_BLAKE2F_INPUT_BYTES;
+    uint32_t rr = ((uint32_t)r[0] << 24) | ((uint32_t)r[1] << 16) | ((uint32_t)r[2] << 8) | r[3];
+    if (r[212] > 1) return set_error(ctx, ZK_E_INPUT, "final-block flag must be 0 or 1");
+    if (rr != K.rounds) return set_error(ctx, ZK_E_INPUT, "record rounds differ from circuit rounds");
+  }
+  ProofWorkspace* W = nullptr;
+  int32_t rc = get_workspace(ctx, K, &W);
+  if (rc) return rc;
+  cudaStream_t st = ctx->stream;
+  const uint64_t n = K.n, en = K.en;
+  const int k = K.k;
+  const uint64_t usable = n - (BLINDING + 1);
+  NttOptions inv;
+  inv.inverse = true;
+  const unsigned T = 256;
+  auto blocks = [&](uint64_t cnt) { return (unsigned)((cnt + T - 1) / T); };
+
+  const size_t total_draws = 12 * 6 + 12 + 12 + 2 + NUM_SETS * 6 + 6 + (n + 1) + 3 + 1 + (n + 1) + 2 * (size_t)k;
+  RandomTape tape(seed, total_draws);
+  TranscriptWriter tr;
+  tr.common_scalar(K.transcript_repr);
+
+  // ---- witness (K1) ---------------------------------------------------------------------------------
+  if (n_compressions)
+    ZK_CUDA(ctx, cudaMemcpyAsync(W->inputs, inputs, n_compressions * 213, cudaMemcpyHostToDevice, st));
+  if ((rc = launch_witness(ctx, k, K.rounds, W->inputs, n_compressions, W->advice_values, W->digests))) return rc;
+  auto adv = [&](int c) { return W->advice_values + (size_t)c * n; };
+  auto adv_poly = [&](int c) { return W->advice_polys + (size_t)c * n; };
+  auto adv_coset = [&](int c) { return W->advice_cosets + (size_t)c * en; };
+
+  // ---- advice blinding rows, blinds, commitments -----------------------------------------------------
+  {
+    Fp tails[12 * 6];
+    for (int i = 0; i < 12 * 6; i++) tails[i] = tape.next();
+    for (int c = 0; c < 12; c++)
+      if ((rc = upload_fp(ctx, adv(c) + usable, tails + 6 * c, 6))) return rc;
+  }
+  Fp advice_blinds[12];
+  for (auto& b : advice_blinds) b = tape.next();
+  for (int c = 0; c < 12; c++) {
+    Affine cm;
+    if ((rc = commit(ctx, adv(c), P.g_lagrange, n, advice_blinds[c], &cm))) return rc;
+    tr.write_point(cm);
+  }
+  for (int c = 0; c < 12; c++)
+    if ((rc = ntt_run(ctx, adv(c), (uint32_t)n, adv_poly(c), k, inv))) return rc;
+
+  const Fp theta = tr.squeeze_challenge();
+
+  // ---- lookup: compress, permute, commit (K7) ----------------------------------------------------------
+  Fp pin_blind, ptab_blind, zl_blind;
+  {
+    lookup_compress_kernel<<<blocks(n), T, 0, st>>>(adv(7), adv(8), adv(9), theta, n, W->cin);
+    lookup_compress_kernel<<<blocks(n), T, 0, st>>>(K.fixed_values[0], K.fixed_values[1], K.fixed_values[2], theta,
+                                                    n, W->ctab);
+    ctx->launches += 2;
+    // table values = compressed table rows 0..65535; sort them on the host (2 MB, once per proof)
+    std::vector<Fp> tv(65536);
+    ZK_CUDA(ctx, cudaMemcpyAsync(tv.data(), W->ctab, 65536 * sizeof(Fp), cudaMemcpyDeviceToHost, st));
+    ZK_CUDA(ctx, cudaStreamSynchronize(st));
+    struct Key {
+      uint64_t c[4];
+      uint32_t idx;
+    };
+    std::vector<Key> keys(65536);
+    for (uint32_t j = 0; j < 65536; j++) {
+      tv[j].to_canonical(keys[j].c);
+      keys[j].idx = j;
+    }
+    std::sort(keys.begin(), keys.end(), [](const Key& a, const Key& b) {
+      for (int l = 3; l >= 0; l--)
+        if (a.c[l] != b.c[l]) return a.c[l] < b.c[l];
+      return a.idx < b.idx;
+    });
+    std::vector<uint32_t> rank_of(65536);
+    std::vector<Fp> sorted(65536);
+    for (uint32_t r = 0; r < 65536; r++) {
+      rank_of[keys[r].idx] = r;
+      sorted[r] = tv[keys[r].idx];
+    }
+    for (uint32_t r = 1; r < 65536; r++)
+      if (sorted[r] == sorted[r - 1]) return set_error(ctx, ZK_E_VERIFY, "theta collision in the spread table");
+    const uint32_t zero_rank = rank_of[0];  // table row 0 = (0,0,0) compresses to 0, the minimum
+    ZK_CUDA(ctx, cudaMemcpyAsync(W->table_vals, tv.data(), 65536 * sizeof(Fp), cudaMemcpyHostToDevice, st));
+    ZK_CUDA(ctx, cudaMemcpyAsync(W->table_sorted, sorted.data(), 65536 * sizeof(Fp), cudaMemcpyHostToDevice, st));
+    ZK_CUDA(ctx, cudaMemcpyAsync(W->rank_of, rank_of.data(), 65536 * 4, cudaMemcpyHostToDevice, st));
+    ZK_CUDA(ctx, cudaMemsetAsync(W->counts, 0, 65536 * 4, st));
+    lookup_count_kernel<<<blocks(usable), T, 0, st>>>(adv(8), W->cin, W->table_vals, W->rank_of, usable, W->counts,
+                                                      ctx->d_status);
+    scan_u32_kernel<<<1, 1024, 0, st>>>(W->counts, W->offsets, 65536, nullptr);
+    // table multiplicity: each of the 65536 rows once, the padding rows (usable - 65536) repeat row 0
+    lookup_leftover_kernel<<<256, 256, 0, st>>>(W->counts, zero_rank, (uint32_t)(usable - 65536 + 1), W->left_cnt);
+    uint32_t* d_total = W->left_off + 65536;
+    scan_u32_kernel<<<1, 1024, 0, st>>>(W->left_cnt, W->left_off, 65536, d_total);
+    ctx->launches += 4;
+    // first-occurrence flags: tmp_c (n field elements) doubles as u32 scratch here
+    uint32_t* first_flag = (uint32_t*)W->tmp_c;
+    lookup_fill_input_kernel<<<65536, 64, 0, st>>>(W->counts, W->offsets, W->table_sorted, W->pin, first_flag);
+    scan_u32_kernel<<<1, 1024, 0, st>>>(first_flag, W->first_flag_scan, (uint32_t)usable, nullptr);
+    lookup_fill_leftover_kernel<<<65536, 64, 0, st>>>(W->left_cnt, W->left_off, W->left_rank);
+    uint32_t n_repeated = 0;
+    ZK_CUDA(ctx, cudaMemcpyAsync(&n_repeated, d_total, 4, cudaMemcpyDeviceToHost, st));
+    int status = 0;
+    ZK_CUDA(ctx, cudaMemcpyAsync(&status, ctx->d_status, 4, cudaMemcpyDeviceToHost, st));
+    ZK_CUDA(ctx, cudaStreamSynchronize(st));
+    if (status) {
+      cudaMemsetAsync(ctx->d_status, 0, 4, st);
+      return set_error(ctx, ZK_E_VERIFY, "lookup input not in the spread table (ConstraintSystemFailure)");
+    }
+    lookup_fill_table_kernel<<<blocks(usable), T, 0, st>>>(W->pin, first_flag, W->first_flag_scan, W->left_rank,
+                                                           W->table_sorted, usable, n_repeated, W->ptab);
+    ctx->launches += 4;
+    ZK_CUDA(ctx, cudaGetLastError());
+    Fp tails[12];
+    for (auto& t : tails) t = tape.next();
+    if ((rc = upload_fp(ctx, W->pin + usable, tails, 6))) return rc;
+    if ((rc = upload_fp(ctx, W->ptab + usable, tails + 6, 6))) return rc;
+    Affine cm;
+    pin_blind = tape.next();
+    if ((rc = commit(ctx, W->pin, P.g_lagrange, n, pin_blind, &cm))) return rc;
+    tr.write_point(cm);
+    ptab_blind = tape.next();
+    if ((rc = commit(ctx, W->ptab, P.g_lagrange, n, ptab_blind, &cm))) return rc;
+    tr.write_point(cm);
+    if ((rc = ntt_run(ctx, W->pin, (uint32_t)n, W->pin_poly, k, inv))) return rc;
+    if ((rc = ntt_run(ctx, W->ptab, (uint32_t)n, W->ptab_poly, k, inv))) return rc;
+  }
+
+  const Fp beta = tr.squeeze_challenge();
+  const Fp gamma = tr.squeeze_challenge();
+
+  // ---- permutation grand products (K8) ------------------------------------------------------------------
+  Fp z_blinds[NUM_SETS];
+  {
+    NttTables* TN = nullptr;
+    if ((rc = ntt_tables(ctx, k, &TN))) return rc;
+    const Fp* tw = TN->tw_fwd;
+    Fp delta_pow[NUM_PERM];
+    delta_pow[0] = Fp::one();
+    for (int i = 1; i < NUM_PERM; i++) delta_pow[i] = delta_pow[i - 1] * Fp::delta();
+    Fp last_z = Fp::one();
+    for (int s = 0; s < NUM_SETS; s++) {
+      const int c0 = 2 * s, c1 = 2 * s + 1;
+      const Fp *v0 = adv(PERM_COLUMNS[c0]), *v1 = adv(PERM_COLUMNS[c1]);
+      const Fp *s0 = K.sigma_values[c0], *s1 = K.sigma_values[c1];
+      Fp* den = W->tmp_a;
+      Fp* num = W->tmp_b;
+      const Fp d0 = delta_pow[c0] * beta, d1 = delta_pow[c1] * beta;
+      launch_map(ctx, n, [=] __device__(uint64_t i) {
+        den[i] = (beta * s0[i] + gamma + v0[i]) * (beta * s1[i] + gamma + v1[i]);
+        Fp w = i < n / 2 ? tw[i] : tw[i - n / 2].neg();
+        num[i] = (d0 * w + gamma + v0[i]) * (d1 * w + gamma + v1[i]);
+      });
+      if ((rc = batch_invert(ctx, den, n))) return rc;
+      launch_map(ctx, n, [=] __device__(uint64_t i) { num[i] = num[i] * den[i]; });
+      Fp* z = W->tmp_c;
+      if ((rc = affine_scan(ctx, num, Fp::zero(), nullptr, n, last_z, z))) return rc;
+      Fp tails[5];
+      for (auto& t : tails) t = tape.next();
+      if ((rc = upload_fp(ctx, z + n - BLINDING, tails, BLINDING))) return rc;
+      ZK_CUDA(ctx, cudaMemcpyAsync(&last_z, z + n - (BLINDING + 1), sizeof(Fp), cudaMemcpyDeviceToHost, st));
+      z_blinds[s] = tape.next();
+      Affine cm;
+      if ((rc = commit(ctx, z, P.g_lagrange, n, z_blinds[s], &cm))) return rc;  // syncs: last_z is valid after
+      tr.write_point(cm);
+      if ((rc = ntt_run(ctx, z, (uint32_t)n, W->z_poly[s], k, inv))) return rc;
+    }
+  }
+  // ---- lookup grand product ------------------------------------------------------------------------------
+  {
+    Fp *den = W->tmp_a, *num = W->tmp_b, *z = W->tmp_c;
+    const Fp *pin = W->pin, *ptab = W->ptab, *cin = W->cin, *ctab = W->ctab;
+    launch_map(ctx, n, [=] __device__(uint64_t i) { den[i] = (beta + pin[i]) * (gamma + ptab[i]); });
+    if ((rc = batch_invert(ctx, den, n))) return rc;
+    launch_map(ctx, n, [=] __device__(uint64_t i) { num[i] = den[i] * (cin[i] + beta) * (ctab[i] + gamma); });
+    if ((rc = affine_scan(ctx, num, Fp::zero(), nullptr, n, Fp::one(), z))) return rc;
+    Fp tails[5];
+    for (auto& t : tails) t = tape.next();
+    if ((rc = upload_fp(ctx, z + n - BLINDING, tails, BLINDING))) return rc;
+    zl_blind = tape.next();
+    Affine cm;
+    if ((rc = commit(ctx, z, P.g_lagrange, n, zl_blind, &cm))) return rc;
+    tr.write_point(cm);
+    if ((rc = ntt_run(ctx, z, (uint32_t)n, W->zl_poly, k, inv))) return rc;
+  }
+  // ---- vanishing argument: random polynomial ----------------------------------------------------------------
+  if ((rc = random_poly_to_device(ctx, W, tape, n, W->random_poly))) return rc;
+  const Fp random_blind = tape.next();
+  {
+    Affine cm;
+    if ((rc = commit(ctx, W->random_poly, P.g, n, random_blind, &cm))) return rc;
+    tr.write_point(cm);
+  }
+  const Fp y = tr.squeeze_challenge();
+
+  // ---- quotient (K5 + K6) ---------------------------------------------------------------------------------------
+  {
+    for (int c = 0; c < 12; c++)
+      if ((rc = coeff_to_extended(ctx, K, adv_poly(c), adv_coset(c)))) return rc;
+    for (int s = 0; s < NUM_SETS; s++)
+      if ((rc = coeff_to_extended(ctx, K, W->z_poly[s], W->z_coset[s]))) return rc;
+    if ((rc = coeff_to_extended(ctx, K, W->zl_poly, W->zl_coset))) return rc;
+    if ((rc = coeff_to_extended(ctx, K, W->pin_poly, W->pin_coset))) return rc;
+    if ((rc = coeff_to_extended(ctx, K, W->ptab_poly, W->ptab_coset))) return rc;
+    NttTables* TE = nullptr;
+    if ((rc = ntt_tables(ctx, K.ek, &TE))) return rc;
+    QuotientArgs qa;
+    for (int c = 0; c < 12; c++) qa.advice[c] = adv_coset(c);
+    for (int c = 0; c < NUM_FIXED; c++) qa.fixed[c] = K.fixed_cosets[c];
+    for (int c = 0; c < NUM_PERM; c++) qa.sigma[c] = K.sigma_cosets[c];
+    for (int s = 0; s < NUM_SETS; s++) qa.perm_z[s] = W->z_coset[s];
+    qa.lookup_z = W->zl_coset;
+    qa.lookup_in = W->pin_coset;
+    qa.lookup_tab = W->ptab_coset;
+    qa.l0 = K.l0;
+    qa.l_last = K.l_last;
+    qa.l_active = K.l_active;
+    qa.tw_ext = TE->tw_fwd;
+    qa.h = W->h;
+    for (int s = 0; s < NUM_SELECTORS; s++) qa.sel[s] = K.selectors[s];
+    qa.theta = theta;
+    qa.beta = beta;
+    qa.gamma = gamma;
+    qa.y = y;
+    qa.zeta = K.zeta;
+    qa.delta_pow[0] = Fp::one();
+    for (int i = 1; i < NUM_PERM; i++) qa.delta_pow[i] = qa.delta_pow[i - 1] * Fp::delta();
+    for (int i = 0; i < 4; i++) {
+      qa.t_inv[i] = K.t_inv[i];
+      qa.small[i] = Fp::from_u64(i);
+    }
+    qa.pow2[0] = Fp::one();
+    for (int e = 1; e < 127; e++) qa.pow2[e] = qa.pow2[e - 1].dbl();
+    if ((rc = quotient_run(ctx, qa, en))) return rc;
+    // extended_to_coeff: inverse NTT, 1/en scaling, undo the coset, keep 3n coefficients
+    NttOptions o;
+    o.inverse = true;
+    o.coset_out = 1;
+    o.coset_out_pow[0] = K.zeta_sq;  // zeta^-1
+    o.coset_out_pow[1] = K.zeta;     // zeta^-2
+    if ((rc = ntt_run(ctx, W->h, (uint32_t)en, W->h_coeffs, K.ek, o))) return rc;
+  }
+  Fp h_blinds[3];
+  for (auto& b : h_blinds) b = tape.next();
+  for (int p = 0; p < 3; p++) {
+    Affine cm;
+    if ((rc = commit(ctx, W->h_coeffs + (size_t)p * n, P.g, n, h_blinds[p], &cm))) return rc;
+    tr.write_point(cm);
+  }
+
+  const Fp x = tr.squeeze_challenge();
+  const Fp xn = x.pow_u64(n);
+  NttTables* TN = nullptr;
+  if ((rc = ntt_tables(ctx, k, &TN))) return rc;
+  auto rotate = [&](const Fp& v, int rot) {
+    return rot >= 0 ? v * TN->omega.pow_u64((uint64_t)rot) : v * TN->omega_inv.pow_u64((uint64_t)(-rot));
+  };
+  const Fp x_next = rotate(x, 1), x_prev = rotate(x, -1), x_last = rotate(x, -(BLINDING + 1));
+
+  // ---- evaluations (K9) -----------------------------------------------------------------------------------------
+  // advice_queries / fixed_queries in first-use order of `configure` (docs/CIRCUIT.md §Queries)
+  static const int ADVICE_QUERIES[24][2] = {{7, 0}, {8, 0},  {9, 0},  {1, 0},  {8, -1}, {8, 1},  {2, 0}, {7, 1},
+                                            {9, 1}, {0, 0},  {1, -1}, {2, -1}, {0, -1}, {3, -1}, {4, -1}, {5, -1},
+                                            {3, 0}, {4, 0},  {5, 0},  {1, 1},  {6, 0},  {9, -1}, {2, 1}, {0, 1}};
+  auto point_of = [&](int rot) { return rot == 0 ? x : (rot == 1 ? x_next : x_prev); };
+  // h_poly = sum_p x^(n p) h_piece_p, h_blind likewise
+  {
+    const Fp* hc = W->h_coeffs;
+    Fp* hp = W->h_poly;
+    const Fp xn2 = xn * xn;
+    launch_map(ctx, n, [=] __device__(uint64_t i) { hp[i] = hc[i] + hc[n + i] * xn + hc[2 * n + i] * xn2; });
+  }
+  const Fp h_blind = h_blinds[0] + h_blinds[1] * xn + h_blinds[2] * xn * xn;
+  std::vector<EvalJob> jobs;
+  for (auto& q : ADVICE_QUERIES) jobs.push_back(EvalJob{adv_poly(q[0]), point_of(q[1])});
+  for (int c = 0; c < NUM_FIXED; c++) jobs.push_back(EvalJob{K.fixed_polys[c], x});
+  jobs.push_back(EvalJob{W->random_poly, x});
+  for (int c = 0; c < NUM_PERM; c++) jobs.push_back(EvalJob{K.sigma_polys[c], x});
+  for (int s = 0; s < NUM_SETS; s++) {
+    jobs.push_back(EvalJob{W->z_poly[s], x});
+    jobs.push_back(EvalJob{W->z_poly[s], x_next});
+    if (s + 1 != NUM_SETS) jobs.push_back(EvalJob{W->z_poly[s], x_last});
+  }
+  jobs.push_back(EvalJob{W->zl_poly, x});
+  jobs.push_back(EvalJob{W->zl_poly, x_next});
+  jobs.push_back(EvalJob{W->pin_poly, x});
+  jobs.push_back(EvalJob{W->pin_poly, x_prev});
+  jobs.push_back(EvalJob{W->ptab_poly, x});
+  {
+    std::vector<Fp> evals(jobs.size());
+    if ((rc = poly_eval_batch(ctx, jobs.data(), (int)jobs.size(), n, evals.data()))) return rc;
+    for (auto& e : evals) tr.write_scalar(e);
+  }
+
+  // ---- multiopen (K10) --------------------------------------------------------------------------------------------
+  struct OpenPoly {
+    const Fp* poly;
+    Fp blind;
+    std::vector<int> points;  // indices into `points`
+    int set = -1;
+  };
+  std::vector<Fp> points;
+  std::vector<OpenPoly> polys;
+  auto point_index = [&](const Fp& p) {
+    for (size_t i = 0; i < points.size(); i++)
+      if (points[i] == p) return (int)i;
+    points.push_back(p);
+    return (int)points.size() - 1;
+  };
+  auto add_query = [&](const Fp* poly, const Fp& blind, const Fp& point) {
+    int pi = point_index(point);
+    for (auto& op : polys)
+      if (op.poly == poly) {
+        op.points.push_back(pi);
+        return;
+      }
+    polys.push_back(OpenPoly{poly, blind, {pi}, -1});
+  };
+  for (auto& q : ADVICE_QUERIES) add_query(adv_poly(q[0]), advice_blinds[q[0]], point_of(q[1]));
+  for (int s = 0; s < NUM_SETS; s++) {
+    add_query(W->z_poly[s], z_blinds[s], x);
+    add_query(W->z_poly[s], z_blinds[s], x_next);
+  }
+  for (int s = NUM_SETS - 2; s >= 0; s--) add_query(W->z_poly[s], z_blinds[s], x_last);
+  add_query(W->zl_poly, zl_blind, x);
+  add_query(W->pin_poly, pin_blind, x);
+  add_query(W->ptab_poly, ptab_blind, x);
+  add_query(W->pin_poly, pin_blind, x_prev);
+  add_query(W->zl_poly, zl_blind, x_next);
+  for (int c = 0; c < NUM_FIXED; c++) add_query(K.fixed_polys[c], Fp::one(), x);
+  for (int c = 0; c < NUM_PERM; c++) add_query(K.sigma_polys[c], Fp::one(), x);
+  add_query(W->h_poly, h_blind, x);
+  add_query(W->random_poly, random_blind, x);
+
+  const Fp x1 = tr.squeeze_challenge();
+  const Fp x2 = tr.squeeze_challenge();
+  // point sets: ordered sets of point indices, numbered by first appearance over `polys`
+  std::vector<std::vector<int>> sets;
+  for (auto& op : polys) {
+    std::vector<int> s = op.points;
+    std::sort(s.begin(), s.end());
+    s.erase(std::unique(s.begin(), s.end()), s.end());
+    int found = -1;
+    for (size_t i = 0; i < sets.size(); i++)
+      if (sets[i] == s) found = (int)i;
+    if (found < 0) {
+      sets.push_back(s);
+      found = (int)sets.size() - 1;
+    }
+    op.set = found;
+  }
+  if (sets.size() > 8) return set_error(ctx, ZK_E_INVALID, "too many multiopen point sets");
+  // halo2 numbers the sets through a BTreeMap keyed by the index set: insertion order defines the
+  // set index (`or_insert(num_sets)`), iteration order does not matter for the prover.
+  std::vector<Fp> q_blinds(sets.size(), Fp::zero());
+  std::vector<bool> started(sets.size(), false);
+  for (auto& op : polys) {
+    Fp* acc = W->q_polys[op.set];
+    const Fp* np = op.poly;
+    if (!started[op.set]) {
+      ZK_CUDA(ctx, cudaMemcpyAsync(acc, np, n * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
+      started[op.set] = true;
+    } else {
+      launch_map(ctx, n, [=] __device__(uint64_t i) { acc[i] = acc[i] * x1 + np[i]; });
+    }
+    q_blinds[op.set] = q_blinds[op.set] * x1 + op.blind;
+  }
+  // q'(X) = sum_sets x2^.. * q_set(X) / prod (X - p): synthetic division as an affine scan over
+  // the reversed coefficient vector
+  for (size_t s = 0; s < sets.size(); s++) {
+    Fp* cur = W->tmp_a;
+    ZK_CUDA(ctx, cudaMemcpyAsync(cur, W->q_polys[s], n * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
+    uint64_t len = n;
+    for (int pi : sets[s]) {
+      const Fp pt = points[pi];
+      Fp* rev = W->tmp_b;
+      Fp* scanned = W->tmp_c;
+      const uint64_t L = len;
+      launch_map(ctx, L, [=] __device__(uint64_t j) { rev[j] = cur[L - 1 - j]; });
+      // y_0 = 0, y_{j+1} = y_j * pt + rev[j];  quotient coefficient i = y_{L-1-i}
+      if ((rc = affine_scan(ctx, nullptr, pt, rev, L, Fp::zero(), scanned))) return rc;
+      launch_map(ctx, n, [=] __device__(uint64_t i) { cur[i] = i + 1 < L ? scanned[L - 1 - i] : Fp::zero(); });
+      len = L - 1;
+    }
+    Fp* qp = W->q_prime;
+    if (s == 0) {
+      ZK_CUDA(ctx, cudaMemcpyAsync(qp, cur, n * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
+    } else {
+      launch_map(ctx, n, [=] __device__(uint64_t i) { qp[i] = qp[i] * x2 + cur[i]; });
+    }
+  }
+  const Fp q_prime_blind = tape.next();
+  {
+    Affine cm;
+    if ((rc = commit(ctx, W->q_prime, P.g, n, q_prime_blind, &cm))) return rc;
+    tr.write_point(cm);
+  }
+  const Fp x3 = tr.squeeze_challenge();
+  {
+    std::vector<EvalJob> qj;
+    for (size_t s = 0; s < sets.size(); s++) qj.push_back(EvalJob{W->q_polys[s], x3});
+    std::vector<Fp> ev(qj.size());
+    if ((rc = poly_eval_batch(ctx, qj.data(), (int)qj.size(), n, ev.data()))) return rc;
+    for (auto& e : ev) tr.write_scalar(e);
+  }
+  const Fp x4 = tr.squeeze_challenge();
+  Fp p_blind = q_prime_blind;
+  {
+    Fp* pp = W->p_poly;
+    ZK_CUDA(ctx, cudaMemcpyAsync(pp, W->q_prime, n * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
+    for (size_t s = 0; s < sets.size(); s++) {
+      const Fp* q = W->q_polys[s];
+      launch_map(ctx, n, [=] __device__(uint64_t i) { pp[i] = pp[i] * x4 + q[i]; });
+      p_blind = p_blind * x4 + q_blinds[s];
+    }
+  }
+
+  // ---- inner product argument (K11) ------------------------------------------------------------------------------
+  {
+    if ((rc = random_poly_to_device(ctx, W, tape, n, W->s_poly))) return rc;
+    Fp* sp = W->s_poly;
+    {
+      EvalJob j{sp, x3};
+      Fp s_at_x3;
+      if ((rc = poly_eval_batch(ctx, &j, 1, n, &s_at_x3))) return rc;
+      launch_map(ctx, 1, [=] __device__(uint64_t) { sp[0] = sp[0] - s_at_x3; });
+    }
+    const Fp s_blind = tape.next();
+    Affine cm;
+    if ((rc = commit(ctx, sp, P.g, n, s_blind, &cm))) return rc;
+    tr.write_point(cm);
+    const Fp xi = tr.squeeze_challenge();
+    const Fp z = tr.squeeze_challenge();
+    Fp* pp = W->p_poly;  // becomes p'
+    launch_map(ctx, n, [=] __device__(uint64_t i) { pp[i] = sp[i] * xi + pp[i]; });
+    {
+      EvalJob j{pp, x3};
+      Fp v;
+      if ((rc = poly_eval_batch(ctx, &j, 1, n, &v))) return rc;
+      launch_map(ctx, 1, [=] __device__(uint64_t) { pp[0] = pp[0] - v; });
+    }
+    Fp f = s_blind * xi + p_blind;
+    // b = powers of x3
+    Fp* b = W->b_vec;
+    if ((rc = affine_scan(ctx, nullptr, x3, nullptr, n, Fp::one(), b))) return rc;
+    Affine* g = W->g_fold;
+    ZK_CUDA(ctx, cudaMemcpyAsync(g, P.g, n * sizeof(Affine), cudaMemcpyDeviceToDevice, st));
+    for (int j = 0; j < k; j++) {
+      const uint64_t half = 1ull << (k - j - 1);
+      XYZZ lj, rj;
+      if ((rc = msm_run(ctx, pp + half, g, half, &lj))) return rc;
+      if ((rc = msm_run(ctx, pp, g + half, half, &rj))) return rc;
+      Fp vl, vr;
+      if ((rc = inner_product(ctx, pp + half, b, half, &vl))) return rc;
+      if ((rc = inner_product(ctx, pp, b + half, half, &vr))) return rc;
+      const Fp l_rand = tape.next(), r_rand = tape.next();
+      auto host_mul = [](const Affine& pt, const Fp& s) {
+        uint64_t e[4];
+        s.to_canonical(e);
+        XYZZ acc = XYZZ::identity();
+        for (int i = 254; i >= 0; i--) {
+          acc = acc.dbl();
+          if ((e[i >> 6] >> (i & 63)) & 1) acc = acc.add_affine(pt);
+        }
+        return acc;
+      };
+      lj = lj.add(host_mul(P.u, vl * z)).add(host_mul(P.w, l_rand));
+      rj = rj.add(host_mul(P.u, vr * z)).add(host_mul(P.w, r_rand));
+      tr.write_point(lj.to_affine());
+      tr.write_point(rj.to_affine());
+      const Fp u = tr.squeeze_challenge();
+      const Fp u_inv = u.inv();
+      launch_map(ctx, half, [=] __device__(uint64_t i) {
+        pp[i] = pp[i] + pp[i + half] * u_inv;
+        b[i] = b[i] + b[i + half] * u;
+      });
+      ScalarBits ub;
+      u.to_canonical(ub.v);
+      generator_collapse_kernel<<<(unsigned)((half + 127) / 128), 128, 0, st>>>(g, half, ub);
+      ctx->launches++;
+      f = f + l_rand * u_inv + r_rand * u;
+    }
+    Fp c;
+    ZK_CUDA(ctx, cudaMemcpyAsync(&c, pp, sizeof(Fp), cudaMemcpyDeviceToHost, st));
+    ZK_CUDA(ctx, cudaStreamSynchronize(st));
+    tr.write_scalar(c);
+    tr.write_scalar(f);
+  }
+  ZK_CUDA(ctx, cudaGetLastError());
+  proof_out = tr.proof();
+  return ZK_OK;
+}
+
+}  // namespace zkodst
+
+using namespace zkodst;
+
+extern "C" int32_t zk_create_proof(zk_ctx* ctx, const uint8_t* inputs, uint64_t n_compressions,
+                                   const uint8_t seed[16], uint8_t* proof_out, uint64_t* proof_len) {
+  if (!ctx || !seed || !proof_len || (n_compressions && !inputs)) return ZK_E_INVALID;
+  ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+  std::vector<uint8_t> proof;
+  int32_t rc;
+  try {
+    rc = create_proof_impl(ctx, inputs, n_compressions, seed, proof);
+  } catch (std::exception& e) {
+    return set_error(ctx, ZK_E_VERIFY, e.what());
+  }
+  if (rc) return rc;
+  if (!proof_out || *proof_len < proof.size()) {
+    *proof_len = proof.size();
+    return set_error(ctx, ZK_E_BUFFER, "proof buffer too small");
+  }
+  memcpy(proof_out, proof.data(), proof.size());
+  *proof_len = proof.size();
+  return ZK_OK;
+}

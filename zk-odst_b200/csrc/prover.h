@@ -19,6 +19,7 @@ int32_t ntt_run(zk_ctx* ctx, const Fp* in, uint32_t n_in, Fp* out, int log_n, co
 
 // msm.cu
 int msm_window_bits(uint64_t n);
-int32_t msm_run(zk_ctx* ctx, const Fp* d_scalars, const Affine* d_bases, uint64_t n, XYZZ* result);
+int32_t msm_run(zk_ctx* ctx, const Fp* d_scalars, const Affine* d_bases, uint64_t n, XYZZ* result,
+                const Fp* d_extra = nullptr);
 
 }  // namespace zkodst

@@ -1,0 +1,71 @@
+// Device-resident parameters and keys of the prover (product code).
+//
+// `DeviceParams` replaces halo2_proofs 0.3.0 `poly::commitment::Params<EqAffine>`
+// (blake2f-circuit/benches/blake2f.rs:83-97); `DeviceKeys` replaces `ProvingKey`/`VerifyingKey`
+// from `keygen_vk` / `keygen_pk` (benches/blake2f.rs:102-103) for the BLAKE2f Table16 circuit.
+#pragma once
+#include <vector>
+
+#include "ec.cuh"
+#include "prover.h"
+
+namespace zkodst {
+
+constexpr int NUM_FIXED = 10;   // 3 table columns + 7 compressed-selector columns
+constexpr int NUM_PERM = 8;     // equality-enabled columns a_1..a_8 (table16.rs:312-314)
+constexpr int NUM_SETS = 4;     // permutation grand products: chunks of degree - 2 = 2 columns
+constexpr int BLINDING = 5;     // ConstraintSystem::blinding_factors() for this circuit
+constexpr int CS_DEGREE = 4;
+
+// halo2 advice column index of each permutation column, in enable_equality order
+static const int PERM_COLUMNS[NUM_PERM] = {8, 9, 1, 2, 0, 3, 4, 5};
+
+struct SelectorExpr {  // compress_selectors result: selector = q * prod_{r != root} (r - q)
+  int fixed_col, root, len;
+};
+
+struct DeviceParams {
+  int k = 0;
+  uint64_t n = 0;
+  Affine* g = nullptr;           // n + 1 entries: g[0..n), then w
+  Affine* g_lagrange = nullptr;  // n + 1 entries: g_lagrange[0..n), then w
+  Affine w, u;
+};
+
+struct DeviceKeys {
+  int k = 0, ek = 0;
+  uint64_t n = 0, en = 0;
+  uint32_t rounds = 0;
+  uint64_t n_compressions = 0, region_rows = 0;
+  SelectorExpr selectors[NUM_SELECTORS];
+  Fp* fixed_values[NUM_FIXED] = {};
+  Fp* fixed_polys[NUM_FIXED] = {};
+  Fp* fixed_cosets[NUM_FIXED] = {};
+  Fp* sigma_values[NUM_PERM] = {};
+  Fp* sigma_polys[NUM_PERM] = {};
+  Fp* sigma_cosets[NUM_PERM] = {};
+  Fp *l0 = nullptr, *l_last = nullptr, *l_active = nullptr;  // extended cosets
+  std::vector<Affine> fixed_commitments, sigma_commitments;
+  Fp transcript_repr;
+  Fp t_inv[4];  // 1 / (X^n - 1) on the extended coset, period 4
+  Fp zeta, zeta_sq;
+  void* workspace = nullptr;  // ProofWorkspace (prover.cu), allocated lazily
+};
+
+struct ProverState {
+  bool has_params = false, has_keys = false;
+  DeviceParams params;
+  DeviceKeys keys;
+};
+
+ProverState* prover_state(zk_ctx* ctx);
+void free_keys(DeviceKeys& k);
+void free_workspace(void* ws);
+
+// commit: MSM(scalars || blind, bases || w) -> affine (host)
+int32_t commit(zk_ctx* ctx, const Fp* d_scalars, const Affine* d_bases_plus_w, uint64_t n, const Fp& blind,
+               Affine* out);
+// coefficients (n) -> evaluations on the extended coset zeta * <omega_ext> (en)
+int32_t coeff_to_extended(zk_ctx* ctx, const DeviceKeys& K, const Fp* coeffs, Fp* out);
+
+}  // namespace zkodst
