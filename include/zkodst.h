@@ -57,6 +57,10 @@ uint64_t zk_ctx_launch_count(const zk_ctx* ctx);
  * events on the context's stream.  which: 0 = witness kernel. */
 int32_t zk_ctx_last_kernel_ms(zk_ctx* ctx, int32_t which, float* ms);
 int32_t zk_ctx_enable_timing(zk_ctx* ctx, int32_t on);
+/* Device time (ms) and number of timed regions per kernel class since the previous report:
+ * 0 witness, 1 msm (whole pipeline), 2 ntt, 3 quotient, 4 ipa generator collapse,
+ * 5 msm bucket accumulation; arrays of 8. */
+int32_t zk_ctx_timing_report(zk_ctx* ctx, float* ms_per_class, uint32_t* launches_per_class);
 
 /* Integer-pipe micro-benchmark (the compute roofline of the field-arithmetic kernels;
  * SURVEY.md §6 asks for it because no INT32 peak was measured by the driver).

@@ -41,6 +41,7 @@ def load_library():
             "zk_ctx_launch_count": (u64, [vp]),
             "zk_ctx_last_kernel_ms": (i32, [vp, i32, c.POINTER(c.c_float)]),
             "zk_ctx_enable_timing": (i32, [vp, i32]),
+            "zk_ctx_timing_report": (i32, [vp, c.POINTER(c.c_float), c.POINTER(u32)]),
             "zk_bench_int_pipe": (i32, [vp, i32, u32, c.POINTER(c.c_double)]),
             "zk_blake2f_rows_per_compression": (i32, [u32, c.POINTER(u64)]),
             "zk_blake2f_min_k": (i32, [u32, u64, c.POINTER(i32)]),
@@ -142,6 +143,13 @@ class Context:
 
     def enable_timing(self, on=True):
         self._check(self.lib.zk_ctx_enable_timing(self.h, 1 if on else 0))
+
+    def timing_report(self):
+        ms = (ctypes.c_float * 8)()
+        cnt = (ctypes.c_uint32 * 8)()
+        self._check(self.lib.zk_ctx_timing_report(self.h, ms, cnt))
+        names = ["witness", "msm", "ntt", "quotient", "collapse", "msm_accumulate", "6", "7"]
+        return {names[i]: (ms[i], cnt[i]) for i in range(8)}
 
     def last_kernel_ms(self, which=0):
         ms = ctypes.c_float()

@@ -71,7 +71,6 @@ int32_t zk_ctx_create(int32_t device_id, zk_ctx** out) {
     return ZK_E_CUDA;
   }
   ctx->stream = ctx->own_stream;
-  for (auto& e : ctx->ev) cudaEventCreate(&e);
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device_id);
   if (cudaMalloc((void**)&ctx->d_status, sizeof(int)) != cudaSuccess ||
       cudaMemset(ctx->d_status, 0, sizeof(int)) != cudaSuccess) {
@@ -104,7 +103,7 @@ void zk_ctx_destroy(zk_ctx* ctx) {
     cudaFree(kv.second.tw_inv);
   }
   cudaFree(ctx->d_status);
-  for (auto& e : ctx->ev)
+  for (auto& e : ctx->ev_pool)
     if (e) cudaEventDestroy(e);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
@@ -139,11 +138,35 @@ int32_t zk_ctx_enable_timing(zk_ctx* ctx, int32_t on) {
   return ZK_OK;
 }
 
+// Sums the timed regions recorded since the previous report, per kernel class.
+int32_t zk_ctx_timing_report(zk_ctx* ctx, float* ms_per_class, uint32_t* launches_per_class) {
+  if (!ctx) return ZK_E_INVALID;
+  ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  float acc[KC_COUNT] = {};
+  uint32_t cnt[KC_COUNT] = {};
+  for (auto& t : ctx->timed) {
+    float ms = 0;
+    ZK_CUDA(ctx, cudaEventElapsedTime(&ms, t.a, t.b));
+    acc[t.which] += ms;
+    cnt[t.which]++;
+    ctx->last_ms[t.which] = ms;
+    ctx->last_valid[t.which] = true;
+  }
+  ctx->timed.clear();
+  ctx->ev_used = 0;
+  for (int i = 0; i < KC_COUNT; i++) {
+    if (ms_per_class) ms_per_class[i] = acc[i];
+    if (launches_per_class) launches_per_class[i] = cnt[i];
+  }
+  return ZK_OK;
+}
+
 int32_t zk_ctx_last_kernel_ms(zk_ctx* ctx, int32_t which, float* ms) {
   if (!ctx || !ms || which < 0 || which >= KC_COUNT) return ZK_E_INVALID;
-  if (!ctx->ev_valid[which]) return set_error(ctx, ZK_E_STATE, "kernel class not timed yet");
-  ZK_CUDA(ctx, cudaEventSynchronize(ctx->ev[2 * which + 1]));
-  ZK_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev[2 * which], ctx->ev[2 * which + 1]));
+  int32_t rc = zk_ctx_timing_report(ctx, nullptr, nullptr);
+  if (rc) return rc;
+  if (!ctx->last_valid[which]) return set_error(ctx, ZK_E_STATE, "kernel class not timed yet");
+  *ms = ctx->last_ms[which];
   return ZK_OK;
 }
 

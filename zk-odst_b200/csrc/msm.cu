@@ -18,6 +18,9 @@
 //
 // Roofline: integer-pipe bound: 16 bucket additions x 11 Fq mults x 136 MAC
 // per full-width term; HBM traffic is 96 B per term.
+#include <chrono>
+#include <cstdlib>
+
 #include "ec.cuh"
 #include "zk_ctx.h"
 
@@ -329,8 +332,11 @@ int32_t msm_device(zk_ctx* ctx, const Fp* d_scalars, const Fp* d_extra, const Af
   msm_scatter_kernel<<<(n + T - 1) / T, T, 0, st>>>(digits, n, c, nwin, offsets, cursor, sorted);
   msm_find_heavy_kernel<<<(nbuckets + T - 1) / T, T, 0, st>>>(counts, offsets, nbuckets, hitems, hcount,
                                                                max_heavy_items, hbuckets, hcount + 1);
-  msm_accumulate_kernel<<<(nbuckets + 127) / 128, 128, 0, st>>>(d_bases, sorted, counts, offsets, nbuckets,
-                                                                 buckets);
+  {
+    KernelTimer acc_timer(ctx, KC_MSM_ACC);
+    msm_accumulate_kernel<<<(nbuckets + 127) / 128, 128, 0, st>>>(d_bases, sorted, counts, offsets, nbuckets,
+                                                                   buckets);
+  }
   ctx->launches += 7;
   // heavy path: sizes are data dependent, so read the two counters back
   uint32_t hc[2];
@@ -375,8 +381,19 @@ int32_t msm_run(zk_ctx* ctx, const Fp* d_scalars, const Affine* d_bases, uint64_
   int nwin = 0;
   int32_t rc = ensure_buf(ctx, ctx->msm_out, 64 * sizeof(XYZZ));
   if (rc) return rc;
+  static const bool trace = getenv("ZK_MSM_TRACE") != nullptr;
+  std::chrono::steady_clock::time_point t0;
+  if (trace) {
+    cudaStreamSynchronize(ctx->stream);
+    t0 = std::chrono::steady_clock::now();
+  }
   rc = msm_device(ctx, d_scalars, d_extra, d_bases, n, c, &nwin, (XYZZ*)ctx->msm_out.ptr);
   if (rc) return rc;
+  if (trace) {
+    cudaStreamSynchronize(ctx->stream);
+    double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    fprintf(stderr, "[msm] n=%llu c=%d nwin=%d device_ms=%.3f\n", (unsigned long long)n, c, nwin, ms);
+  }
   XYZZ sums[48];
   ZK_CUDA(ctx, cudaMemcpyAsync(sums, ctx->msm_out.ptr, (size_t)nwin * sizeof(XYZZ),
                                cudaMemcpyDeviceToHost, ctx->stream));

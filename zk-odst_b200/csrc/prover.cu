@@ -341,7 +341,7 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, uint64_t n_
   for (auto& b : advice_blinds) b = tape.next();
   for (int c = 0; c < 12; c++) {
     Affine cm;
-    if ((rc = commit(ctx, adv(c), P.g_lagrange, n, advice_blinds[c], &cm))) return rc;
+    if ((rc = commit(ctx, adv(c), P.fb_gl, n,advice_blinds[c], &cm))) return rc;
     tr.write_point(cm);
   }
   for (int c = 0; c < 12; c++)
@@ -419,10 +419,10 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, uint64_t n_
     if ((rc = upload_fp(ctx, W->ptab + usable, tails + 6, 6))) return rc;
     Affine cm;
     pin_blind = tape.next();
-    if ((rc = commit(ctx, W->pin, P.g_lagrange, n, pin_blind, &cm))) return rc;
+    if ((rc = commit(ctx, W->pin, P.fb_gl, n,pin_blind, &cm))) return rc;
     tr.write_point(cm);
     ptab_blind = tape.next();
-    if ((rc = commit(ctx, W->ptab, P.g_lagrange, n, ptab_blind, &cm))) return rc;
+    if ((rc = commit(ctx, W->ptab, P.fb_gl, n,ptab_blind, &cm))) return rc;
     tr.write_point(cm);
     if ((rc = ntt_run(ctx, W->pin, (uint32_t)n, W->pin_poly, k, inv))) return rc;
     if ((rc = ntt_run(ctx, W->ptab, (uint32_t)n, W->ptab_poly, k, inv))) return rc;
@@ -463,7 +463,7 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, uint64_t n_
       ZK_CUDA(ctx, cudaMemcpyAsync(&last_z, z + n - (BLINDING + 1), sizeof(Fp), cudaMemcpyDeviceToHost, st));
       z_blinds[s] = tape.next();
       Affine cm;
-      if ((rc = commit(ctx, z, P.g_lagrange, n, z_blinds[s], &cm))) return rc;  // syncs: last_z is valid after
+      if ((rc = commit(ctx, z, P.fb_gl, n,z_blinds[s], &cm))) return rc;  // syncs: last_z is valid after
       tr.write_point(cm);
       if ((rc = ntt_run(ctx, z, (uint32_t)n, W->z_poly[s], k, inv))) return rc;
     }
@@ -481,7 +481,7 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, uint64_t n_
     if ((rc = upload_fp(ctx, z + n - BLINDING, tails, BLINDING))) return rc;
     zl_blind = tape.next();
     Affine cm;
-    if ((rc = commit(ctx, z, P.g_lagrange, n, zl_blind, &cm))) return rc;
+    if ((rc = commit(ctx, z, P.fb_gl, n,zl_blind, &cm))) return rc;
     tr.write_point(cm);
     if ((rc = ntt_run(ctx, z, (uint32_t)n, W->zl_poly, k, inv))) return rc;
   }
@@ -490,7 +490,7 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, uint64_t n_
   const Fp random_blind = tape.next();
   {
     Affine cm;
-    if ((rc = commit(ctx, W->random_poly, P.g, n, random_blind, &cm))) return rc;
+    if ((rc = commit(ctx, W->random_poly, P.fb_g, n,random_blind, &cm))) return rc;
     tr.write_point(cm);
   }
   const Fp y = tr.squeeze_challenge();
@@ -546,7 +546,7 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, uint64_t n_
   for (auto& b : h_blinds) b = tape.next();
   for (int p = 0; p < 3; p++) {
     Affine cm;
-    if ((rc = commit(ctx, W->h_coeffs + (size_t)p * n, P.g, n, h_blinds[p], &cm))) return rc;
+    if ((rc = commit(ctx, W->h_coeffs + (size_t)p * n, P.fb_g, n,h_blinds[p], &cm))) return rc;
     tr.write_point(cm);
   }
 
@@ -694,7 +694,7 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, uint64_t n_
   const Fp q_prime_blind = tape.next();
   {
     Affine cm;
-    if ((rc = commit(ctx, W->q_prime, P.g, n, q_prime_blind, &cm))) return rc;
+    if ((rc = commit(ctx, W->q_prime, P.fb_g, n,q_prime_blind, &cm))) return rc;
     tr.write_point(cm);
   }
   const Fp x3 = tr.squeeze_challenge();
@@ -729,7 +729,7 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, uint64_t n_
     }
     const Fp s_blind = tape.next();
     Affine cm;
-    if ((rc = commit(ctx, sp, P.g, n, s_blind, &cm))) return rc;
+    if ((rc = commit(ctx, sp, P.fb_g, n,s_blind, &cm))) return rc;
     tr.write_point(cm);
     const Fp xi = tr.squeeze_challenge();
     const Fp z = tr.squeeze_challenge();
@@ -745,29 +745,31 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, uint64_t n_
     // b = powers of x3
     Fp* b = W->b_vec;
     if ((rc = affine_scan(ctx, nullptr, x3, nullptr, n, Fp::one(), b))) return rc;
-    Affine* g = W->g_fold;
-    ZK_CUDA(ctx, cudaMemcpyAsync(g, P.g, n * sizeof(Affine), cudaMemcpyDeviceToDevice, st));
+    // The folded generators G' are never materialised.  After j rounds
+    //     G'_i = sum_m [m = i mod len] s_m g_m,   s_m = prod_{r < j} u_r^(bit_{k-1-r}(m)),
+    // so L_j = <p'_hi, G'_lo> and R_j = <p'_lo, G'_hi> are MSMs over the ORIGINAL g with scalars
+    // c_m = p'[(m mod len) +- half] * s_m, supported on bit_{k-1-j}(m) = 0 (L) or 1 (R).  This keeps
+    // every MSM on the precomputed fixed-base tables and replaces halo2's
+    // `parallel_generator_collapse` (n scalar multiplications per proof) by elementwise updates of s.
+    Fp* svec = W->tmp_a;
+    Fp* cvec = W->tmp_b;
+    launch_map(ctx, n, [=] __device__(uint64_t m) { svec[m] = Fp::one(); });
+    const uint32_t idx_w = (uint32_t)n, idx_u = (uint32_t)n + 1;
     for (int j = 0; j < k; j++) {
       const uint64_t half = 1ull << (k - j - 1);
-      XYZZ lj, rj;
-      if ((rc = msm_run(ctx, pp + half, g, half, &lj))) return rc;
-      if ((rc = msm_run(ctx, pp, g + half, half, &rj))) return rc;
+      launch_map(ctx, n, [=] __device__(uint64_t m) {
+        uint64_t i = m & (2 * half - 1);
+        cvec[m] = (i < half ? pp[i + half] : pp[i - half]) * svec[m];
+      });
       Fp vl, vr;
       if ((rc = inner_product(ctx, pp + half, b, half, &vl))) return rc;
       if ((rc = inner_product(ctx, pp, b + half, half, &vr))) return rc;
       const Fp l_rand = tape.next(), r_rand = tape.next();
-      auto host_mul = [](const Affine& pt, const Fp& s) {
-        uint64_t e[4];
-        s.to_canonical(e);
-        XYZZ acc = XYZZ::identity();
-        for (int i = 254; i >= 0; i--) {
-          acc = acc.dbl();
-          if ((e[i >> 6] >> (i & 63)) & 1) acc = acc.add_affine(pt);
-        }
-        return acc;
-      };
-      lj = lj.add(host_mul(P.u, vl * z)).add(host_mul(P.w, l_rand));
-      rj = rj.add(host_mul(P.u, vr * z)).add(host_mul(P.w, r_rand));
+      const uint32_t extra_idx[2] = {idx_u, idx_w};
+      const Fp extra_l[2] = {vl * z, l_rand}, extra_r[2] = {vr * z, r_rand};
+      XYZZ lj, rj;
+      if ((rc = msm_fixed(ctx, P.fb_g, cvec, n, extra_l, extra_idx, 2, &lj, (uint32_t)half, 0))) return rc;
+      if ((rc = msm_fixed(ctx, P.fb_g, cvec, n, extra_r, extra_idx, 2, &rj, (uint32_t)half, 1))) return rc;
       tr.write_point(lj.to_affine());
       tr.write_point(rj.to_affine());
       const Fp u = tr.squeeze_challenge();
@@ -776,10 +778,9 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, uint64_t n_
         pp[i] = pp[i] + pp[i + half] * u_inv;
         b[i] = b[i] + b[i + half] * u;
       });
-      ScalarBits ub;
-      u.to_canonical(ub.v);
-      generator_collapse_kernel<<<(unsigned)((half + 127) / 128), 128, 0, st>>>(g, half, ub);
-      ctx->launches++;
+      launch_map(ctx, n, [=] __device__(uint64_t m) {
+        if (m & half) svec[m] = svec[m] * u;
+      });
       f = f + l_rand * u_inv + r_rand * u;
     }
     Fp c;

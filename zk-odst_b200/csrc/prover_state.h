@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "ec.cuh"
+#include "msm_fixed.h"
 #include "prover.h"
 
 namespace zkodst {
@@ -27,9 +28,10 @@ struct SelectorExpr {  // compress_selectors result: selector = q * prod_{r != r
 struct DeviceParams {
   int k = 0;
   uint64_t n = 0;
-  Affine* g = nullptr;           // n + 1 entries: g[0..n), then w
+  Affine* g = nullptr;           // n + 2 entries: g[0..n), then w, u
   Affine* g_lagrange = nullptr;  // n + 1 entries: g_lagrange[0..n), then w
   Affine w, u;
+  FixedBase fb_g, fb_gl;         // window tables over the two arrays above
 };
 
 struct DeviceKeys {
@@ -63,8 +65,7 @@ void free_keys(DeviceKeys& k);
 void free_workspace(void* ws);
 
 // commit: MSM(scalars || blind, bases || w) -> affine (host)
-int32_t commit(zk_ctx* ctx, const Fp* d_scalars, const Affine* d_bases_plus_w, uint64_t n, const Fp& blind,
-               Affine* out);
+int32_t commit(zk_ctx* ctx, const Fp* d_scalars, const FixedBase& fb, uint64_t n, const Fp& blind, Affine* out);
 // coefficients (n) -> evaluations on the extended coset zeta * <omega_ext> (en)
 int32_t coeff_to_extended(zk_ctx* ctx, const DeviceKeys& K, const Fp* coeffs, Fp* out);
 

@@ -25,6 +25,8 @@ static void free_state(void* p) {
   ProverState* s = (ProverState*)p;
   cudaFree(s->params.g);
   cudaFree(s->params.g_lagrange);
+  fixed_base_free(s->params.fb_g);
+  fixed_base_free(s->params.fb_gl);
   free_keys(s->keys);
   delete s;
 }
@@ -183,15 +185,25 @@ int32_t install_params(zk_ctx* ctx, int k, Affine* g, Affine* g_lagrange, const 
   }
   cudaFree(S->params.g);
   cudaFree(S->params.g_lagrange);
+  fixed_base_free(S->params.fb_g);
+  fixed_base_free(S->params.fb_gl);
+  S->has_params = false;
   S->params.k = k;
   S->params.n = 1ull << k;
   S->params.g = g;
   S->params.g_lagrange = g_lagrange;
   S->params.w = w;
   S->params.u = u;
-  ZK_CUDA(ctx, cudaMemcpyAsync(g + S->params.n, &S->params.w, sizeof(Affine), cudaMemcpyHostToDevice, ctx->stream));
-  ZK_CUDA(ctx, cudaMemcpyAsync(g_lagrange + S->params.n, &S->params.w, sizeof(Affine), cudaMemcpyHostToDevice,
-                               ctx->stream));
+  const uint64_t n = S->params.n;
+  // bases are stored as [g_0 .. g_{n-1}, w, u] and [gl_0 .. gl_{n-1}, w] so that a commitment's
+  // blinding term (and the IPA's U term) ride in the same MSM
+  ZK_CUDA(ctx, cudaMemcpyAsync(g + n, &S->params.w, sizeof(Affine), cudaMemcpyHostToDevice, ctx->stream));
+  ZK_CUDA(ctx, cudaMemcpyAsync(g + n + 1, &S->params.u, sizeof(Affine), cudaMemcpyHostToDevice, ctx->stream));
+  ZK_CUDA(ctx, cudaMemcpyAsync(g_lagrange + n, &S->params.w, sizeof(Affine), cudaMemcpyHostToDevice, ctx->stream));
+  int32_t rc = fixed_base_build(ctx, g, n + 2, &S->params.fb_g);
+  if (rc) return rc;
+  rc = fixed_base_build(ctx, g_lagrange, n + 1, &S->params.fb_gl);
+  if (rc) return rc;
   ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   S->has_params = true;
   return ZK_OK;
@@ -199,14 +211,10 @@ int32_t install_params(zk_ctx* ctx, int k, Affine* g, Affine* g_lagrange, const 
 
 }  // namespace
 
-int32_t commit(zk_ctx* ctx, const Fp* d_scalars, const Affine* d_bases_plus_w, uint64_t n, const Fp& blind,
-               Affine* out) {
-  int32_t rc = ensure_buf(ctx, ctx->misc_ws, 4096);
-  if (rc) return rc;
-  Fp* d_blind = (Fp*)ctx->misc_ws.ptr;
-  ZK_CUDA(ctx, cudaMemcpyAsync(d_blind, &blind, sizeof(Fp), cudaMemcpyHostToDevice, ctx->stream));
+int32_t commit(zk_ctx* ctx, const Fp* d_scalars, const FixedBase& fb, uint64_t n, const Fp& blind, Affine* out) {
+  const uint32_t w_index = (uint32_t)n;  // W follows the n base points in both tables
   XYZZ r;
-  rc = msm_run(ctx, d_scalars, d_bases_plus_w, n + 1, &r, d_blind);
+  int32_t rc = msm_fixed(ctx, fb, d_scalars, n, &blind, &w_index, 1, &r);
   if (rc) return rc;
   *out = r.to_affine();
   return ZK_OK;
@@ -255,8 +263,8 @@ extern "C" int32_t zk_params_generate_substitute(zk_ctx* ctx, int32_t k, const u
   ZK_CUDA(ctx, cudaMalloc((void**)&d_s, n * sizeof(Fp)));
   ZK_CUDA(ctx, cudaMalloc((void**)&d_sl, n * sizeof(Fp)));
   ZK_CUDA(ctx, cudaMalloc((void**)&d_table, table.size() * sizeof(Affine)));
-  ZK_CUDA(ctx, cudaMalloc((void**)&g, (n + 1) * sizeof(Affine)));
-  ZK_CUDA(ctx, cudaMalloc((void**)&gl, (n + 1) * sizeof(Affine)));
+  ZK_CUDA(ctx, cudaMalloc((void**)&g, (n + 2) * sizeof(Affine)));
+  ZK_CUDA(ctx, cudaMalloc((void**)&gl, (n + 2) * sizeof(Affine)));
   ZK_CUDA(ctx, cudaMemcpyAsync(d_raw, raw.data(), raw.size() * 8, cudaMemcpyHostToDevice, st));
   ZK_CUDA(ctx, cudaMemcpyAsync(d_table, table.data(), table.size() * sizeof(Affine), cudaMemcpyHostToDevice, st));
   const unsigned T = 128, blocks = (unsigned)((n + T - 1) / T);
@@ -292,8 +300,8 @@ extern "C" int32_t zk_params_load(zk_ctx* ctx, const uint8_t* bytes, uint64_t le
   Affine *g = nullptr, *gl = nullptr, *d_wu = nullptr;
   int* d_bad = nullptr;
   ZK_CUDA(ctx, cudaMalloc((void**)&d_bytes, len - 4));
-  ZK_CUDA(ctx, cudaMalloc((void**)&g, (n + 1) * sizeof(Affine)));
-  ZK_CUDA(ctx, cudaMalloc((void**)&gl, (n + 1) * sizeof(Affine)));
+  ZK_CUDA(ctx, cudaMalloc((void**)&g, (n + 2) * sizeof(Affine)));
+  ZK_CUDA(ctx, cudaMalloc((void**)&gl, (n + 2) * sizeof(Affine)));
   ZK_CUDA(ctx, cudaMalloc((void**)&d_wu, 2 * sizeof(Affine)));
   ZK_CUDA(ctx, cudaMalloc((void**)&d_bad, sizeof(int)));
   ZK_CUDA(ctx, cudaMemsetAsync(d_bad, 0, sizeof(int), st));
@@ -613,12 +621,12 @@ extern "C" int32_t zk_blake2f_keygen(zk_ctx* ctx, uint32_t rounds, uint64_t n_co
   K.fixed_commitments.resize(NUM_FIXED);
   K.sigma_commitments.resize(NUM_PERM);
   for (int c = 0; c < NUM_FIXED; c++) {
-    if ((rc = commit(ctx, K.fixed_values[c], S->params.g_lagrange, n, Fp::one(), &K.fixed_commitments[c]))) return rc;
+    if ((rc = commit(ctx, K.fixed_values[c], S->params.fb_gl, n, Fp::one(), &K.fixed_commitments[c]))) return rc;
     if ((rc = ntt_run(ctx, K.fixed_values[c], (uint32_t)n, K.fixed_polys[c], k, inv))) return rc;
     if ((rc = coeff_to_extended(ctx, K, K.fixed_polys[c], K.fixed_cosets[c]))) return rc;
   }
   for (int c = 0; c < NUM_PERM; c++) {
-    if ((rc = commit(ctx, K.sigma_values[c], S->params.g_lagrange, n, Fp::one(), &K.sigma_commitments[c]))) return rc;
+    if ((rc = commit(ctx, K.sigma_values[c], S->params.fb_gl, n, Fp::one(), &K.sigma_commitments[c]))) return rc;
     if ((rc = ntt_run(ctx, K.sigma_values[c], (uint32_t)n, K.sigma_polys[c], k, inv))) return rc;
     if ((rc = coeff_to_extended(ctx, K, K.sigma_polys[c], K.sigma_cosets[c]))) return rc;
   }

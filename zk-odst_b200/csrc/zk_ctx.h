@@ -31,7 +31,9 @@ struct NttTables {  // per-domain twiddle tables (device) and host constants
   Fp* tw_inv = nullptr;  // omega^-i
 };
 
-enum KernelClass { KC_WITNESS = 0, KC_MSM = 1, KC_NTT = 2, KC_QUOTIENT = 3, KC_COUNT = 8 };
+enum KernelClass {
+  KC_WITNESS = 0, KC_MSM = 1, KC_NTT = 2, KC_QUOTIENT = 3, KC_COLLAPSE = 4, KC_MSM_ACC = 5, KC_COUNT = 8
+};
 
 }  // namespace zkodst
 
@@ -42,8 +44,16 @@ struct zk_ctx {
   std::string err;
   uint64_t launches = 0;
   bool timing = false;
-  cudaEvent_t ev[2 * zkodst::KC_COUNT] = {};
-  bool ev_valid[zkodst::KC_COUNT] = {};
+  // timed regions since the last report: events come from a grow-only pool
+  struct Timed {
+    cudaEvent_t a, b;
+    int which;
+  };
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  std::vector<Timed> timed;
+  float last_ms[zkodst::KC_COUNT] = {};
+  bool last_valid[zkodst::KC_COUNT] = {};
   std::map<uint32_t, zkodst::DeviceRegionLayout> layouts;
   zkodst::DevBuf scratch_inputs, scratch_advice, scratch_digests;
   zkodst::DevBuf scratch_a, scratch_b, msm_ws, msm_out, ntt_tmp, scan_ws, eval_ws, misc_ws;
@@ -64,14 +74,21 @@ int32_t get_layout(zk_ctx* ctx, uint32_t rounds, DeviceRegionLayout** out);
 struct KernelTimer {  // CUDA-event bracket on the context's stream, only when timing is on
   zk_ctx* ctx;
   int which;
+  cudaEvent_t a = nullptr, b = nullptr;
   KernelTimer(zk_ctx* c, int w) : ctx(c), which(w) {
-    if (ctx->timing) cudaEventRecord(ctx->ev[2 * which], ctx->stream);
+    if (!ctx->timing) return;
+    if (ctx->ev_used + 2 > ctx->ev_pool.size()) {
+      ctx->ev_pool.resize(ctx->ev_pool.size() + 64, nullptr);
+      for (size_t i = ctx->ev_pool.size() - 64; i < ctx->ev_pool.size(); i++) cudaEventCreate(&ctx->ev_pool[i]);
+    }
+    a = ctx->ev_pool[ctx->ev_used++];
+    b = ctx->ev_pool[ctx->ev_used++];
+    cudaEventRecord(a, ctx->stream);
   }
   ~KernelTimer() {
-    if (ctx->timing) {
-      cudaEventRecord(ctx->ev[2 * which + 1], ctx->stream);
-      ctx->ev_valid[which] = true;
-    }
+    if (!a) return;
+    cudaEventRecord(b, ctx->stream);
+    ctx->timed.push_back(zk_ctx::Timed{a, b, which});
   }
 };
 
