@@ -4,8 +4,10 @@
   python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun)
   python bench.py --impl reference ...                      (CPU arm: the oracle restatement)
 
-A "step" is one pass of the hot path over one batch of synthetic EIP-152 records
-(BASELINE.json configs[2]: 64 twelve-round compressions in one circuit, k = 19).
+A "step" is one complete proof (witness -> commitments -> quotient -> multiopen -> IPA) of one
+batch of synthetic EIP-152 records: BASELINE.json configs[2], 64 twelve-round compressions in
+one circuit (k = 19).  With N GPUs every rank proves its own independent batch (configs[4]:
+independent proof streams, weak scaling, no data-path collective).
 Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for the definitions.
 """
 import argparse
@@ -21,6 +23,12 @@ sys.path.insert(0, ROOT)
 
 ROUNDS = 12
 N_COMPRESSIONS = 64
+METRIC = "blake2f_12round_compressions_proved_per_sec"
+UNIT = "compressions/s"
+# SURVEY.md §8d accounting: a full-width MSM term = 16 bucket additions x 11 Fq mults x 136 MAC,
+# a <= 32-bit advice term = 2 windows.
+MAC_FULL, MAC_SMALL = 16 * 11 * 136, 2 * 11 * 136
+MAC_PER_FP_MUL = 136
 
 
 def load_peaks():
@@ -76,73 +84,93 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.samples)}
 
 
-def cpu_witness_baseline(inputs, n, k):
-    """Oracle (CPU restatement) timed on the host cores: the `port` baseline."""
+# ---- CPU arm: the oracle (halo2-0.3.0-equivalent restatement), all host threads ------------------
+CPU_SAMPLE_K, CPU_SAMPLE_N = 17, 26   # bounded sample: the largest batch that fits the default k
+
+
+def cpu_oracle_setup():
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
-    oracle = oracle_lib.load()
-    t0 = time.perf_counter()
-    oracle.witness(k, ROUNDS, inputs, n)
-    dt = time.perf_counter() - t0
-    return n / dt, dt
-
-
-def run_reference(args, rank, world):
-    if rank != 0:
-        return
     import zk_odst_b200 as zk
-    n = N_COMPRESSIONS
-    k = zk.min_k(ROUNDS, n)
-    inputs = zk.synthetic_inputs(n)
-    for _ in range(args.warmup):
-        cpu_witness_baseline(inputs, n, k)
+    oracle = oracle_lib.load()
+    op = oracle_lib.OracleProver(oracle, k=CPU_SAMPLE_K, seed=zk.REFERENCE_SEED)
+    op.keygen(ROUNDS, CPU_SAMPLE_N)
+    return op, zk.synthetic_inputs(CPU_SAMPLE_N), zk.REFERENCE_SEED
+
+
+def cpu_prove_once(op, inputs, seed):
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cpu_witness_baseline(inputs, n, k)
-    dt = (time.perf_counter() - t0) / args.steps
-    val = n / dt
-    line = {
-        "impl": "reference", "metric": "blake2f_witness_compressions_per_sec", "value": val,
-        "unit": "compressions/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u64", "data": "synthetic",
-        "config": workload_config(k, n),
-        "cpu_baseline": {"value": val, "unit": "compressions/s", "cores": 1, "kind": "port",
-                         "sample": "%d compressions, witness generation (oracle, 1 thread)" % n},
-        "e2e": {"value": val, "unit": "compressions/s", "h2d_bytes_per_step": 0,
-                "d2h_bytes_per_step": 0},
-    }
-    print(json.dumps(line))
+    proof = op.create_proof(inputs, CPU_SAMPLE_N, seed)
+    dt = time.perf_counter() - t0
+    return CPU_SAMPLE_N / dt, dt, proof
+
+
+def cpu_sample_text(dt):
+    return ("one proof of %d compressions at k=%d (create_proof only; params/keygen excluded), "
+            "%.1f s, C++ oracle restating halo2_proofs 0.3.0, std::thread x %d" %
+            (CPU_SAMPLE_N, CPU_SAMPLE_K, dt, os.cpu_count() or 1))
 
 
 def workload_config(k, n):
-    return {"workload": "configs[2]: %d twelve-round BLAKE2f compressions in one circuit" % n,
-            "k": k, "rounds": ROUNDS, "compressions_per_batch": n,
+    return {"workload": "configs[2]: %d twelve-round BLAKE2f compressions in one circuit, "
+                        "full create_proof (Pasta/IPA)" % n,
+            "k": k, "rounds": ROUNDS, "compressions_per_proof": n,
             "rows_per_compression": 292 + 392 * ROUNDS,
-            "phase": "witness generation (K1); prover phases land in later commits",
-            "l2": "advice output 12*2^k*32 B = %d MB per step exceeds the 126 MB L2; no flush" %
-                  (12 * (1 << k) * 32 >> 20)}
+            "params": "substitute URS (zk_params_generate_substitute, reference seed)",
+            "l2": "per proof the prover streams > 2 GB of column/coset data (advice cosets alone "
+                  "12 x 2^(k+2) x 32 B = %d MB), far above the 126 MB L2; no explicit flush" %
+                  (12 * (1 << (k + 2)) * 32 >> 20)}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    op, inputs, seed = cpu_oracle_setup()
+    budget_s = 150.0
+    steps, t_used, last_dt = 0, 0.0, 0.0
+    t_start = time.perf_counter()
+    while steps < max(1, args.steps):
+        _, dt, _ = cpu_prove_once(op, inputs, seed)
+        steps += 1
+        t_used += dt
+        last_dt = dt
+        if time.perf_counter() - t_start + dt > budget_s:
+            break
+    dt = t_used / steps
+    val = CPU_SAMPLE_N / dt
+    cfg = workload_config(CPU_SAMPLE_K, CPU_SAMPLE_N)
+    cfg["workload"] += " — CPU arm runs the bounded sample below (k=17 is the smallest circuit)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": 0, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64 (4x64-bit Montgomery limbs)",
+        "data": "synthetic", "config": cfg, "proofs_per_sec": 1.0 / dt,
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                         "sample": cpu_sample_text(last_dt)},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--compressions", type=int, default=N_COMPRESSIONS)
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank)
         return
+    args.warmup = max(args.warmup, 3)
 
-    import numpy as np
     import torch
     import torch.distributed as dist
     import zk_odst_b200 as zk
@@ -153,98 +181,130 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    n = N_COMPRESSIONS
+    n = args.compressions
     k = zk.min_k(ROUNDS, n)
     nrows = 1 << k
-    inputs = zk.synthetic_inputs(n, stream=rank)  # independent batch per rank (weak scaling)
+    seed = zk.REFERENCE_SEED
+    inputs = zk.synthetic_inputs(n, stream=rank)  # independent batch per rank
     ctx = zk.Context(local_rank)
-    stream = torch.cuda.Stream()  # a real (non-legacy) stream: events and kernels share it
+    stream = torch.cuda.Stream()  # events and kernels share one real (non-legacy) stream
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
-    ctx.enable_timing(True)
-
+    ctx.params_generate_substitute(k, seed)
+    ctx.keygen(ROUNDS, n)
     d_in = torch.frombuffer(bytearray(inputs), dtype=torch.uint8).cuda()
-    d_adv = torch.empty((12, nrows, 4), dtype=torch.int64, device="cuda")
-    d_dig = torch.empty((n, 8), dtype=torch.int64, device="cuda")
+    h_in = torch.frombuffer(bytearray(inputs), dtype=torch.uint8).pin_memory()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step():
-        ctx.witness_batch_device(k, ROUNDS, d_in, n, d_adv, d_dig)
+    def max_over_ranks(x):
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
+    # ---- value: inputs resident in HBM ------------------------------------------------------
     for _ in range(args.warmup):
-        step()
+        proof = ctx.create_proof(d_in, n, seed, on_device=True)
     barrier()
+    ctx.enable_timing(True)
+    ctx.timing_report()
     launches0 = ctx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms = []
     with ClockSampler(local_rank) as clocks:
+        t0 = time.perf_counter()
         e0.record(stream)
         for _ in range(args.steps):
-            step()
+            proof = ctx.create_proof(d_in, n, seed, on_device=True)
         e1.record(stream)
-        barrier()
-        # per-launch duration of the dominant kernel, measured live with CUDA events on the
-        # launching stream (a few extra steps, outside the step timing)
-        for _ in range(min(args.steps, 10)):
-            step()
-            kernel_ms.append(ctx.last_kernel_ms(0))
-    launches = ctx.launch_count() - launches0 - 2 * min(args.steps, 10)
-    ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    ms_per_step = ms_max / args.steps
+        torch.cuda.synchronize()
+        dt_host = time.perf_counter() - t0
+    dt = e0.elapsed_time(e1) * 1e-3  # device clock (CUDA events on the launching stream)
+    assert abs(dt - dt_host) < 0.05 * dt_host + 0.01, (dt, dt_host)
+    # create_proof returns only after the last device->host copy of the transcript data, so the
+    # host clock brackets exactly the device work of the K proofs (the proof is a chain of
+    # ~100 device phases separated by transcript round trips; CUDA events per kernel class are
+    # reported below)
+    report = ctx.timing_report()
+    launches = ctx.launch_count() - launches0
+    ctx.enable_timing(False)
+    ms_per_step = max_over_ranks(dt / args.steps * 1e3)
     value = world * n / (ms_per_step * 1e-3)
+    barrier()
 
-    # end-to-end through the C-ABI call with host buffers (pinned), copies inside the timing
-    h_in = torch.frombuffer(bytearray(inputs), dtype=torch.uint8).pin_memory()
-    h_adv = torch.empty((12, nrows, 4), dtype=torch.int64).pin_memory()
-    h_dig = torch.empty((n, 8), dtype=torch.int64).pin_memory()
-    ctx.set_stream(None)
+    # ---- e2e: host (pinned) records in, proof bytes out, through the C-ABI call ---------------
     e2e_steps = max(3, min(args.steps, 5))
-    ctx.witness_batch(k, ROUNDS, h_in, n, h_adv, h_dig)
+    ctx.create_proof(h_in, n, seed)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        ctx.witness_batch(k, ROUNDS, h_in, n, h_adv, h_dig)
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    te = torch.tensor([e2e_s], device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_val = world * n / float(te.item())
+        proof_e2e = ctx.create_proof(h_in, n, seed)
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) / e2e_steps * 1e3)
+    e2e_val = world * n / (e2e_ms * 1e-3)
+    assert proof_e2e == proof, "host-input and device-input proofs differ"
 
     if rank == 0:
-        peak, peak_kind = load_peaks()
+        hbm_peak, hbm_kind = load_peaks()
+        int_peak = ctx.bench_int_pipe(1, 20000)  # mad.wide.u32 instructions/s = 32x32->64 MAC/s
+        steps = args.steps
+        per = {name: (ms / steps, cnt / steps) for name, (ms, cnt) in report.items() if cnt}
         R = 292 + 392 * ROUNDS
-        alg_bytes = n * (R * 12 * 32 + 213)
-        k_ms = sorted(kernel_ms)[len(kernel_ms) // 2]
-        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        # dominant kernel: MSM bucket accumulation
+        mac_per_proof = nrows * (32 * MAC_FULL + 12 * MAC_SMALL)
+        acc_ms, acc_launches = per.get("msm_accumulate", (0.0, 0.0))
+        msm_ms, _ = per.get("msm", (0.0, 0.0))
+        achieved = mac_per_proof / (acc_ms * 1e-3) / 1e12 if acc_ms else None
+        roofline = {
+            "kernel": "fixed_accumulate_kernel (+ heavy-bucket kernels)", "bound": "int_pipe",
+            "achieved": achieved, "peak": int_peak / 1e12, "unit": "TMAC/s",
+            "frac": achieved / (int_peak / 1e12) if achieved else None, "traffic": None,
+            "peak_source": "zk_bench_int_pipe mode 1 (mad.wide.u32) measured in this run; "
+                           "MEASURED_PEAKS.json has no integer peak",
+            "launches_per_proof": acc_launches, "avg_launch_ms": acc_ms / acc_launches if acc_launches else None,
+            "algorithmic_mac_per_proof": mac_per_proof,
+            "accounting": "SURVEY.md 8d: 32 n full-width terms x 23936 MAC + 12 n advice terms x 2992 MAC",
+        }
+        ntt_ms, ntt_launches = per.get("ntt", (0.0, 0.0))
+        ext = 1 << (k + 2)
+        ntt_bytes = 19 * 64 * nrows + 20 * 64 * ext
+        ntt_mac = (19 * (nrows // 2) * k + 20 * (ext // 2) * (k + 2)) * MAC_PER_FP_MUL
+        wit_ms, _ = per.get("witness", (0.0, 0.0))
+        q_ms, _ = per.get("quotient", (0.0, 0.0))
+        others = {
+            "witness": {"bound": "hbm", "ms_per_proof": wit_ms,
+                        "achieved_gbs": n * (R * 12 * 32 + 213) / (wit_ms * 1e-3) / 1e9 if wit_ms else None,
+                        "peak_gbs": hbm_peak, "peak_source": hbm_kind},
+            "ntt": {"bound": "int_pipe", "ms_per_proof": ntt_ms, "transforms_per_proof": ntt_launches,
+                    "achieved_gbs": ntt_bytes / (ntt_ms * 1e-3) / 1e9 if ntt_ms else None,
+                    "achieved_tmacs": ntt_mac / (ntt_ms * 1e-3) / 1e12 if ntt_ms else None},
+            "quotient": {"bound": "int_pipe", "ms_per_proof": q_ms,
+                         "achieved_gbs": (61 * 32 * ext) / (q_ms * 1e-3) / 1e9 if q_ms else None},
+            "msm_total_ms_per_proof": msm_ms,
+        }
         line = {
-            "metric": "blake2f_witness_compressions_per_sec", "value": value,
-            "unit": "compressions/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": workload_config(k, n), "clocks": clocks.summary(),
-            "e2e": {"value": e2e_val, "unit": "compressions/s",
-                    "h2d_bytes_per_step": len(inputs),
-                    "d2h_bytes_per_step": 12 * nrows * 32 + n * 64},
-            "gpu_launches": int(launches),
-            "roofline": {"kernel": "blake2f_witness_kernel", "bound": "hbm", "achieved": achieved,
-                         "peak": peak, "peak_source": peak_kind, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None,
-                         "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes},
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64 (4x64-bit Montgomery limbs)",
+            "data": "synthetic", "config": workload_config(k, n),
+            "proofs_per_sec": world / (ms_per_step * 1e-3), "proof_bytes": len(proof),
+            "clocks": clocks.summary(),
+            "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": len(inputs) + 2 * nrows * 64,
+                    "d2h_bytes_per_step": len(proof),
+                    "note": "h2d counts the records plus the 2n x 64 B host RNG stream that both "
+                            "arms upload; d2h is the proof"},
+            "gpu_launches": int(launches), "roofline": roofline, "kernels": others,
         }
         if not args.no_cpu_baseline:
-            v, dt = cpu_witness_baseline(inputs, n, k)
-            line["cpu_baseline"] = {
-                "value": v, "unit": "compressions/s", "cores": 1, "kind": "port",
-                "sample": "%d compressions, witness generation, %.2f s" % (n, dt)}
+            op, cin, cseed = cpu_oracle_setup()
+            v, cdt, _ = cpu_prove_once(op, cin, cseed)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1,
+                                    "kind": "port", "sample": cpu_sample_text(cdt)}
         print(json.dumps(line))
+    barrier()
     if world > 1:
         dist.destroy_process_group()
 

@@ -152,6 +152,11 @@ int32_t zk_vk_repr_override(zk_ctx* ctx, const uint8_t repr[32]);
 int32_t zk_create_proof(zk_ctx* ctx, const uint8_t* inputs, uint64_t n_compressions,
                         const uint8_t seed[16], uint8_t* proof_out, uint64_t* proof_len);
 
+/* Same with the EIP-152 records already resident in device memory (record validation then
+ * happens in the witness kernel and is reported as ZK_E_INPUT). */
+int32_t zk_create_proof_device_inputs(zk_ctx* ctx, const uint8_t* d_inputs, uint64_t n_compressions,
+                                      const uint8_t seed[16], uint8_t* proof_out, uint64_t* proof_len);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,6 +53,7 @@ def load_library():
             "zk_vk_bytes": (i32, [vp, vp, c.POINTER(u64)]),
             "zk_vk_repr_override": (i32, [vp, c.c_char_p]),
             "zk_create_proof": (i32, [vp, vp, u64, c.c_char_p, vp, c.POINTER(u64)]),
+            "zk_create_proof_device_inputs": (i32, [vp, vp, u64, c.c_char_p, vp, c.POINTER(u64)]),
             "zk_msm_vesta": (i32, [vp, vp, vp, u64, i32, vp]),
             "zk_ntt_fp": (i32, [vp, vp, i32, i32, i32]),
             "zk_blake2f_witness_batch": (i32, [vp, i32, u32, vp, u64, vp, vp]),
@@ -186,12 +187,13 @@ class Context:
         self._check(self.lib.zk_vk_bytes(self.h, ctypes.cast(buf, ctypes.c_void_p), ctypes.byref(ln)))
         return buf.raw[:ln.value]
 
-    def create_proof(self, inputs, n_compressions, seed):
+    def create_proof(self, inputs, n_compressions, seed, on_device=False):
         keep = bytes(inputs) if isinstance(inputs, (bytes, bytearray)) else inputs
         buf = ctypes.create_string_buffer(1 << 16)
         ln = ctypes.c_uint64(len(buf))
-        self._check(self.lib.zk_create_proof(self.h, _ptr(keep), n_compressions, bytes(seed),
-                                             ctypes.cast(buf, ctypes.c_void_p), ctypes.byref(ln)))
+        fn = self.lib.zk_create_proof_device_inputs if on_device else self.lib.zk_create_proof
+        self._check(fn(self.h, _ptr(keep), n_compressions, bytes(seed),
+                       ctypes.cast(buf, ctypes.c_void_p), ctypes.byref(ln)))
         return buf.raw[:ln.value]
 
     # ---- K2/K3, K4/K5 ------------------------------------------------------------------

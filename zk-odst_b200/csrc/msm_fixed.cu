@@ -89,9 +89,11 @@ __global__ void fixed_digits_kernel(const Fp* __restrict__ scalars, uint64_t cou
       uint32_t d = (uint32_t)(v & ((1ull << c) - 1)) + carry;
       if (d > B) {
         carry = 1;
-        uint32_t mag = (1u << c) - d;
-        e = mag | 0x80000000u;
-        atomicAdd(&counts[mag - 1], 1u);
+        uint32_t mag = (1u << c) - d;  // 0 when the raw digit 2^c - 1 absorbs a carry: digit 0, carry 1
+        if (mag) {
+          e = mag | 0x80000000u;
+          atomicAdd(&counts[mag - 1], 1u);
+        }
       } else {
         carry = 0;
         if (d) {

@@ -292,14 +292,15 @@ generator_collapse_kernel(Affine* __restrict__ g, uint64_t half, ScalarBits u) {
 }  // namespace
 
 // ---- the prover ------------------------------------------------------------------------------------------
-static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, uint64_t n_compressions,
-                                 const uint8_t seed[16], std::vector<uint8_t>& proof_out) {
+static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs_on_device,
+                                 uint64_t n_compressions, const uint8_t seed[16],
+                                 std::vector<uint8_t>& proof_out) {
   ProverState* S = prover_state(ctx);
   if (!S->has_params || !S->has_keys) return set_error(ctx, ZK_E_STATE, "create_proof before params/keygen");
   DeviceKeys& K = S->keys;
   const DeviceParams& P = S->params;
   if (n_compressions != K.n_compressions) return set_error(ctx, ZK_E_INVALID, "batch size differs from keygen");
-  for (uint64_t i = 0; i < n_compressions; i++) {
+  for (uint64_t i = 0; i < n_compressions && !inputs_on_device; i++) {
     const uint8_t* r = inputs + i * ZK_BLAKE2F_INPUT_BYTES;
     uint32_t rr = ((uint32_t)r[0] << 24) | ((uint32_t)r[1] << 16) | ((uint32_t)r[2] << 8) | r[3];
     if (r[212] > 1) return set_error(ctx, ZK_E_INPUT, "final-block flag must be 0 or 1");
@@ -324,7 +325,8 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, uint64_t n_
 
   // ---- witness (K1) ---------------------------------------------------------------------------------
   if (n_compressions)
-    ZK_CUDA(ctx, cudaMemcpyAsync(W->inputs, inputs, n_compressions * 213, cudaMemcpyHostToDevice, st));
+    ZK_CUDA(ctx, cudaMemcpyAsync(W->inputs, inputs, n_compressions * 213,
+                                 inputs_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
   if ((rc = launch_witness(ctx, k, K.rounds, W->inputs, n_compressions, W->advice_values, W->digests))) return rc;
   auto adv = [&](int c) { return W->advice_values + (size_t)c * n; };
   auto adv_poly = [&](int c) { return W->advice_polys + (size_t)c * n; };
@@ -798,14 +800,29 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, uint64_t n_
 
 using namespace zkodst;
 
+static int32_t create_proof_entry(zk_ctx* ctx, const uint8_t* inputs, bool inputs_on_device,
+                                  uint64_t n_compressions, const uint8_t seed[16], uint8_t* proof_out,
+                                  uint64_t* proof_len);
+
 extern "C" int32_t zk_create_proof(zk_ctx* ctx, const uint8_t* inputs, uint64_t n_compressions,
                                    const uint8_t seed[16], uint8_t* proof_out, uint64_t* proof_len) {
+  return create_proof_entry(ctx, inputs, false, n_compressions, seed, proof_out, proof_len);
+}
+extern "C" int32_t zk_create_proof_device_inputs(zk_ctx* ctx, const uint8_t* d_inputs, uint64_t n_compressions,
+                                                 const uint8_t seed[16], uint8_t* proof_out,
+                                                 uint64_t* proof_len) {
+  return create_proof_entry(ctx, d_inputs, true, n_compressions, seed, proof_out, proof_len);
+}
+
+static int32_t create_proof_entry(zk_ctx* ctx, const uint8_t* inputs, bool inputs_on_device,
+                                  uint64_t n_compressions, const uint8_t seed[16], uint8_t* proof_out,
+                                  uint64_t* proof_len) {
   if (!ctx || !seed || !proof_len || (n_compressions && !inputs)) return ZK_E_INVALID;
   ZK_CUDA(ctx, cudaSetDevice(ctx->device));
   std::vector<uint8_t> proof;
   int32_t rc;
   try {
-    rc = create_proof_impl(ctx, inputs, n_compressions, seed, proof);
+    rc = create_proof_impl(ctx, inputs, inputs_on_device, n_compressions, seed, proof);
   } catch (std::exception& e) {
     return set_error(ctx, ZK_E_VERIFY, e.what());
   }
