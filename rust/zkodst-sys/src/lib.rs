@@ -1,0 +1,43 @@
+//! `extern "C"` declarations mirroring include/zkodst.h one to one.
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_void};
+
+#[repr(C)]
+pub struct zk_ctx {
+    _private: [u8; 0],
+}
+
+pub const ZK_OK: i32 = 0;
+pub const ZK_E_INVALID: i32 = -1;
+pub const ZK_E_CUDA: i32 = -2;
+pub const ZK_E_NOMEM: i32 = -3;
+pub const ZK_E_ROWS: i32 = -4;
+pub const ZK_E_INPUT: i32 = -5;
+pub const ZK_E_STATE: i32 = -6;
+pub const ZK_E_VERIFY: i32 = -7;
+pub const ZK_E_BUFFER: i32 = -8;
+pub const ZK_BLAKE2F_INPUT_BYTES: usize = 213;
+
+extern "C" {
+    pub fn zk_ctx_create(device_id: i32, out: *mut *mut zk_ctx) -> i32;
+    pub fn zk_ctx_destroy(ctx: *mut zk_ctx);
+    pub fn zk_last_error(ctx: *const zk_ctx) -> *const c_char;
+    pub fn zk_ctx_set_stream(ctx: *mut zk_ctx, cuda_stream: *mut c_void) -> i32;
+    pub fn zk_ctx_synchronize(ctx: *mut zk_ctx) -> i32;
+    pub fn zk_ctx_launch_count(ctx: *const zk_ctx) -> u64;
+    pub fn zk_blake2f_rows_per_compression(rounds: u32, rows: *mut u64) -> i32;
+    pub fn zk_blake2f_min_k(rounds: u32, n_compressions: u64, k: *mut i32) -> i32;
+    pub fn zk_blake2f_witness_batch(ctx: *mut zk_ctx, k: i32, rounds: u32, inputs: *const u8,
+        n_compressions: u64, advice_out: *mut c_void, digests_out: *mut u64) -> i32;
+    pub fn zk_msm_vesta(ctx: *mut zk_ctx, scalars: *const c_void, bases: *const c_void, n: u64,
+        on_device: i32, out_affine: *mut c_void) -> i32;
+    pub fn zk_ntt_fp(ctx: *mut zk_ctx, data: *mut c_void, log_n: i32, inverse: i32, on_device: i32) -> i32;
+    pub fn zk_params_generate_substitute(ctx: *mut zk_ctx, k: i32, seed: *const u8) -> i32;
+    pub fn zk_params_load(ctx: *mut zk_ctx, bytes: *const u8, len: u64) -> i32;
+    pub fn zk_params_write(ctx: *mut zk_ctx, out: *mut u8, len: *mut u64) -> i32;
+    pub fn zk_blake2f_keygen(ctx: *mut zk_ctx, rounds: u32, n_compressions: u64) -> i32;
+    pub fn zk_vk_bytes(ctx: *mut zk_ctx, out: *mut u8, len: *mut u64) -> i32;
+    pub fn zk_vk_repr_override(ctx: *mut zk_ctx, repr: *const u8) -> i32;
+    pub fn zk_create_proof(ctx: *mut zk_ctx, inputs: *const u8, n_compressions: u64,
+        seed: *const u8, proof_out: *mut u8, proof_len: *mut u64) -> i32;
+}
