@@ -53,6 +53,14 @@ struct XYZZ {  // 128 bytes; identity has zz == 0
     Fq y3 = m * (s - x3) - w * y;
     return XYZZ{x3, y3, v * zz, w * zzz};
   }
+  // same x: doubling or P + (-P); kept out of line on the device so the accumulation loops stay small
+#if defined(__CUDACC__)
+  __host__ __device__ __noinline__
+#endif
+  static XYZZ add_affine_same_x(const Affine& p, const Fq& r) {
+    if (r.is_zero()) return dbl_affine(p);
+    return identity();
+  }
   // this + affine                                                    [madd-2008-s]
   ZK_HD XYZZ add_affine(const Affine& p) const {
     if (p.is_identity()) return *this;
@@ -61,16 +69,20 @@ struct XYZZ {  // 128 bytes; identity has zz == 0
     Fq s2 = p.y * zzz;
     Fq pp_ = u2 - x;
     Fq r = s2 - y;
-    if (pp_.is_zero()) {
-      if (r.is_zero()) return dbl_affine(p);
-      return identity();
-    }
+    if (pp_.is_zero()) return add_affine_same_x(p, r);
     Fq pp = pp_.sqr();
     Fq ppp = pp_ * pp;
     Fq q = x * pp;
     Fq x3 = r.sqr() - ppp - q.dbl();
     Fq y3 = r * (q - x3) - y * ppp;
     return XYZZ{x3, y3, zz * pp, zzz * ppp};
+  }
+#if defined(__CUDACC__)
+  __host__ __device__ __noinline__
+#endif
+  static XYZZ add_same_x(const XYZZ& a, const Fq& r) {
+    if (r.is_zero()) return a.dbl();
+    return identity();
   }
   // this + other                                                     [add-2008-s]
   ZK_HD XYZZ add(const XYZZ& o) const {
@@ -82,10 +94,7 @@ struct XYZZ {  // 128 bytes; identity has zz == 0
     Fq s2 = o.y * zzz;
     Fq pp_ = u2 - u1;
     Fq r = s2 - s1;
-    if (pp_.is_zero()) {
-      if (r.is_zero()) return dbl();
-      return identity();
-    }
+    if (pp_.is_zero()) return add_same_x(*this, r);
     Fq pp = pp_.sqr();
     Fq ppp = pp_ * pp;
     Fq q = u1 * pp;

@@ -9,6 +9,9 @@
 #include <cstring>
 
 #include "field_consts.h"
+#if defined(__CUDACC__)
+#include "mont_ptx.cuh"
+#endif
 
 #if defined(__CUDACC__)
 #define ZK_HD __host__ __device__ __forceinline__
@@ -61,6 +64,9 @@ struct alignas(16) Fe {
   }
 
   ZK_HD Fe operator+(const Fe& o) const {
+#if defined(__CUDA_ARCH__)
+    return add_device(o);
+#else
     Fe r;
     u128 c = (u128)l[0] + o.l[0];
     r.l[0] = (uint64_t)c;
@@ -73,8 +79,12 @@ struct alignas(16) Fe {
     // MOD < 2^255 so the sum of two reduced elements never carries out of 256 bits
     if (geq_mod(r.l)) sub_mod_raw(r.l);
     return r;
+#endif
   }
   ZK_HD Fe operator-(const Fe& o) const {
+#if defined(__CUDA_ARCH__)
+    return sub_device(o);
+#else
     Fe r;
     u128 d = (u128)l[0] - o.l[0];
     r.l[0] = (uint64_t)d;
@@ -95,13 +105,81 @@ struct alignas(16) Fe {
       r.l[3] = (uint64_t)c;
     }
     return r;
+#endif
   }
   ZK_HD Fe neg() const { return zero() - *this; }
   ZK_HD Fe dbl() const { return *this + *this; }
 
-  // Montgomery product, CIOS with 64-bit limbs.  Result < MOD for inputs < MOD
-  // (and for one input < 2^256 when the other is < MOD).
+  // Montgomery product.  Both operands must be < MOD (the device path drops no carries only
+  // under that bound; the portable CIOS below also tolerates one operand < 2^256).
   ZK_HD Fe operator*(const Fe& o) const {
+#if defined(__CUDA_ARCH__)
+    return mul_device(o);
+#else
+    return mul_portable(o);
+#endif
+  }
+#if defined(__CUDACC__)
+  // Device product: PTX carry chains over 32-bit limbs (mont_ptx.cuh), one asm statement per row.
+  __device__ __forceinline__ Fe mul_device(const Fe& o) const {
+    uint32_t a[8], E[8], O[8];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      a[2 * i] = (uint32_t)l[i];
+      a[2 * i + 1] = (uint32_t)(l[i] >> 32);
+    }
+    if constexpr (P::MOD[0] == FpParams::MOD[0]) {
+      montptx::mont_first_row_fp(E, O, a, (uint32_t)o.l[0]);
+      montptx::mont_row_fp(O, E, a, (uint32_t)(o.l[0] >> 32));
+      montptx::mont_row_fp(E, O, a, (uint32_t)o.l[1]);
+      montptx::mont_row_fp(O, E, a, (uint32_t)(o.l[1] >> 32));
+      montptx::mont_row_fp(E, O, a, (uint32_t)o.l[2]);
+      montptx::mont_row_fp(O, E, a, (uint32_t)(o.l[2] >> 32));
+      montptx::mont_row_fp(E, O, a, (uint32_t)o.l[3]);
+      montptx::mont_row_fp(O, E, a, (uint32_t)(o.l[3] >> 32));
+    } else {
+      montptx::mont_first_row_fq(E, O, a, (uint32_t)o.l[0]);
+      montptx::mont_row_fq(O, E, a, (uint32_t)(o.l[0] >> 32));
+      montptx::mont_row_fq(E, O, a, (uint32_t)o.l[1]);
+      montptx::mont_row_fq(O, E, a, (uint32_t)(o.l[1] >> 32));
+      montptx::mont_row_fq(E, O, a, (uint32_t)o.l[2]);
+      montptx::mont_row_fq(O, E, a, (uint32_t)(o.l[2] >> 32));
+      montptx::mont_row_fq(E, O, a, (uint32_t)o.l[3]);
+      montptx::mont_row_fq(O, E, a, (uint32_t)(o.l[3] >> 32));
+    }
+    montptx::mont_merge(E, O);
+    if constexpr (P::MOD[0] == FpParams::MOD[0]) montptx::final_sub_fp(E); else montptx::final_sub_fq(E);
+    return pack(E);
+  }
+  __device__ __forceinline__ static Fe pack(const uint32_t (&w)[8]) {
+    Fe r;
+#pragma unroll
+    for (int i = 0; i < 4; i++) r.l[i] = (uint64_t)w[2 * i] | ((uint64_t)w[2 * i + 1] << 32);
+    return r;
+  }
+  __device__ __forceinline__ void unpack(uint32_t (&w)[8]) const {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      w[2 * i] = (uint32_t)l[i];
+      w[2 * i + 1] = (uint32_t)(l[i] >> 32);
+    }
+  }
+  __device__ __forceinline__ Fe add_device(const Fe& o) const {
+    uint32_t a[8], b[8], r[8];
+    unpack(a);
+    o.unpack(b);
+    if constexpr (P::MOD[0] == FpParams::MOD[0]) montptx::add_fp(r, a, b); else montptx::add_fq(r, a, b);
+    return pack(r);
+  }
+  __device__ __forceinline__ Fe sub_device(const Fe& o) const {
+    uint32_t a[8], b[8], r[8];
+    unpack(a);
+    o.unpack(b);
+    if constexpr (P::MOD[0] == FpParams::MOD[0]) montptx::sub_fp(r, a, b); else montptx::sub_fq(r, a, b);
+    return pack(r);
+  }
+#endif
+  ZK_HD Fe mul_portable(const Fe& o) const {
     uint64_t t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -144,7 +222,13 @@ struct alignas(16) Fe {
   }
   // 512-bit little-endian integer reduced mod MOD (ff::FromUniformBytes<64>, Field::random)
   ZK_HD static Fe from_u512(const uint64_t v[8]) {
+    // the device product requires both operands < MOD; a raw 256-bit word is < 4 MOD
     Fe lo{{v[0], v[1], v[2], v[3]}}, hi{{v[4], v[5], v[6], v[7]}};
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      if (geq_mod(lo.l)) sub_mod_raw(lo.l);
+      if (geq_mod(hi.l)) sub_mod_raw(hi.l);
+    }
     return lo * r2() + hi * r3();
   }
   ZK_HD Fe pow_u64(uint64_t e) const {

@@ -69,11 +69,38 @@ __global__ void __launch_bounds__(128) fieldmul_kernel(uint64_t* out, uint32_t i
   Fq r = a + b + c + d;
   out[blockIdx.x * blockDim.x + threadIdx.x] = r.l[0] ^ r.l[3];
 }
-__global__ void __launch_bounds__(128) madd_kernel(uint64_t* out, uint32_t iters, uint64_t seed) {
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) madd_kernel(uint64_t* out, uint32_t iters, uint64_t seed) {
   Affine p{Fq{{seed + threadIdx.x, 2, 3, 4}}, Fq{{5, seed ^ blockIdx.x, 7, 8}}};
   XYZZ acc = XYZZ::from_affine(Affine{Fq{{11, 12, 13, 14}}, Fq{{1, 2, 3, 5}}});
   for (uint32_t i = 0; i < iters; i++) {
     acc = acc.add_affine(p);
+    p.x.l[0] += i;
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc.x.l[0] ^ acc.zzz.l[3];
+}
+
+// mode 5: the same mixed addition with the field product as a real call (small loop body: the
+// instruction-cache footprint drops from ~40 KB to a few KB at the price of call overhead)
+__device__ __noinline__ Fq fq_mul_call(Fq a, Fq b) { return a * b; }
+__device__ __forceinline__ XYZZ add_affine_calls(const XYZZ& a, const Affine& p) {
+  Fq u2 = fq_mul_call(p.x, a.zz);
+  Fq s2 = fq_mul_call(p.y, a.zzz);
+  Fq pp_ = u2 - a.x;
+  Fq r = s2 - a.y;
+  if (pp_.is_zero()) return XYZZ::add_affine_same_x(p, r);
+  Fq pp = fq_mul_call(pp_, pp_);
+  Fq ppp = fq_mul_call(pp_, pp);
+  Fq q = fq_mul_call(a.x, pp);
+  Fq x3 = fq_mul_call(r, r) - ppp - q.dbl();
+  Fq y3 = fq_mul_call(r, q - x3) - fq_mul_call(a.y, ppp);
+  return XYZZ{x3, y3, fq_mul_call(a.zz, pp), fq_mul_call(a.zzz, ppp)};
+}
+__global__ void __launch_bounds__(128) madd_calls_kernel(uint64_t* out, uint32_t iters, uint64_t seed) {
+  Affine p{Fq{{seed + threadIdx.x, 2, 3, 4}}, Fq{{5, seed ^ blockIdx.x, 7, 8}}};
+  XYZZ acc = XYZZ::from_affine(Affine{Fq{{11, 12, 13, 14}}, Fq{{1, 2, 3, 5}}});
+  for (uint32_t i = 0; i < iters; i++) {
+    acc = add_affine_calls(acc, p);
     p.x.l[0] += i;
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = acc.x.l[0] ^ acc.zzz.l[3];
@@ -86,9 +113,9 @@ using namespace zkodst;
 
 extern "C" int32_t zk_bench_int_pipe(zk_ctx* ctx, int32_t mode, uint32_t iters,
                                      double* instr_per_sec) {
-  if (!ctx || !instr_per_sec || mode < 0 || mode > 4) return ZK_E_INVALID;
+  if (!ctx || !instr_per_sec || mode < 0 || mode > 8) return ZK_E_INVALID;
   ZK_CUDA(ctx, cudaSetDevice(ctx->device));
-  const int blocks = ctx->sm_count * 8, threads = mode >= 3 ? 128 : 256;
+  const int blocks = ctx->sm_count * 120, threads = mode >= 3 ? 128 : 256;
   int32_t rc = ensure_buf(ctx, ctx->scratch_digests, (size_t)blocks * threads * 8);
   if (rc) return rc;
   uint32_t* out = (uint32_t*)ctx->scratch_digests.ptr;
@@ -102,7 +129,11 @@ extern "C" int32_t zk_bench_int_pipe(zk_ctx* ctx, int32_t mode, uint32_t iters,
     if (mode == 1) imad_kernel<1><<<blocks, threads, 0, ctx->stream>>>(out, iters, 12345u + rep);
     if (mode == 2) imad_kernel<2><<<blocks, threads, 0, ctx->stream>>>(out, iters, 12345u + rep);
     if (mode == 3) fieldmul_kernel<<<blocks, threads, 0, ctx->stream>>>((uint64_t*)out, iters, 12345u + rep);
-    if (mode == 4) madd_kernel<<<blocks, threads, 0, ctx->stream>>>((uint64_t*)out, iters, 12345u + rep);
+    if (mode == 4) madd_kernel<4><<<blocks, threads, 0, ctx->stream>>>((uint64_t*)out, iters, 12345u + rep);
+    if (mode == 6) madd_kernel<5><<<blocks, threads, 0, ctx->stream>>>((uint64_t*)out, iters, 12345u + rep);
+    if (mode == 7) madd_kernel<6><<<blocks, threads, 0, ctx->stream>>>((uint64_t*)out, iters, 12345u + rep);
+    if (mode == 8) madd_kernel<8><<<blocks, threads, 0, ctx->stream>>>((uint64_t*)out, iters, 12345u + rep);
+    if (mode == 5) madd_calls_kernel<<<blocks, threads, 0, ctx->stream>>>((uint64_t*)out, iters, 12345u + rep);
     ctx->launches++;
     ZK_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
     ZK_CUDA(ctx, cudaEventSynchronize(e1));
@@ -112,7 +143,7 @@ extern "C" int32_t zk_bench_int_pipe(zk_ctx* ctx, int32_t mode, uint32_t iters,
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
-  double per_iter = mode == 3 ? 4.0 : (mode == 4 ? 1.0 : 64.0);  // field mults / madds / instructions
+  double per_iter = mode == 3 ? 4.0 : (mode >= 4 ? 1.0 : 64.0);  // field mults / madds / instructions
   double instr = (double)blocks * threads * (double)iters * per_iter;
   *instr_per_sec = instr / (best * 1e-3);
   return ZK_OK;

@@ -1,4 +1,4 @@
-// K2/K3/K11 — fixed-base Pippenger MSM with precomputed window tables.
+// K2/K3/K11 — batched fixed-base Pippenger MSM with precomputed window tables.
 //
 // Every commitment of the proof is an MSM over one of two fixed bases, g or g_lagrange
 // (`Params::commit` / `Params::commit_lagrange`, halo2_proofs 0.3.0; reached from
@@ -7,38 +7,64 @@
 // tabulated once per params (`FixedBase`), which turns the classic per-window bucket sets into
 // ONE set of 2^(c-1) buckets shared by all windows:
 //     sum_i s_i G_i = sum_b b * ( sum_{(i,w): |d_iw| = b} sgn(d_iw) * T[w][i] )
-// so there is a single bucket reduction per MSM and no doubling chain.
+// so there is a single bucket reduction per MSM and no doubling chain.  Several MSMs over the
+// same base (the 12 advice columns, the L/R pair of an IPA round, the h pieces) run as ONE
+// pipeline over `nb * 2^(c-1)` buckets with one host synchronisation.
 //
-// Pipeline (async on the context's stream, one D2H of <= 32 partial points at the end):
-//   digits -> histogram -> scan -> scatter            counting sort of (w, i) by |digit|
-//   accumulate                                         thread per light bucket; buckets above
-//                                                      HEAVY_THRESHOLD (skewed small-value
-//                                                      advice columns) are cut into block-sized
-//                                                      items reduced by a shared-memory tree
-//   reduce                                             sum_b b * B_b: running sums over segments
-//                                                      of 8 buckets, then per-bit tree sums of the
-//                                                      segment totals (shallow dependency chains:
-//                                                      one EC addition is ~10 us of latency)
-//   host                                               Horner over <= 20 partial sums
+// Pipeline (async on the context's stream, one D2H of the partial sums at the end):
+//   digits -> histogram -> scan -> scatter   counting sort of (job, w, i) by (job, |digit|)
+//   plan                                       chunk length L = entries / resident threads: the
+//                                              accumulation is ONE wave of equal-sized chunks
+//   accumulate                                 thread per chunk of L consecutive sorted entries,
+//                                              whatever the bucket sizes: the piece of the bucket
+//                                              a chunk starts in goes to heads[chunk], buckets that
+//                                              begin inside the chunk are written directly
+//   fix-up                                     thread per bucket adds the heads of the chunks it
+//                                              spills into; buckets spanning many chunks (skewed
+//                                              small-value advice columns) go through a block-wide
+//                                              tree reduction
+//   reduce                                     sum_b b * B_b: running sums over segments of 8
+//                                              buckets, then per-bit tree sums of the segment
+//                                              totals (shallow dependency chains)
+//   host                                       Horner over <= 16 partial sums per job
 //
 // Roofline: integer-pipe bound; see DESIGN.md §MSM for the MAC accounting.
+#include <algorithm>
 #include <chrono>
 #include <cstdlib>
+#include <vector>
 
 #include "msm_fixed.h"
 
 namespace zkodst {
 namespace {
 
-constexpr int HEAVY_THRESHOLD = 256;
-constexpr int HEAVY_ITEM = 2048;
-constexpr int HEAVY_THREADS = 128;
+constexpr int ACC_THREADS = 128;
+constexpr int ACC_MIN_BLOCKS = 4;   // registers: 124 per thread
+constexpr int MIN_CHUNK = 16;
+constexpr int SERIAL_HEADS = 8;     // buckets spilling into more chunks than this take the heavy path
+constexpr int PIECE = 2048;         // heads per heavy work item
+constexpr int HEAVY_THREADS = 256;
 constexpr int SEG = 8;
 constexpr int TREE_THREADS = 128;
 constexpr int TREE_PER_THREAD = 8;
 
 struct HeavyItem {
-  uint32_t bucket, start, len, slot;
+  uint32_t start, len;
+};
+struct HeavyBucket {
+  uint32_t bucket, first, pieces, own;
+};
+struct Plan {
+  uint32_t entries, chunk, nchunks, pad;
+  uint32_t heavy_items, heavy_buckets, overflow, pad2;
+};
+
+struct DevJobs {
+  const Fp* scalars[MSM_MAX_BATCH];
+  uint32_t side_mask[MSM_MAX_BATCH];
+  int32_t side_select[MSM_MAX_BATCH];
+  int32_t n_extra[MSM_MAX_BATCH];
 };
 
 // ---- table construction --------------------------------------------------------------------------
@@ -57,28 +83,44 @@ table_next_kernel(const Affine* __restrict__ prev, Affine* __restrict__ next, ui
 }
 
 // ---- digits + histogram -----------------------------------------------------------------------------
-__global__ void fixed_digits_kernel(const Fp* __restrict__ scalars, uint64_t count, const Fp* __restrict__ extra,
-                                    const uint32_t* __restrict__ extra_index, int n_extra, int c, int nwin,
-                                    uint64_t npoints, uint32_t* __restrict__ entries_tmp,
-                                    uint32_t* __restrict__ counts, uint32_t side_bit_mask, int side_select) {
-  // entries_tmp[w * (count + n_extra) + t] = bucket + 1 | sign << 31   (0 = no entry)
+// warp-aggregated increment: lanes with the same key elect a leader that adds the group size
+__device__ __forceinline__ uint32_t aggregated_add(uint32_t* counters, uint32_t key, bool active) {
+  uint32_t base = 0;
+  if (active) {
+    const uint32_t peers = __match_any_sync(__activemask(), key);
+    const int leader = __ffs(peers) - 1;
+    const int lane = threadIdx.x & 31;
+    if (lane == leader) base = atomicAdd(&counters[key], (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    base += __popc(peers & ((1u << lane) - 1));
+  }
+  return base;
+}
+
+// entries_tmp[((job * nwin + w) * stride) + t] = bucket + 1 | sign << 31   (0 = no entry)
+__global__ void fixed_digits_kernel(DevJobs jobs, uint64_t count, const Fp* __restrict__ extra, int c, int nwin,
+                                    uint64_t stride, uint32_t B, uint32_t* __restrict__ entries_tmp,
+                                    uint32_t* __restrict__ counts) {
+  const int job = blockIdx.y;
   uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  const uint64_t total = count + n_extra;
+  const uint64_t total = count + jobs.n_extra[job];
   if (t >= total) return;
   uint64_t s[4];
   bool zero = false;
   if (t < count) {
     // optional support mask (IPA rounds): keep index t only if ((t & mask) != 0) == side_select
-    if (side_bit_mask && (((t & side_bit_mask) != 0) != (side_select != 0))) zero = true;
+    const uint32_t mask = jobs.side_mask[job];
+    if (mask && (((t & mask) != 0) != (jobs.side_select[job] != 0))) zero = true;
     if (!zero) {
-      Fp v = scalars[t];
+      Fp v = jobs.scalars[job][t];
       zero = v.is_zero();
       if (!zero) v.to_canonical(s);
     }
   } else {
-    extra[t - count].to_canonical(s);
+    extra[job * 4 + (t - count)].to_canonical(s);
   }
-  const uint32_t B = 1u << (c - 1);
+  uint32_t* my_counts = counts + (size_t)job * B;
+  uint32_t* my_tmp = entries_tmp + (size_t)job * nwin * stride + t;
   uint32_t carry = 0;
   for (int w = 0; w < nwin; w++) {
     uint32_t e = 0;
@@ -90,22 +132,15 @@ __global__ void fixed_digits_kernel(const Fp* __restrict__ scalars, uint64_t cou
       if (d > B) {
         carry = 1;
         uint32_t mag = (1u << c) - d;  // 0 when the raw digit 2^c - 1 absorbs a carry: digit 0, carry 1
-        if (mag) {
-          e = mag | 0x80000000u;
-          atomicAdd(&counts[mag - 1], 1u);
-        }
+        if (mag) e = mag | 0x80000000u;
       } else {
         carry = 0;
-        if (d) {
-          e = d;
-          atomicAdd(&counts[d - 1], 1u);
-        }
+        e = d;
       }
     }
-    entries_tmp[(size_t)w * total + t] = e;
+    my_tmp[(size_t)w * stride] = e;
+    aggregated_add(my_counts, (e & 0x7fffffffu) - 1, e != 0);
   }
-  (void)npoints;
-  (void)extra_index;
 }
 
 constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 4, SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
@@ -162,26 +197,48 @@ __global__ void fscan_sums_kernel(uint32_t* tile_sums, uint32_t ntiles) {  // si
     __syncthreads();
   }
 }
-__global__ void fscan_add_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ tile_sums, uint32_t n) {
+// offsets += tile offsets; the last thread also writes the sentinel offsets[n] and the plan
+__global__ void fscan_add_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ tile_sums,
+                                 const uint32_t* __restrict__ counts, uint32_t n, uint32_t resident_threads,
+                                 Plan* __restrict__ plan) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] += tile_sums[i / SCAN_TILE];
+  if (i >= n) return;
+  uint32_t v = out[i] + tile_sums[i / SCAN_TILE];
+  out[i] = v;
+  if (i == n - 1) {
+    const uint32_t entries = v + counts[i];
+    out[n] = entries;
+    uint32_t chunk = (entries + resident_threads - 1) / resident_threads;
+    chunk = (chunk + 3) & ~3u;
+    if (chunk < MIN_CHUNK) chunk = MIN_CHUNK;
+    Plan p;
+    p.entries = entries;
+    p.chunk = chunk;
+    p.nchunks = (entries + chunk - 1) / chunk;
+    p.pad = 0;
+    p.heavy_items = p.heavy_buckets = p.overflow = p.pad2 = 0;
+    *plan = p;
+  }
 }
 
 // scatter: sorted[pos] = table entry index (w * npoints + point) | sign << 31
-__global__ void fixed_scatter_kernel(const uint32_t* __restrict__ entries_tmp, uint64_t count, int n_extra,
-                                     const uint32_t* __restrict__ extra_index, int nwin, uint64_t npoints,
-                                     const uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursor,
-                                     uint32_t* __restrict__ sorted) {
+__global__ void fixed_scatter_kernel(DevJobs jobs, const uint32_t* __restrict__ entries_tmp, uint64_t count,
+                                     const uint32_t* __restrict__ extra_index, int nwin, uint64_t stride,
+                                     uint64_t npoints, uint32_t B, const uint32_t* __restrict__ offsets,
+                                     uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
+  const int job = blockIdx.y;
   uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  const uint64_t total = count + n_extra;
+  const uint64_t total = count + jobs.n_extra[job];
   if (t >= total) return;
-  const uint32_t point = t < count ? (uint32_t)t : extra_index[t - count];
+  const uint32_t point = t < count ? (uint32_t)t : extra_index[job * 4 + (t - count)];
+  const uint32_t* my_tmp = entries_tmp + (size_t)job * nwin * stride + t;
+  uint32_t* my_cursor = cursor + (size_t)job * B;
+  const uint32_t* my_offsets = offsets + (size_t)job * B;
   for (int w = 0; w < nwin; w++) {
-    uint32_t e = entries_tmp[(size_t)w * total + t];
-    if (!e) continue;
-    uint32_t bucket = (e & 0x7fffffffu) - 1;
-    uint32_t pos = offsets[bucket] + atomicAdd(&cursor[bucket], 1u);
-    sorted[pos] = (uint32_t)((uint64_t)w * npoints + point) | (e & 0x80000000u);
+    const uint32_t e = my_tmp[(size_t)w * stride];
+    const uint32_t bucket = (e & 0x7fffffffu) - 1;
+    const uint32_t rank = aggregated_add(my_cursor, bucket, e != 0);
+    if (e) sorted[my_offsets[bucket] + rank] = (uint32_t)((uint64_t)w * npoints + point) | (e & 0x80000000u);
   }
 }
 
@@ -191,83 +248,117 @@ __device__ __forceinline__ Affine load_entry(const Affine* __restrict__ table, u
   return p;
 }
 
-__global__ void fixed_find_heavy_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
-                                        uint32_t nbuckets, HeavyItem* __restrict__ items,
-                                        uint32_t* __restrict__ hcount, uint32_t max_items,
-                                        uint32_t* __restrict__ heavy_buckets) {
+// ---- accumulation: one chunk of `plan->chunk` consecutive sorted entries per thread -------------------
+__global__ void __launch_bounds__(ACC_THREADS, ACC_MIN_BLOCKS)
+fixed_accumulate_kernel(const Affine* __restrict__ table, const uint32_t* __restrict__ sorted,
+                        const uint32_t* __restrict__ offsets, uint32_t nbuckets, const Plan* __restrict__ plan,
+                        XYZZ* __restrict__ heads, XYZZ* __restrict__ buckets) {
+  const uint32_t entries = plan->entries, L = plan->chunk;
+  for (uint32_t chunk = blockIdx.x * ACC_THREADS + threadIdx.x; chunk < plan->nchunks;
+       chunk += gridDim.x * ACC_THREADS) {
+    const uint32_t start = chunk * L;
+    const uint32_t end = start + L < entries ? start + L : entries;
+    // bucket containing `start`: first b with offsets[b + 1] > start
+    uint32_t lo = 0, hi = nbuckets - 1;
+    while (lo < hi) {
+      uint32_t mid = (lo + hi) >> 1;
+      if (offsets[mid + 1] <= start) lo = mid + 1; else hi = mid;
+    }
+    uint32_t b = lo, boundary = offsets[b + 1];
+    bool first = true;
+    XYZZ acc = XYZZ::identity();
+    Affine nxt = load_entry(table, sorted[start]);
+    for (uint32_t pos = start; pos < end; pos++) {
+      const Affine cur = nxt;
+      if (pos + 1 < end) nxt = load_entry(table, sorted[pos + 1]);
+      if (pos >= boundary) {
+        if (first) heads[chunk] = acc; else buckets[b] = acc;
+        first = false;
+        acc = XYZZ::identity();
+        do {
+          b++;
+          boundary = offsets[b + 1];
+        } while (pos >= boundary);
+      }
+      acc = acc.add_affine(cur);
+    }
+    if (first) heads[chunk] = acc; else buckets[b] = acc;
+  }
+}
+
+// ---- fix-up: bucket = (piece written by the chunk it starts in) + heads of the chunks it spills into ---
+__global__ void __launch_bounds__(128)
+fixed_fixup_kernel(const uint32_t* __restrict__ offsets, uint32_t nbuckets, Plan* __restrict__ plan,
+                   const XYZZ* __restrict__ heads, XYZZ* __restrict__ buckets, HeavyItem* __restrict__ items,
+                   HeavyBucket* __restrict__ hbuckets, uint32_t max_items, uint32_t max_hbuckets) {
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nbuckets) return;
-  uint32_t cnt = counts[b];
-  if (cnt <= HEAVY_THRESHOLD) return;
-  uint32_t pieces = (cnt + HEAVY_ITEM - 1) / HEAVY_ITEM;
-  uint32_t first = atomicAdd(&hcount[0], pieces);
-  uint32_t hb = atomicAdd(&hcount[1], 1u);
-  if (first + pieces > max_items) {
-    hcount[2] = 1;  // overflow flag
+  const uint32_t s = offsets[b], e = offsets[b + 1];
+  if (s == e) {
+    buckets[b] = XYZZ::identity();
     return;
   }
-  heavy_buckets[3 * hb] = b;
-  heavy_buckets[3 * hb + 1] = first;
-  heavy_buckets[3 * hb + 2] = pieces;
+  const uint32_t L = plan->chunk;
+  const uint32_t t_first = s / L, t_last = (e - 1) / L;
+  const bool own = (s % L) != 0;
+  const uint32_t h0 = own ? t_first + 1 : t_first;
+  const uint32_t nheads = t_last + 1 - h0;
+  if (nheads == 0) return;
+  if (nheads <= SERIAL_HEADS) {
+    XYZZ acc = own ? buckets[b] : heads[h0];
+    for (uint32_t t = own ? h0 : h0 + 1; t <= t_last; t++) acc = acc.add(heads[t]);
+    buckets[b] = acc;
+    return;
+  }
+  const uint32_t pieces = (nheads + PIECE - 1) / PIECE;
+  const uint32_t first = atomicAdd(&plan->heavy_items, pieces);
+  const uint32_t hb = atomicAdd(&plan->heavy_buckets, 1u);
+  if (first + pieces > max_items || hb >= max_hbuckets) {
+    plan->overflow = 1;
+    return;
+  }
+  hbuckets[hb] = HeavyBucket{b, first, pieces, own ? 1u : 0u};
   for (uint32_t p = 0; p < pieces; p++) {
-    uint32_t start = p * HEAVY_ITEM;
-    uint32_t len = cnt - start < HEAVY_ITEM ? cnt - start : HEAVY_ITEM;
-    items[first + p] = HeavyItem{b, offsets[b] + start, len, first + p};
+    const uint32_t st = p * PIECE;
+    items[first + p] = HeavyItem{h0 + st, nheads - st < PIECE ? nheads - st : PIECE};
   }
 }
-
-__global__ void __launch_bounds__(128)
-fixed_accumulate_kernel(const Affine* __restrict__ table, const uint32_t* __restrict__ sorted,
-                        const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
-                        uint32_t nbuckets, XYZZ* __restrict__ buckets) {
-  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nbuckets) return;
-  uint32_t cnt = counts[b];
-  if (cnt > HEAVY_THRESHOLD) return;
-  XYZZ acc = XYZZ::identity();
-  const uint32_t* list = sorted + offsets[b];
-  for (uint32_t k = 0; k < cnt; k++) acc = acc.add_affine(load_entry(table, list[k]));
-  buckets[b] = acc;
-}
-
 __global__ void __launch_bounds__(HEAVY_THREADS)
-fixed_heavy_accumulate_kernel(const Affine* __restrict__ table, const uint32_t* __restrict__ sorted,
-                              const HeavyItem* __restrict__ items, const uint32_t* __restrict__ hcount,
-                              XYZZ* __restrict__ partials) {
+fixed_heavy_kernel(const XYZZ* __restrict__ heads, const HeavyItem* __restrict__ items,
+                   const Plan* __restrict__ plan, XYZZ* __restrict__ partials) {
   __shared__ XYZZ sh[HEAVY_THREADS];
-  for (uint32_t item = blockIdx.x; item < hcount[0]; item += gridDim.x) {
-    HeavyItem it = items[item];
+  const uint32_t nitems = plan->overflow ? 0 : plan->heavy_items;
+  for (uint32_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const HeavyItem it = items[item];
     XYZZ acc = XYZZ::identity();
-    for (uint32_t k = threadIdx.x; k < it.len; k += HEAVY_THREADS)
-      acc = acc.add_affine(load_entry(table, sorted[it.start + k]));
+    for (uint32_t k = threadIdx.x; k < it.len; k += HEAVY_THREADS) acc = acc.add(heads[it.start + k]);
     sh[threadIdx.x] = acc;
     __syncthreads();
     for (int stride = HEAVY_THREADS / 2; stride > 0; stride >>= 1) {
       if ((int)threadIdx.x < stride) sh[threadIdx.x] = sh[threadIdx.x].add(sh[threadIdx.x + stride]);
       __syncthreads();
     }
-    if (threadIdx.x == 0) partials[it.slot] = sh[0];
+    if (threadIdx.x == 0) partials[item] = sh[0];
     __syncthreads();
   }
 }
-__global__ void fixed_heavy_finalize_kernel(const uint32_t* __restrict__ heavy_buckets,
-                                            const uint32_t* __restrict__ hcount, const XYZZ* __restrict__ partials,
-                                            XYZZ* __restrict__ buckets) {
+__global__ void fixed_heavy_finalize_kernel(const HeavyBucket* __restrict__ hbuckets, const Plan* __restrict__ plan,
+                                            const XYZZ* __restrict__ partials, XYZZ* __restrict__ buckets) {
   uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
-  if (h >= hcount[1]) return;
-  uint32_t b = heavy_buckets[3 * h], first = heavy_buckets[3 * h + 1], pieces = heavy_buckets[3 * h + 2];
-  XYZZ acc = partials[first];
-  for (uint32_t p = 1; p < pieces; p++) acc = acc.add(partials[first + p]);
-  buckets[b] = acc;
+  if (plan->overflow || h >= plan->heavy_buckets) return;
+  const HeavyBucket hb = hbuckets[h];
+  XYZZ acc = hb.own ? buckets[hb.bucket] : XYZZ::identity();
+  for (uint32_t p = 0; p < hb.pieces; p++) acc = acc.add(partials[hb.first + p]);
+  buckets[hb.bucket] = acc;
 }
 
-// ---- reduction: W = sum_{b=1..B} b * bucket[b-1] -----------------------------------------------------
+// ---- reduction: W = sum_{b=1..B} b * bucket[b-1], per job (blockIdx.z / .y selects the job) -----------
 // level 1: per segment s of SEG buckets:  S_s = sum B,  A_s = sum (b_local + 1) B
 __global__ void __launch_bounds__(128)
-fixed_reduce_level1_kernel(const XYZZ* __restrict__ buckets, uint32_t nsegs, XYZZ* __restrict__ outA,
+fixed_reduce_level1_kernel(const XYZZ* __restrict__ buckets, uint32_t nsegs_total, XYZZ* __restrict__ outA,
                            XYZZ* __restrict__ outS) {
   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= nsegs) return;
+  if (s >= nsegs_total) return;
   const XYZZ* seg = buckets + (size_t)s * SEG;
   XYZZ running = XYZZ::identity(), acc = XYZZ::identity();
 #pragma unroll 1
@@ -282,10 +373,10 @@ fixed_reduce_level1_kernel(const XYZZ* __restrict__ buckets, uint32_t nsegs, XYZ
 // Tree kernel: blockIdx.y = 0 sums all A_s; blockIdx.y = 1 + j sums the S_s with bit j of s set.
 __global__ void __launch_bounds__(TREE_THREADS)
 fixed_reduce_tree_kernel(const XYZZ* __restrict__ A, const XYZZ* __restrict__ S, uint32_t nsegs,
-                         XYZZ* __restrict__ partials, uint32_t blocks_x) {
+                         XYZZ* __restrict__ partials, uint32_t blocks_x, uint32_t nout) {
   __shared__ XYZZ sh[TREE_THREADS];
-  const int which = blockIdx.y;
-  const XYZZ* src = which == 0 ? A : S;
+  const int which = blockIdx.y, job = blockIdx.z;
+  const XYZZ* src = (which == 0 ? A : S) + (size_t)job * nsegs;
   const uint32_t bitmask = which == 0 ? 0 : (1u << (which - 1));
   uint32_t base = (blockIdx.x * TREE_THREADS + threadIdx.x) * TREE_PER_THREAD;
   XYZZ acc = XYZZ::identity();
@@ -299,30 +390,35 @@ fixed_reduce_tree_kernel(const XYZZ* __restrict__ A, const XYZZ* __restrict__ S,
     if ((int)threadIdx.x < stride) sh[threadIdx.x] = sh[threadIdx.x].add(sh[threadIdx.x + stride]);
     __syncthreads();
   }
-  if (threadIdx.x == 0) partials[(size_t)which * blocks_x + blockIdx.x] = sh[0];
+  if (threadIdx.x == 0) partials[((size_t)job * nout + which) * blocks_x + blockIdx.x] = sh[0];
 }
-// second stage: one block per output sums its blocks_x partials
-__global__ void __launch_bounds__(TREE_THREADS)
+// second stage: one block per (output, job) sums its blocks_x partials
+__global__ void __launch_bounds__(32)
 fixed_reduce_final_kernel(const XYZZ* __restrict__ partials, uint32_t blocks_x, XYZZ* __restrict__ out) {
-  __shared__ XYZZ sh[TREE_THREADS];
-  XYZZ acc = XYZZ::identity();
-  for (uint32_t k = threadIdx.x; k < blocks_x; k += TREE_THREADS) acc = acc.add(partials[(size_t)blockIdx.x * blocks_x + k]);
-  sh[threadIdx.x] = acc;
-  __syncthreads();
-  for (int stride = TREE_THREADS / 2; stride > 0; stride >>= 1) {
-    if ((int)threadIdx.x < stride) sh[threadIdx.x] = sh[threadIdx.x].add(sh[threadIdx.x + stride]);
-    __syncthreads();
+  const size_t o = blockIdx.x;
+  if (threadIdx.x == 0) {
+    XYZZ acc = partials[o * blocks_x];
+    for (uint32_t k = 1; k < blocks_x; k++) acc = acc.add(partials[o * blocks_x + k]);
+    out[o] = acc;
   }
-  if (threadIdx.x == 0) out[blockIdx.x] = sh[0];
+}
+
+int window_bits_override() {
+  static const int v = [] {
+    const char* e = getenv("ZK_MSM_C");
+    return e ? atoi(e) : 0;
+  }();
+  return v;
 }
 
 }  // namespace
 
 int fixed_window_bits(uint64_t npoints) {
+  const int o = window_bits_override();
+  if (o >= 4 && o <= 20) return o;
   if (npoints <= (1u << 10)) return 8;
   if (npoints <= (1u << 14)) return 12;
-  if (npoints <= (1u << 17)) return 16;
-  return 18;
+  return 16;
 }
 
 int32_t fixed_base_build(zk_ctx* ctx, const Affine* d_bases, uint64_t npoints, FixedBase* out) {
@@ -348,47 +444,62 @@ void fixed_base_free(FixedBase& fb) {
   fb = FixedBase();
 }
 
-int32_t msm_fixed(zk_ctx* ctx, const FixedBase& fb, const Fp* d_scalars, uint64_t count, const Fp* extra_host,
-                  const uint32_t* extra_index_host, int n_extra, XYZZ* result, uint32_t side_bit_mask,
-                  int side_select) {
-  if (count > fb.npoints || n_extra > 4) return set_error(ctx, ZK_E_INVALID, "msm_fixed: bad sizes");
-  const uint64_t total = count + n_extra;
-  if (total == 0) {
-    *result = XYZZ::identity();
-    return ZK_OK;
-  }
+int32_t msm_fixed_batch(zk_ctx* ctx, const FixedBase& fb, const MsmJob* jobs, int nb, uint64_t count,
+                        XYZZ* results) {
+  if (nb < 1 || nb > MSM_MAX_BATCH || count > fb.npoints) return set_error(ctx, ZK_E_INVALID, "msm_fixed: bad sizes");
+  for (int m = 0; m < nb; m++)
+    if (jobs[m].n_extra < 0 || jobs[m].n_extra > 4) return set_error(ctx, ZK_E_INVALID, "msm_fixed: bad extras");
   cudaStream_t st = ctx->stream;
   const int c = fb.c, nwin = fb.nwin;
   const uint32_t B = 1u << (c - 1);
+  const uint32_t NB = (uint32_t)nb * B;
+  const uint64_t stride = count + 4;
+  const uint64_t max_entries = (uint64_t)nb * nwin * stride;
+  if (max_entries >= 0xffffffffull) return set_error(ctx, ZK_E_INVALID, "msm_fixed: batch too large");
+  static int acc_blocks_per_sm = 0;
+  if (!acc_blocks_per_sm) {
+    int v = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, fixed_accumulate_kernel, ACC_THREADS, 0);
+    acc_blocks_per_sm = v > 0 ? v : ACC_MIN_BLOCKS;
+  }
+  const uint32_t acc_grid = (uint32_t)ctx->sm_count * acc_blocks_per_sm;
+  const uint32_t resident = acc_grid * ACC_THREADS;
+  // chunk = max(MIN_CHUNK, entries / resident) so there are never more chunks than resident threads
+  const uint32_t max_chunks = (uint32_t)std::min<uint64_t>(max_entries / MIN_CHUNK + 1, (uint64_t)resident + 1);
+  const uint32_t max_hbuckets = max_chunks / (SERIAL_HEADS + 1) + 16;
+  const uint32_t max_items = max_chunks / PIECE + max_hbuckets + 16;
   const uint32_t nsegs = B / SEG;
   int nbits = 0;
   while ((1u << nbits) < nsegs) nbits++;
   const uint32_t blocks_x = (nsegs + TREE_THREADS * TREE_PER_THREAD - 1) / (TREE_THREADS * TREE_PER_THREAD);
   const uint32_t nout = 1 + nbits;
-  const uint32_t max_heavy = (uint32_t)((uint64_t)nwin * total / HEAVY_THRESHOLD + 64);
-  const uint32_t ntiles = (B + SCAN_TILE - 1) / SCAN_TILE;
+  const uint32_t ntiles = (NB + SCAN_TILE - 1) / SCAN_TILE;
   size_t off = 0;
   auto take = [&](size_t bytes) {
     size_t o = off;
     off += (bytes + 255) / 256 * 256;
     return o;
   };
-  size_t o_tmp = take((size_t)nwin * total * 4), o_counts = take((size_t)B * 4), o_offsets = take((size_t)B * 4),
-         o_cursor = take((size_t)B * 4), o_tiles = take((size_t)ntiles * 4 + 16), o_sorted = take((size_t)nwin * total * 4),
-         o_hitems = take((size_t)max_heavy * sizeof(HeavyItem)), o_hb = take((size_t)max_heavy * 12),
-         o_hcount = take(16), o_hpart = take((size_t)max_heavy * sizeof(XYZZ)),
-         o_buckets = take((size_t)B * sizeof(XYZZ)), o_A = take((size_t)nsegs * sizeof(XYZZ)),
-         o_S = take((size_t)nsegs * sizeof(XYZZ)), o_part = take((size_t)nout * blocks_x * sizeof(XYZZ)),
-         o_out = take((size_t)nout * sizeof(XYZZ)), o_extra = take(4 * sizeof(Fp)), o_eidx = take(64);
+  const size_t o_tmp = take(max_entries * 4), o_counts = take((size_t)NB * 4), o_offsets = take((size_t)(NB + 1) * 4),
+               o_cursor = take((size_t)NB * 4), o_tiles = take((size_t)ntiles * 4 + 16), o_sorted = take(max_entries * 4 + 16),
+               o_plan = take(sizeof(Plan)), o_heads = take((size_t)max_chunks * sizeof(XYZZ)),
+               o_hitems = take((size_t)max_items * sizeof(HeavyItem)),
+               o_hb = take((size_t)max_hbuckets * sizeof(HeavyBucket)),
+               o_hpart = take((size_t)max_items * sizeof(XYZZ)), o_buckets = take((size_t)NB * sizeof(XYZZ)),
+               o_A = take((size_t)nb * nsegs * sizeof(XYZZ)), o_S = take((size_t)nb * nsegs * sizeof(XYZZ)),
+               o_part = take((size_t)nb * nout * blocks_x * sizeof(XYZZ)), o_out = take((size_t)nb * nout * sizeof(XYZZ)),
+               o_extra = take((size_t)MSM_MAX_BATCH * 4 * sizeof(Fp)), o_eidx = take((size_t)MSM_MAX_BATCH * 4 * 4);
   int32_t rc = ensure_buf(ctx, ctx->msm_ws, off);
   if (rc) return rc;
   char* ws = (char*)ctx->msm_ws.ptr;
   uint32_t *tmp = (uint32_t*)(ws + o_tmp), *counts = (uint32_t*)(ws + o_counts), *offsets = (uint32_t*)(ws + o_offsets),
            *cursor = (uint32_t*)(ws + o_cursor), *tiles = (uint32_t*)(ws + o_tiles), *sorted = (uint32_t*)(ws + o_sorted),
-           *hb = (uint32_t*)(ws + o_hb), *hcount = (uint32_t*)(ws + o_hcount), *eidx = (uint32_t*)(ws + o_eidx);
+           *eidx = (uint32_t*)(ws + o_eidx);
+  Plan* plan = (Plan*)(ws + o_plan);
   HeavyItem* hitems = (HeavyItem*)(ws + o_hitems);
-  XYZZ *hpart = (XYZZ*)(ws + o_hpart), *buckets = (XYZZ*)(ws + o_buckets), *A = (XYZZ*)(ws + o_A),
-       *S = (XYZZ*)(ws + o_S), *part = (XYZZ*)(ws + o_part), *out = (XYZZ*)(ws + o_out);
+  HeavyBucket* hb = (HeavyBucket*)(ws + o_hb);
+  XYZZ *heads = (XYZZ*)(ws + o_heads), *hpart = (XYZZ*)(ws + o_hpart), *buckets = (XYZZ*)(ws + o_buckets),
+       *A = (XYZZ*)(ws + o_A), *S = (XYZZ*)(ws + o_S), *part = (XYZZ*)(ws + o_part), *out = (XYZZ*)(ws + o_out);
   Fp* d_extra = (Fp*)(ws + o_extra);
   static const bool trace = getenv("ZK_MSM_TRACE") != nullptr;
   std::chrono::steady_clock::time_point t0;
@@ -396,56 +507,97 @@ int32_t msm_fixed(zk_ctx* ctx, const FixedBase& fb, const Fp* d_scalars, uint64_
     cudaStreamSynchronize(st);
     t0 = std::chrono::steady_clock::now();
   }
-  if (n_extra) {
-    ZK_CUDA(ctx, cudaMemcpyAsync(d_extra, extra_host, n_extra * sizeof(Fp), cudaMemcpyHostToDevice, st));
-    ZK_CUDA(ctx, cudaMemcpyAsync(eidx, extra_index_host, n_extra * 4, cudaMemcpyHostToDevice, st));
+  DevJobs dj;
+  Fp h_extra[MSM_MAX_BATCH * 4];
+  uint32_t h_eidx[MSM_MAX_BATCH * 4];
+  bool any_extra = false;
+  for (int m = 0; m < MSM_MAX_BATCH; m++) {
+    const MsmJob& j = jobs[m < nb ? m : 0];
+    dj.scalars[m] = j.scalars;
+    dj.side_mask[m] = j.side_mask;
+    dj.side_select[m] = j.side_select;
+    dj.n_extra[m] = m < nb ? j.n_extra : 0;
+    for (int e = 0; e < 4; e++) {
+      h_extra[m * 4 + e] = (m < nb && e < j.n_extra) ? j.extra[e] : Fp::zero();
+      h_eidx[m * 4 + e] = (m < nb && e < j.n_extra) ? j.extra_index[e] : 0;
+    }
+    if (m < nb && j.n_extra) any_extra = true;
   }
-  ZK_CUDA(ctx, cudaMemsetAsync(counts, 0, (size_t)B * 4, st));
-  ZK_CUDA(ctx, cudaMemsetAsync(cursor, 0, (size_t)B * 4, st));
-  ZK_CUDA(ctx, cudaMemsetAsync(hcount, 0, 16, st));
+  if (any_extra) {
+    // pageable copies: the runtime stages them before returning, so the stack arrays may go away
+    ZK_CUDA(ctx, cudaMemcpyAsync(d_extra, h_extra, sizeof(h_extra), cudaMemcpyHostToDevice, st));
+    ZK_CUDA(ctx, cudaMemcpyAsync(eidx, h_eidx, sizeof(h_eidx), cudaMemcpyHostToDevice, st));
+  }
+  ZK_CUDA(ctx, cudaMemsetAsync(counts, 0, (size_t)NB * 4, st));
+  ZK_CUDA(ctx, cudaMemsetAsync(cursor, 0, (size_t)NB * 4, st));
   {
     KernelTimer timer(ctx, KC_MSM);
     const int T = 256;
-    const unsigned gt = (unsigned)((total + T - 1) / T);
-    fixed_digits_kernel<<<gt, T, 0, st>>>(d_scalars, count, d_extra, eidx, n_extra, c, nwin, fb.npoints, tmp, counts,
-                                          side_bit_mask, side_select);
-    fscan_tiles_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(counts, offsets, tiles, B);
+    const dim3 gt((unsigned)((stride + T - 1) / T), (unsigned)nb);
+    fixed_digits_kernel<<<gt, T, 0, st>>>(dj, count, d_extra, c, nwin, stride, B, tmp, counts);
+    fscan_tiles_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(counts, offsets, tiles, NB);
     fscan_sums_kernel<<<1, 1024, 0, st>>>(tiles, ntiles);
-    fscan_add_kernel<<<(B + T - 1) / T, T, 0, st>>>(offsets, tiles, B);
-    fixed_scatter_kernel<<<gt, T, 0, st>>>(tmp, count, n_extra, eidx, nwin, fb.npoints, offsets, cursor, sorted);
-    fixed_find_heavy_kernel<<<(B + T - 1) / T, T, 0, st>>>(counts, offsets, B, hitems, hcount, max_heavy, hb);
+    fscan_add_kernel<<<(NB + T - 1) / T, T, 0, st>>>(offsets, tiles, counts, NB, resident, plan);
+    fixed_scatter_kernel<<<gt, T, 0, st>>>(dj, tmp, count, eidx, nwin, stride, fb.npoints, B, offsets, cursor, sorted);
     {
       KernelTimer acc_timer(ctx, KC_MSM_ACC);
-      fixed_accumulate_kernel<<<(B + 127) / 128, 128, 0, st>>>(fb.table, sorted, counts, offsets, B, buckets);
-      fixed_heavy_accumulate_kernel<<<ctx->sm_count * 4, HEAVY_THREADS, 0, st>>>(fb.table, sorted, hitems, hcount, hpart);
-      fixed_heavy_finalize_kernel<<<(max_heavy + 63) / 64, 64, 0, st>>>(hb, hcount, hpart, buckets);
+      fixed_accumulate_kernel<<<acc_grid, ACC_THREADS, 0, st>>>(fb.table, sorted, offsets, NB, plan, heads, buckets);
+      fixed_fixup_kernel<<<(NB + 127) / 128, 128, 0, st>>>(offsets, NB, plan, heads, buckets, hitems, hb, max_items,
+                                                           max_hbuckets);
+      fixed_heavy_kernel<<<ctx->sm_count * 2, HEAVY_THREADS, 0, st>>>(heads, hitems, plan, hpart);
+      fixed_heavy_finalize_kernel<<<(max_hbuckets + 63) / 64, 64, 0, st>>>(hb, plan, hpart, buckets);
     }
-    fixed_reduce_level1_kernel<<<(nsegs + 127) / 128, 128, 0, st>>>(buckets, nsegs, A, S);
-    fixed_reduce_tree_kernel<<<dim3(blocks_x, nout), TREE_THREADS, 0, st>>>(A, S, nsegs, part, blocks_x);
-    fixed_reduce_final_kernel<<<nout, TREE_THREADS, 0, st>>>(part, blocks_x, out);
+    const uint32_t nsegs_total = (uint32_t)nb * nsegs;
+    fixed_reduce_level1_kernel<<<(nsegs_total + 127) / 128, 128, 0, st>>>(buckets, nsegs_total, A, S);
+    fixed_reduce_tree_kernel<<<dim3(blocks_x, nout, (unsigned)nb), TREE_THREADS, 0, st>>>(A, S, nsegs, part, blocks_x,
+                                                                                         nout);
+    fixed_reduce_final_kernel<<<(unsigned)nb * nout, 32, 0, st>>>(part, blocks_x, out);
     ctx->launches += 12;
   }
   ZK_CUDA(ctx, cudaGetLastError());
-  XYZZ sums[40];
-  uint32_t hc[4];
-  ZK_CUDA(ctx, cudaMemcpyAsync(sums, out, (size_t)nout * sizeof(XYZZ), cudaMemcpyDeviceToHost, st));
-  ZK_CUDA(ctx, cudaMemcpyAsync(hc, hcount, 16, cudaMemcpyDeviceToHost, st));
+  std::vector<XYZZ> sums((size_t)nb * nout);
+  Plan hp;
+  ZK_CUDA(ctx, cudaMemcpyAsync(sums.data(), out, sums.size() * sizeof(XYZZ), cudaMemcpyDeviceToHost, st));
+  ZK_CUDA(ctx, cudaMemcpyAsync(&hp, plan, sizeof(Plan), cudaMemcpyDeviceToHost, st));
   ZK_CUDA(ctx, cudaStreamSynchronize(st));
-  if (hc[2]) return set_error(ctx, ZK_E_NOMEM, "msm_fixed: heavy work list overflow");
-  // W = sums[0] + SEG * sum_j 2^j sums[1 + j]
-  XYZZ weighted = XYZZ::identity();
-  for (int j = nbits - 1; j >= 0; j--) {
-    weighted = weighted.dbl();
-    weighted = weighted.add(sums[1 + j]);
+  if (hp.overflow) return set_error(ctx, ZK_E_NOMEM, "msm_fixed: heavy work list overflow");
+  for (int m = 0; m < nb; m++) {
+    const XYZZ* sm = &sums[(size_t)m * nout];
+    // W = sums[0] + SEG * sum_j 2^j sums[1 + j]
+    XYZZ weighted = XYZZ::identity();
+    for (int j = nbits - 1; j >= 0; j--) {
+      weighted = weighted.dbl();
+      weighted = weighted.add(sm[1 + j]);
+    }
+    for (int d = 0; (1 << d) < SEG; d++) weighted = weighted.dbl();
+    results[m] = sm[0].add(weighted);
   }
-  for (int d = 0; (1 << d) < SEG; d++) weighted = weighted.dbl();
-  *result = sums[0].add(weighted);
   if (trace) {
     double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    fprintf(stderr, "[msm_fixed] count=%llu c=%d nwin=%d heavy_items=%u ms=%.3f\n", (unsigned long long)total, c, nwin,
-            hc[0], ms);
+    fprintf(stderr, "[msm_fixed] jobs=%d count=%llu c=%d nwin=%d entries=%u chunk=%u heavy_items=%u ms=%.3f\n", nb,
+            (unsigned long long)count, c, nwin, hp.entries, hp.chunk, hp.heavy_items, ms);
   }
   return ZK_OK;
+}
+
+int32_t msm_fixed(zk_ctx* ctx, const FixedBase& fb, const Fp* d_scalars, uint64_t count, const Fp* extra_host,
+                  const uint32_t* extra_index_host, int n_extra, XYZZ* result, uint32_t side_bit_mask,
+                  int side_select) {
+  if (n_extra < 0 || n_extra > 4) return set_error(ctx, ZK_E_INVALID, "msm_fixed: bad sizes");
+  if (count + n_extra == 0) {
+    *result = XYZZ::identity();
+    return ZK_OK;
+  }
+  MsmJob j;
+  j.scalars = d_scalars;
+  j.n_extra = n_extra;
+  for (int e = 0; e < n_extra; e++) {
+    j.extra[e] = extra_host[e];
+    j.extra_index[e] = extra_index_host[e];
+  }
+  j.side_mask = side_bit_mask;
+  j.side_select = side_select;
+  return msm_fixed_batch(ctx, fb, &j, 1, count, result);
 }
 
 }  // namespace zkodst

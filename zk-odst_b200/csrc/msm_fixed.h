@@ -15,6 +15,19 @@ int fixed_window_bits(uint64_t npoints);
 int32_t fixed_base_build(zk_ctx* ctx, const Affine* d_bases, uint64_t npoints, FixedBase* out);
 void fixed_base_free(FixedBase& fb);
 
+constexpr int MSM_MAX_BATCH = 16;
+struct MsmJob {  // one MSM of a batch over the same base
+  const Fp* scalars = nullptr;  // device, `count` entries (jobs may share the vector)
+  Fp extra[4];                  // host scalars of up to 4 extra terms (blinds on W, IPA terms on U)
+  uint32_t extra_index[4] = {};
+  int n_extra = 0;
+  uint32_t side_mask = 0;       // != 0: keep index t only if ((t & mask) != 0) == side_select
+  int side_select = 0;
+};
+// results[m] = sum_{t < count} jobs[m].scalars[t] * base_t + extras, for all jobs in one pipeline
+int32_t msm_fixed_batch(zk_ctx* ctx, const FixedBase& fb, const MsmJob* jobs, int nb, uint64_t count,
+                        XYZZ* results);
+
 // result = sum_{t < count} scalars[t] * base_t + sum_e extra[e] * base_{extra_index[e]}.
 // side_bit_mask != 0 restricts the first sum to indices t with ((t & mask) != 0) == side_select.
 int32_t msm_fixed(zk_ctx* ctx, const FixedBase& fb, const Fp* d_scalars, uint64_t count, const Fp* extra_host,

@@ -9,6 +9,8 @@
 // product argument (K11).  The order of transcript writes, challenge squeezes and RNG draws is
 // halo2's; proof bytes are compared with the CPU oracle byte for byte in tests/.
 #include <atomic>
+#include <chrono>
+#include <cstdlib>
 #include <thread>
 
 #include "polyops.cuh"
@@ -30,6 +32,7 @@ struct ProofWorkspace {
   Fp *pin_poly = nullptr, *ptab_poly = nullptr, *zl_poly = nullptr;
   Fp *pin_coset = nullptr, *ptab_coset = nullptr, *zl_coset = nullptr;
   Fp* z_poly[NUM_SETS] = {};
+  Fp* z_vals[NUM_SETS + 1] = {};  // grand products (values) of the permutation sets, then the lookup
   Fp* z_coset[NUM_SETS] = {};
   Fp *tmp_a = nullptr, *tmp_b = nullptr, *tmp_c = nullptr;  // n each
   Fp *h = nullptr, *h_coeffs = nullptr;                      // en each
@@ -87,6 +90,7 @@ int32_t get_workspace(zk_ctx* ctx, DeviceKeys& K, ProofWorkspace** out) {
       A(z_poly[s], n);
       A(z_coset[s], en);
     }
+    for (int s = 0; s <= NUM_SETS; s++) A(z_vals[s], n);
     A(tmp_a, n); A(tmp_b, n); A(tmp_c, n);
     A(h, en); A(h_coeffs, en);
     A(random_poly, n); A(s_poly, n); A(q_prime, n); A(p_poly, n); A(b_vec, n); A(h_poly, n);
@@ -161,6 +165,26 @@ int32_t upload_fp(zk_ctx* ctx, Fp* dst, const Fp* src, size_t count) {
   ZK_CUDA(ctx, cudaMemcpyAsync(dst, src, count * sizeof(Fp), cudaMemcpyHostToDevice, ctx->stream));
   return ZK_OK;
 }
+
+// ---- optional wall-clock phase trace (ZK_PHASE_TRACE=1): syncs at phase boundaries, stderr only ---------
+struct PhaseTrace {
+  bool on;
+  cudaStream_t st;
+  std::chrono::steady_clock::time_point t;
+  explicit PhaseTrace(cudaStream_t s) : on(getenv("ZK_PHASE_TRACE") != nullptr), st(s) {
+    if (on) {
+      cudaStreamSynchronize(st);
+      t = std::chrono::steady_clock::now();
+    }
+  }
+  void mark(const char* name) {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[phase] %-28s %8.3f ms\n", name, std::chrono::duration<double, std::milli>(now - t).count());
+    t = now;
+  }
+};
 
 // ---- lookup argument helpers (A.5 permute_expression_pair, specialised to this circuit) ------------
 // The lookup inputs are (tag, dense, spread) triples; a valid row equals table row `dense`, so the
@@ -323,6 +347,7 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
   TranscriptWriter tr;
   tr.common_scalar(K.transcript_repr);
 
+  PhaseTrace phase(st);
   // ---- witness (K1) ---------------------------------------------------------------------------------
   if (n_compressions)
     ZK_CUDA(ctx, cudaMemcpyAsync(W->inputs, inputs, n_compressions * 213,
@@ -332,6 +357,7 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
   auto adv_poly = [&](int c) { return W->advice_polys + (size_t)c * n; };
   auto adv_coset = [&](int c) { return W->advice_cosets + (size_t)c * en; };
 
+  phase.mark("witness");
   // ---- advice blinding rows, blinds, commitments -----------------------------------------------------
   {
     Fp tails[12 * 6];
@@ -341,16 +367,19 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
   }
   Fp advice_blinds[12];
   for (auto& b : advice_blinds) b = tape.next();
-  for (int c = 0; c < 12; c++) {
-    Affine cm;
-    if ((rc = commit(ctx, adv(c), P.fb_gl, n,advice_blinds[c], &cm))) return rc;
-    tr.write_point(cm);
+  {
+    const Fp* cols[12];
+    Affine cms[12];
+    for (int c = 0; c < 12; c++) cols[c] = adv(c);
+    if ((rc = commit_batch(ctx, cols, P.fb_gl, n, advice_blinds, 12, cms))) return rc;
+    for (int c = 0; c < 12; c++) tr.write_point(cms[c]);
   }
   for (int c = 0; c < 12; c++)
     if ((rc = ntt_run(ctx, adv(c), (uint32_t)n, adv_poly(c), k, inv))) return rc;
 
   const Fp theta = tr.squeeze_challenge();
 
+  phase.mark("advice commit + iNTT");
   // ---- lookup: compress, permute, commit (K7) ----------------------------------------------------------
   Fp pin_blind, ptab_blind, zl_blind;
   {
@@ -419,13 +448,14 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
     for (auto& t : tails) t = tape.next();
     if ((rc = upload_fp(ctx, W->pin + usable, tails, 6))) return rc;
     if ((rc = upload_fp(ctx, W->ptab + usable, tails + 6, 6))) return rc;
-    Affine cm;
     pin_blind = tape.next();
-    if ((rc = commit(ctx, W->pin, P.fb_gl, n,pin_blind, &cm))) return rc;
-    tr.write_point(cm);
     ptab_blind = tape.next();
-    if ((rc = commit(ctx, W->ptab, P.fb_gl, n,ptab_blind, &cm))) return rc;
-    tr.write_point(cm);
+    const Fp* cols[2] = {W->pin, W->ptab};
+    const Fp blinds[2] = {pin_blind, ptab_blind};
+    Affine cms[2];
+    if ((rc = commit_batch(ctx, cols, P.fb_gl, n, blinds, 2, cms))) return rc;
+    tr.write_point(cms[0]);
+    tr.write_point(cms[1]);
     if ((rc = ntt_run(ctx, W->pin, (uint32_t)n, W->pin_poly, k, inv))) return rc;
     if ((rc = ntt_run(ctx, W->ptab, (uint32_t)n, W->ptab_poly, k, inv))) return rc;
   }
@@ -433,6 +463,7 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
   const Fp beta = tr.squeeze_challenge();
   const Fp gamma = tr.squeeze_challenge();
 
+  phase.mark("lookup permute + commit");
   // ---- permutation grand products (K8) ------------------------------------------------------------------
   Fp z_blinds[NUM_SETS];
   {
@@ -457,22 +488,22 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
       });
       if ((rc = batch_invert(ctx, den, n))) return rc;
       launch_map(ctx, n, [=] __device__(uint64_t i) { num[i] = num[i] * den[i]; });
-      Fp* z = W->tmp_c;
+      Fp* z = W->z_vals[s];
       if ((rc = affine_scan(ctx, num, Fp::zero(), nullptr, n, last_z, z))) return rc;
       Fp tails[5];
       for (auto& t : tails) t = tape.next();
       if ((rc = upload_fp(ctx, z + n - BLINDING, tails, BLINDING))) return rc;
-      ZK_CUDA(ctx, cudaMemcpyAsync(&last_z, z + n - (BLINDING + 1), sizeof(Fp), cudaMemcpyDeviceToHost, st));
+      if (s + 1 < NUM_SETS) {  // the next set starts from this set's last usable value
+        ZK_CUDA(ctx, cudaMemcpyAsync(&last_z, z + n - (BLINDING + 1), sizeof(Fp), cudaMemcpyDeviceToHost, st));
+        ZK_CUDA(ctx, cudaStreamSynchronize(st));
+      }
       z_blinds[s] = tape.next();
-      Affine cm;
-      if ((rc = commit(ctx, z, P.fb_gl, n,z_blinds[s], &cm))) return rc;  // syncs: last_z is valid after
-      tr.write_point(cm);
-      if ((rc = ntt_run(ctx, z, (uint32_t)n, W->z_poly[s], k, inv))) return rc;
     }
   }
+  phase.mark("permutation products");
   // ---- lookup grand product ------------------------------------------------------------------------------
   {
-    Fp *den = W->tmp_a, *num = W->tmp_b, *z = W->tmp_c;
+    Fp *den = W->tmp_a, *num = W->tmp_b, *z = W->z_vals[NUM_SETS];
     const Fp *pin = W->pin, *ptab = W->ptab, *cin = W->cin, *ctab = W->ctab;
     launch_map(ctx, n, [=] __device__(uint64_t i) { den[i] = (beta + pin[i]) * (gamma + ptab[i]); });
     if ((rc = batch_invert(ctx, den, n))) return rc;
@@ -482,11 +513,23 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
     for (auto& t : tails) t = tape.next();
     if ((rc = upload_fp(ctx, z + n - BLINDING, tails, BLINDING))) return rc;
     zl_blind = tape.next();
-    Affine cm;
-    if ((rc = commit(ctx, z, P.fb_gl, n,zl_blind, &cm))) return rc;
-    tr.write_point(cm);
+    // one MSM pipeline for the four permutation products and the lookup product
+    const Fp* cols[NUM_SETS + 1];
+    Fp blinds[NUM_SETS + 1];
+    Affine cms[NUM_SETS + 1];
+    for (int s = 0; s < NUM_SETS; s++) {
+      cols[s] = W->z_vals[s];
+      blinds[s] = z_blinds[s];
+    }
+    cols[NUM_SETS] = z;
+    blinds[NUM_SETS] = zl_blind;
+    if ((rc = commit_batch(ctx, cols, P.fb_gl, n, blinds, NUM_SETS + 1, cms))) return rc;
+    for (int s = 0; s <= NUM_SETS; s++) tr.write_point(cms[s]);
+    for (int s = 0; s < NUM_SETS; s++)
+      if ((rc = ntt_run(ctx, W->z_vals[s], (uint32_t)n, W->z_poly[s], k, inv))) return rc;
     if ((rc = ntt_run(ctx, z, (uint32_t)n, W->zl_poly, k, inv))) return rc;
   }
+  phase.mark("lookup product");
   // ---- vanishing argument: random polynomial ----------------------------------------------------------------
   if ((rc = random_poly_to_device(ctx, W, tape, n, W->random_poly))) return rc;
   const Fp random_blind = tape.next();
@@ -497,6 +540,7 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
   }
   const Fp y = tr.squeeze_challenge();
 
+  phase.mark("random poly commit");
   // ---- quotient (K5 + K6) ---------------------------------------------------------------------------------------
   {
     for (int c = 0; c < 12; c++)
@@ -544,12 +588,14 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
     o.coset_out_pow[1] = K.zeta;     // zeta^-2
     if ((rc = ntt_run(ctx, W->h, (uint32_t)en, W->h_coeffs, K.ek, o))) return rc;
   }
+  phase.mark("cosets + quotient + iNTT");
   Fp h_blinds[3];
   for (auto& b : h_blinds) b = tape.next();
-  for (int p = 0; p < 3; p++) {
-    Affine cm;
-    if ((rc = commit(ctx, W->h_coeffs + (size_t)p * n, P.fb_g, n,h_blinds[p], &cm))) return rc;
-    tr.write_point(cm);
+  {
+    const Fp* cols[3] = {W->h_coeffs, W->h_coeffs + n, W->h_coeffs + 2 * n};
+    Affine cms[3];
+    if ((rc = commit_batch(ctx, cols, P.fb_g, n, h_blinds, 3, cms))) return rc;
+    for (int p = 0; p < 3; p++) tr.write_point(cms[p]);
   }
 
   const Fp x = tr.squeeze_challenge();
@@ -561,6 +607,7 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
   };
   const Fp x_next = rotate(x, 1), x_prev = rotate(x, -1), x_last = rotate(x, -(BLINDING + 1));
 
+  phase.mark("h commit");
   // ---- evaluations (K9) -----------------------------------------------------------------------------------------
   // advice_queries / fixed_queries in first-use order of `configure` (docs/CIRCUIT.md §Queries)
   static const int ADVICE_QUERIES[24][2] = {{7, 0}, {8, 0},  {9, 0},  {1, 0},  {8, -1}, {8, 1},  {2, 0}, {7, 1},
@@ -596,6 +643,7 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
     for (auto& e : evals) tr.write_scalar(e);
   }
 
+  phase.mark("evaluations");
   // ---- multiopen (K10) --------------------------------------------------------------------------------------------
   struct OpenPoly {
     const Fp* poly;
@@ -719,6 +767,7 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
     }
   }
 
+  phase.mark("multiopen");
   // ---- inner product argument (K11) ------------------------------------------------------------------------------
   {
     if ((rc = random_poly_to_device(ctx, W, tape, n, W->s_poly))) return rc;
@@ -767,13 +816,22 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
       if ((rc = inner_product(ctx, pp + half, b, half, &vl))) return rc;
       if ((rc = inner_product(ctx, pp, b + half, half, &vr))) return rc;
       const Fp l_rand = tape.next(), r_rand = tape.next();
-      const uint32_t extra_idx[2] = {idx_u, idx_w};
-      const Fp extra_l[2] = {vl * z, l_rand}, extra_r[2] = {vr * z, r_rand};
-      XYZZ lj, rj;
-      if ((rc = msm_fixed(ctx, P.fb_g, cvec, n, extra_l, extra_idx, 2, &lj, (uint32_t)half, 0))) return rc;
-      if ((rc = msm_fixed(ctx, P.fb_g, cvec, n, extra_r, extra_idx, 2, &rj, (uint32_t)half, 1))) return rc;
-      tr.write_point(lj.to_affine());
-      tr.write_point(rj.to_affine());
+      // L and R share the scalar vector and differ in the index bit they keep: one pipeline, 2 jobs
+      MsmJob lr[2];
+      for (int side = 0; side < 2; side++) {
+        lr[side].scalars = cvec;
+        lr[side].n_extra = 2;
+        lr[side].extra[0] = (side == 0 ? vl : vr) * z;
+        lr[side].extra[1] = side == 0 ? l_rand : r_rand;
+        lr[side].extra_index[0] = idx_u;
+        lr[side].extra_index[1] = idx_w;
+        lr[side].side_mask = (uint32_t)half;
+        lr[side].side_select = side;
+      }
+      XYZZ lrj[2];
+      if ((rc = msm_fixed_batch(ctx, P.fb_g, lr, 2, n, lrj))) return rc;
+      tr.write_point(lrj[0].to_affine());
+      tr.write_point(lrj[1].to_affine());
       const Fp u = tr.squeeze_challenge();
       const Fp u_inv = u.inv();
       launch_map(ctx, half, [=] __device__(uint64_t i) {
@@ -791,6 +849,7 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
     tr.write_scalar(c);
     tr.write_scalar(f);
   }
+  phase.mark("ipa");
   ZK_CUDA(ctx, cudaGetLastError());
   proof_out = tr.proof();
   return ZK_OK;

@@ -66,6 +66,9 @@ void free_workspace(void* ws);
 
 // commit: MSM(scalars || blind, bases || w) -> affine (host)
 int32_t commit(zk_ctx* ctx, const Fp* d_scalars, const FixedBase& fb, uint64_t n, const Fp& blind, Affine* out);
+// the same for nb columns over one base in a single MSM pipeline (nb <= MSM_MAX_BATCH)
+int32_t commit_batch(zk_ctx* ctx, const Fp* const* d_scalars, const FixedBase& fb, uint64_t n, const Fp* blinds,
+                     int nb, Affine* out);
 // coefficients (n) -> evaluations on the extended coset zeta * <omega_ext> (en)
 int32_t coeff_to_extended(zk_ctx* ctx, const DeviceKeys& K, const Fp* coeffs, Fp* out);
 

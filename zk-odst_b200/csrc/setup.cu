@@ -220,6 +220,23 @@ int32_t commit(zk_ctx* ctx, const Fp* d_scalars, const FixedBase& fb, uint64_t n
   return ZK_OK;
 }
 
+int32_t commit_batch(zk_ctx* ctx, const Fp* const* d_scalars, const FixedBase& fb, uint64_t n, const Fp* blinds,
+                     int nb, Affine* out) {
+  MsmJob jobs[MSM_MAX_BATCH];
+  XYZZ r[MSM_MAX_BATCH];
+  if (nb > MSM_MAX_BATCH) return set_error(ctx, ZK_E_INVALID, "commit_batch: too many columns");
+  for (int m = 0; m < nb; m++) {
+    jobs[m].scalars = d_scalars[m];
+    jobs[m].n_extra = 1;
+    jobs[m].extra[0] = blinds[m];
+    jobs[m].extra_index[0] = (uint32_t)n;  // W follows the n base points in both tables
+  }
+  int32_t rc = msm_fixed_batch(ctx, fb, jobs, nb, n, r);
+  if (rc) return rc;
+  for (int m = 0; m < nb; m++) out[m] = r[m].to_affine();
+  return ZK_OK;
+}
+
 int32_t coeff_to_extended(zk_ctx* ctx, const DeviceKeys& K, const Fp* coeffs, Fp* out) {
   NttOptions opt;
   opt.coset_in = 1;
