@@ -8,15 +8,14 @@
 // (K7), grand products (K8), the quotient (K6), evaluations (K9), multiopen (K10) and the inner
 // product argument (K11).  The order of transcript writes, challenge squeezes and RNG draws is
 // halo2's; proof bytes are compared with the CPU oracle byte for byte in tests/.
-#include <atomic>
 #include <chrono>
 #include <cstdlib>
-#include <thread>
 
 #include "polyops.cuh"
 #include "prover_state.h"
 #include "quotient.h"
 #include "transcript.h"
+#include "xorshift_jump.h"
 
 namespace zkodst {
 
@@ -40,7 +39,6 @@ struct ProofWorkspace {
   Fp* q_polys[8] = {};
   Fp* h_poly = nullptr;
   Affine* g_fold = nullptr;  // n
-  uint64_t* raw = nullptr;   // n * 8 words of RNG output
   // lookup permutation tables
   Fp* table_vals = nullptr;      // 65536 compressed table values
   Fp* table_sorted = nullptr;    // ascending
@@ -96,7 +94,6 @@ int32_t get_workspace(zk_ctx* ctx, DeviceKeys& K, ProofWorkspace** out) {
     A(random_poly, n); A(s_poly, n); A(q_prime, n); A(p_poly, n); A(b_vec, n); A(h_poly, n);
     for (int s = 0; s < 8; s++) A(q_polys[s], n);
     A(g_fold, n);
-    A(raw, n * 8);
     A(table_vals, 65536); A(table_sorted, 65536);
     A(rank_of, 65536); A(counts, 65536 + 8); A(offsets, 65536 + 8); A(left_cnt, 65536 + 8); A(left_off, 65536 + 8);
     A(first_flag_scan, n + 8); A(left_rank, n + 8);
@@ -106,60 +103,67 @@ int32_t get_workspace(zk_ctx* ctx, DeviceKeys& K, ProofWorkspace** out) {
   return ZK_OK;
 }
 
-// ---- RNG tape: the whole XorShift stream of one proof, produced by a worker thread -----------------
-class RandomTape {
+// ---- prover randomness: the seeded XorShift stream, sequential on the host for the ~170 scalar draws of
+// a proof, generated on the device (jump-ahead, xorshift_jump.h) for the two n-element random polynomials
+constexpr int XS_FIELDS_PER_THREAD = 64;        // 1024 stream words per thread
+constexpr int XS_THREAD_SHIFT = 10;             // log2(16 * XS_FIELDS_PER_THREAD)
+
+__global__ void __launch_bounds__(128)
+xorshift_fields_kernel(XsState base, const XsMatrix* __restrict__ pow2, uint64_t n, Fp* __restrict__ out) {
+  const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t first = t * XS_FIELDS_PER_THREAD;
+  if (first >= n) return;
+  XsState st = base;
+  for (int b = 0; (t >> b) != 0; b++)
+    if ((t >> b) & 1) st = xs_apply(pow2[XS_THREAD_SHIFT + b], st);
+  const uint64_t last = first + XS_FIELDS_PER_THREAD < n ? first + XS_FIELDS_PER_THREAD : n;
+  for (uint64_t i = first; i < last; i++) {
+    uint64_t w[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const uint64_t lo = xs_step(st);
+      w[j] = lo | ((uint64_t)xs_step(st) << 32);
+    }
+    out[i] = Fp::from_u512(w);
+  }
+}
+
+class ProofRng {
  public:
-  RandomTape(const uint8_t seed[16], size_t total_fields) : words_(total_fields * 8), ready_(0), pos_(0) {
-    memcpy(seed_, seed, 16);
-    worker_ = std::thread([this] {
-      XorShift rng(seed_);
-      const size_t total = words_.size();
-      for (size_t i = 0; i < total; i += 8) {
-        rng.next_wide(&words_[i]);
-        if ((i & 0xfff8) == 0xfff8 || i + 8 >= total) ready_.store(i + 8, std::memory_order_release);
-      }
-    });
+  ProofRng(zk_ctx* ctx, const uint8_t seed[16]) : ctx_(ctx) {
+    memcpy(st_.s, seed, 16);
+    if (!(st_.s[0] | st_.s[1] | st_.s[2] | st_.s[3])) st_.s[0] = st_.s[1] = st_.s[2] = st_.s[3] = 0x0BAD5EED;
   }
-  ~RandomTape() {
-    if (worker_.joinable()) worker_.join();
+  Fp next() {  // Field::random: eight next_u64 (low word first) -> from_u512
+    uint64_t w[8];
+    for (int j = 0; j < 8; j++) {
+      const uint64_t lo = xs_step(st_);
+      w[j] = lo | ((uint64_t)xs_step(st_) << 32);
+    }
+    return Fp::from_u512(w);
   }
-  // raw words of the next `count` field elements
-  const uint64_t* take(size_t count) {
-    size_t need = (pos_ + count) * 8;
-    if (need > words_.size()) throw std::runtime_error("RNG tape exhausted");
-    while (ready_.load(std::memory_order_acquire) < need) std::this_thread::yield();
-    const uint64_t* p = &words_[pos_ * 8];
-    pos_ += count;
-    return p;
+  // the next n field elements of the stream, produced on the device
+  int32_t fill_device(uint64_t n, Fp* out) {
+    int32_t rc = ensure_buf(ctx_, ctx_->misc_ws, sizeof(XsMatrix) * XS_JUMP_POWERS);
+    if (rc) return rc;
+    if (!ctx_->xs_table_loaded) {
+      ZK_CUDA(ctx_, cudaMemcpyAsync(ctx_->misc_ws.ptr, xs_jump_table(), sizeof(XsMatrix) * XS_JUMP_POWERS,
+                                    cudaMemcpyHostToDevice, ctx_->stream));
+      ctx_->xs_table_loaded = true;
+    }
+    const uint64_t threads = (n + XS_FIELDS_PER_THREAD - 1) / XS_FIELDS_PER_THREAD;
+    xorshift_fields_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, ctx_->stream>>>(
+        st_, (const XsMatrix*)ctx_->misc_ws.ptr, n, out);
+    ctx_->launches++;
+    ZK_CUDA(ctx_, cudaGetLastError());
+    st_ = xs_jump(st_, n * 16);
+    return ZK_OK;
   }
-  Fp next() { return Fp::from_u512(take(1)); }
 
  private:
-  std::vector<uint64_t> words_;
-  std::atomic<size_t> ready_;
-  size_t pos_;
-  uint8_t seed_[16];
-  std::thread worker_;
+  zk_ctx* ctx_;
+  XsState st_;
 };
-
-__global__ void from_u512_kernel2(const uint64_t* __restrict__ raw, uint64_t n, Fp* __restrict__ out) {
-  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  uint64_t w[8];
-#pragma unroll
-  for (int j = 0; j < 8; j++) w[j] = raw[8 * i + j];
-  out[i] = Fp::from_u512(w);
-}
-
-// n random field elements from the tape -> device
-int32_t random_poly_to_device(zk_ctx* ctx, ProofWorkspace* W, RandomTape& tape, uint64_t n, Fp* out) {
-  const uint64_t* raw = tape.take(n);
-  ZK_CUDA(ctx, cudaMemcpyAsync(W->raw, raw, n * 64, cudaMemcpyHostToDevice, ctx->stream));
-  from_u512_kernel2<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(W->raw, n, out);
-  ctx->launches++;
-  ZK_CUDA(ctx, cudaGetLastError());
-  return ZK_OK;
-}
 
 int32_t upload_fp(zk_ctx* ctx, Fp* dst, const Fp* src, size_t count) {
   ZK_CUDA(ctx, cudaMemcpyAsync(dst, src, count * sizeof(Fp), cudaMemcpyHostToDevice, ctx->stream));
@@ -196,6 +200,52 @@ __global__ void lookup_compress_kernel(const Fp* __restrict__ c0, const Fp* __re
                                        const Fp* __restrict__ c2, Fp theta, uint64_t n, Fp* __restrict__ out) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i < n) out[i] = (c0[i] * theta + c1[i]) * theta + c2[i];
+}
+// Ascending order of the 65536 compressed table rows (field `Ord` = canonical integer order):
+// rank by counting, top limbs staged through shared memory; equal top limbs (probability ~2^-30
+// per proof) fall back to a full comparison, equal values raise status 3 (theta collision).
+__global__ void table_keys_kernel(const Fp* __restrict__ vals, uint64_t* __restrict__ keys) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 65536) return;
+  uint64_t c[4];
+  vals[i].to_canonical(c);
+#pragma unroll
+  for (int l = 0; l < 4; l++) keys[(size_t)l * 65536 + i] = c[l];  // limb-major
+}
+constexpr int RANK_TILE = 2048;
+__global__ void __launch_bounds__(256)
+table_rank_kernel(const uint64_t* __restrict__ keys, const Fp* __restrict__ vals, uint32_t* __restrict__ rank_of,
+                  Fp* __restrict__ sorted, int* __restrict__ status) {
+  __shared__ uint64_t top[RANK_TILE];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t* k3 = keys + (size_t)3 * 65536;
+  const uint64_t mine = k3[i];
+  uint32_t cnt = 0;
+  for (uint32_t base = 0; base < 65536; base += RANK_TILE) {
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < RANK_TILE; j += blockDim.x) top[j] = k3[base + j];
+    __syncthreads();
+#pragma unroll 8
+    for (uint32_t j = 0; j < RANK_TILE; j++) {
+      const uint64_t t = top[j];
+      cnt += t < mine ? 1u : 0u;
+      if (t == mine && base + j != i) {  // rare: decide on the lower limbs
+        const uint32_t o = base + j;
+        bool less = false, equal = true;
+        for (int l = 2; l >= 0 && equal; l--) {
+          const uint64_t a = keys[(size_t)l * 65536 + o], b = keys[(size_t)l * 65536 + i];
+          if (a != b) {
+            equal = false;
+            less = a < b;
+          }
+        }
+        if (equal) atomicExch(status, 3);
+        cnt += less ? 1u : 0u;
+      }
+    }
+  }
+  rank_of[i] = cnt;
+  sorted[cnt < 65536 ? cnt : 0] = vals[i];
 }
 __global__ void lookup_count_kernel(const Fp* __restrict__ dense_col, const Fp* __restrict__ cin,
                                     const Fp* __restrict__ table_vals, const uint32_t* __restrict__ rank_of,
@@ -342,8 +392,7 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
   const unsigned T = 256;
   auto blocks = [&](uint64_t cnt) { return (unsigned)((cnt + T - 1) / T); };
 
-  const size_t total_draws = 12 * 6 + 12 + 12 + 2 + NUM_SETS * 6 + 6 + (n + 1) + 3 + 1 + (n + 1) + 2 * (size_t)k;
-  RandomTape tape(seed, total_draws);
+  ProofRng tape(ctx, seed);
   TranscriptWriter tr;
   tr.common_scalar(K.transcript_repr);
 
@@ -387,36 +436,13 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
     lookup_compress_kernel<<<blocks(n), T, 0, st>>>(K.fixed_values[0], K.fixed_values[1], K.fixed_values[2], theta,
                                                     n, W->ctab);
     ctx->launches += 2;
-    // table values = compressed table rows 0..65535; sort them on the host (2 MB, once per proof)
-    std::vector<Fp> tv(65536);
-    ZK_CUDA(ctx, cudaMemcpyAsync(tv.data(), W->ctab, 65536 * sizeof(Fp), cudaMemcpyDeviceToHost, st));
-    ZK_CUDA(ctx, cudaStreamSynchronize(st));
-    struct Key {
-      uint64_t c[4];
-      uint32_t idx;
-    };
-    std::vector<Key> keys(65536);
-    for (uint32_t j = 0; j < 65536; j++) {
-      tv[j].to_canonical(keys[j].c);
-      keys[j].idx = j;
-    }
-    std::sort(keys.begin(), keys.end(), [](const Key& a, const Key& b) {
-      for (int l = 3; l >= 0; l--)
-        if (a.c[l] != b.c[l]) return a.c[l] < b.c[l];
-      return a.idx < b.idx;
-    });
-    std::vector<uint32_t> rank_of(65536);
-    std::vector<Fp> sorted(65536);
-    for (uint32_t r = 0; r < 65536; r++) {
-      rank_of[keys[r].idx] = r;
-      sorted[r] = tv[keys[r].idx];
-    }
-    for (uint32_t r = 1; r < 65536; r++)
-      if (sorted[r] == sorted[r - 1]) return set_error(ctx, ZK_E_VERIFY, "theta collision in the spread table");
-    const uint32_t zero_rank = rank_of[0];  // table row 0 = (0,0,0) compresses to 0, the minimum
-    ZK_CUDA(ctx, cudaMemcpyAsync(W->table_vals, tv.data(), 65536 * sizeof(Fp), cudaMemcpyHostToDevice, st));
-    ZK_CUDA(ctx, cudaMemcpyAsync(W->table_sorted, sorted.data(), 65536 * sizeof(Fp), cudaMemcpyHostToDevice, st));
-    ZK_CUDA(ctx, cudaMemcpyAsync(W->rank_of, rank_of.data(), 65536 * 4, cudaMemcpyHostToDevice, st));
+    // table values = compressed table rows 0..65535, ranked on the device
+    uint64_t* keys = (uint64_t*)W->tmp_a;  // 65536 x 4 limbs, limb-major (tmp_a holds n >= 2^16 elements)
+    table_keys_kernel<<<256, 256, 0, st>>>(W->ctab, keys);
+    table_rank_kernel<<<256, 256, 0, st>>>(keys, W->ctab, W->rank_of, W->table_sorted, ctx->d_status);
+    ZK_CUDA(ctx, cudaMemcpyAsync(W->table_vals, W->ctab, 65536 * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
+    ctx->launches += 2;
+    const uint32_t zero_rank = 0;  // table row 0 = (0,0,0) compresses to 0, the minimum
     ZK_CUDA(ctx, cudaMemsetAsync(W->counts, 0, 65536 * 4, st));
     lookup_count_kernel<<<blocks(usable), T, 0, st>>>(adv(8), W->cin, W->table_vals, W->rank_of, usable, W->counts,
                                                       ctx->d_status);
@@ -438,7 +464,8 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
     ZK_CUDA(ctx, cudaStreamSynchronize(st));
     if (status) {
       cudaMemsetAsync(ctx->d_status, 0, 4, st);
-      return set_error(ctx, ZK_E_VERIFY, "lookup input not in the spread table (ConstraintSystemFailure)");
+      return set_error(ctx, ZK_E_VERIFY, status == 3 ? "theta collision in the spread table"
+                                                     : "lookup input not in the spread table (ConstraintSystemFailure)");
     }
     lookup_fill_table_kernel<<<blocks(usable), T, 0, st>>>(W->pin, first_flag, W->first_flag_scan, W->left_rank,
                                                            W->table_sorted, usable, n_repeated, W->ptab);
@@ -531,7 +558,7 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
   }
   phase.mark("lookup product");
   // ---- vanishing argument: random polynomial ----------------------------------------------------------------
-  if ((rc = random_poly_to_device(ctx, W, tape, n, W->random_poly))) return rc;
+  if ((rc = tape.fill_device(n, W->random_poly))) return rc;
   const Fp random_blind = tape.next();
   {
     Affine cm;
@@ -770,7 +797,7 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
   phase.mark("multiopen");
   // ---- inner product argument (K11) ------------------------------------------------------------------------------
   {
-    if ((rc = random_poly_to_device(ctx, W, tape, n, W->s_poly))) return rc;
+    if ((rc = tape.fill_device(n, W->s_poly))) return rc;
     Fp* sp = W->s_poly;
     {
       EvalJob j{sp, x3};

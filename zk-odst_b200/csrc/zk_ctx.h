@@ -62,6 +62,7 @@ struct zk_ctx {
   std::map<int, zkodst::NttTables> ntt_tables;
   int* d_status = nullptr;  // device-side error flag (bad EIP-152 record seen by a kernel)
   int sm_count = 148;
+  bool xs_table_loaded = false;  // XorShift jump matrices resident in misc_ws (prover.cu)
 };
 
 namespace zkodst {
