@@ -157,6 +157,25 @@ int32_t zk_create_proof(zk_ctx* ctx, const uint8_t* inputs, uint64_t n_compressi
 int32_t zk_create_proof_device_inputs(zk_ctx* ctx, const uint8_t* d_inputs, uint64_t n_compressions,
                                       const uint8_t seed[16], uint8_t* proof_out, uint64_t* proof_len);
 
+/* ---- one MSM split across the GPUs of a box (BASELINE configs[3]) --------------
+ * The reference is single-threaded and has no counterpart; these calls are what a multi-process
+ * Rust harness (one process per GPU) adds around `Params::new` / `create_proof`
+ * (blake2f-circuit/benches/blake2f.rs:85,125).  After zk_dist_init every MSM of the context
+ * (`Params::commit`, `commit_lagrange`, the IPA rounds) covers only this rank's contiguous range
+ * of the base points; the per-rank partial points are all-gathered over NCCL and summed, so all
+ * ranks obtain the same commitment and — fed the same records and seed — the same proof bytes as
+ * a single GPU.  Everything that is not an MSM runs replicated.
+ *   rank 0: zk_dist_unique_id(id); share id with the other ranks by any means
+ *   all:    zk_ctx_create; zk_dist_init(ctx, id, rank, world); params; keygen; create_proof */
+#define ZK_DIST_ID_BYTES 128
+int32_t zk_dist_unique_id(uint8_t out[ZK_DIST_ID_BYTES]);
+/* Collective over the group; must precede zk_params_* on the context.  world == 1 is a no-op. */
+int32_t zk_dist_init(zk_ctx* ctx, const uint8_t id[ZK_DIST_ID_BYTES], int32_t rank, int32_t world);
+int32_t zk_dist_info(const zk_ctx* ctx, int32_t* rank, int32_t* world);
+/* The contiguous range [lo, hi) of the n base points that `rank` of `world` tabulates and sums
+ * (host-only helper; the partition the MSM split uses). */
+int32_t zk_dist_range(uint64_t n_points, int32_t rank, int32_t world, uint64_t* lo, uint64_t* hi);
+
 #ifdef __cplusplus
 }
 #endif

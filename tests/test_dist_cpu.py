@@ -1,0 +1,76 @@
+"""Host logic of the MSM split on CPU, world_size 2 over gloo: every rank sums
+the terms of its zk_dist_range slice, the partial points are all-gathered and added — the result
+must equal the unsplit MSM bit for bit.  The arithmetic here is the oracle's (this is a test of
+the partition / exchange / combine structure that dist.cu implements over NCCL)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+SEED = bytes(range(1, 17))
+K = 10
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, n, out_path):
+    import torch
+    import torch.distributed as dist
+    import oracle_lib
+    import zk_odst_b200 as zk
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    oracle = oracle_lib.load()
+    p = oracle_lib.OracleProver(oracle, k=K, seed=SEED)
+    bases = p.points(0, 1 << K)[:n]
+    p.close()
+    scalars = oracle_lib.random_fields(oracle, SEED, n)
+    lo, hi = zk.dist_range(n, rank, world)
+    if hi > lo:
+        part = oracle_lib.msm(oracle, np.ascontiguousarray(scalars[lo:hi]), np.ascontiguousarray(bases[lo:hi]))
+    else:
+        part = np.zeros(8, dtype=np.uint64)
+    mine = torch.from_numpy(part.view(np.int64).copy())
+    gathered = [torch.zeros(8, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    parts = np.stack([g.numpy().view(np.uint64) for g in gathered])
+    one = oracle_lib.Oracle._limbs(oracle.field_op(0, 4, 1)[1])
+    ones = np.tile(np.array(one, dtype=np.uint64), (world, 1))
+    total = oracle_lib.msm(oracle, np.ascontiguousarray(ones), np.ascontiguousarray(parts.reshape(world, 8)))
+    whole = oracle_lib.msm(oracle, scalars, np.ascontiguousarray(bases))
+    ok = np.array_equal(total, whole)
+    with open(out_path + ".%d" % rank, "w") as f:
+        f.write("ok" if ok else "mismatch")
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [1, 2, 777, 1 << K])
+def test_range_split_msm_world2(tmp_path, n):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    out = str(tmp_path / "res")
+    mp.spawn(_worker, args=(2, port, n, out), nprocs=2, join=True)
+    for r in range(2):
+        assert open(out + ".%d" % r).read() == "ok"
+
+
+def test_ranges_partition_the_points():
+    import zk_odst_b200 as zk
+    for n in (0, 1, 5, 1 << 19, (1 << 23) + 3):
+        for world in (1, 2, 3, 4, 8):
+            prev = 0
+            for r in range(world):
+                lo, hi = zk.dist_range(n, r, world)
+                assert lo == prev and hi >= lo
+                prev = hi
+            assert prev == n

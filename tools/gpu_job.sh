@@ -1,4 +1,3 @@
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_gpu.log
-ZK_PHASE_TRACE=1 timeout 300 python tools/profile_proof.py 19 64 1 > gpurun_out/phase.log 2>&1; echo "phase rc=$?"; tail -14 gpurun_out/phase.log
-timeout 300 python tools/profile_proof.py 19 64 5 2>&1 | tail -1
+timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:fixed_accumulate_kernel -s 8 -c 2 -o gpurun_out/prof_fixed_accumulate_v2 -f python tools/profile_proof.py 19 64 1 > gpurun_out/ncu2.log 2>&1; echo "ncu-full rc=$?"

@@ -12,5 +12,7 @@ from .binding import (  # noqa: F401
     rows_per_compression,
     min_k,
     layout_hash,
+    dist_unique_id,
+    dist_range,
 )
 from .inputs import eip152_record, synthetic_inputs, XorShiftRng, REFERENCE_SEED  # noqa: F401

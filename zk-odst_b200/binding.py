@@ -58,6 +58,10 @@ def load_library():
             "zk_ntt_fp": (i32, [vp, vp, i32, i32, i32]),
             "zk_blake2f_witness_batch": (i32, [vp, i32, u32, vp, u64, vp, vp]),
             "zk_blake2f_witness_batch_device": (i32, [vp, i32, u32, vp, u64, vp, vp]),
+            "zk_dist_unique_id": (i32, [c.c_char_p]),
+            "zk_dist_init": (i32, [vp, c.c_char_p, i32, i32]),
+            "zk_dist_info": (i32, [vp, c.POINTER(i32), c.POINTER(i32)]),
+            "zk_dist_range": (i32, [u64, i32, i32, c.POINTER(u64), c.POINTER(u64)]),
         }
         for name, (res, args) in sigs.items():
             fn = getattr(lib, name)
@@ -65,6 +69,22 @@ def load_library():
             fn.argtypes = args
         _LIB = lib
     return _LIB
+
+
+def dist_unique_id():
+    buf = ctypes.create_string_buffer(128)
+    rc = load_library().zk_dist_unique_id(buf)
+    if rc:
+        raise ZkError(rc, "zk_dist_unique_id failed (libnccl.so.2 missing?)")
+    return buf.raw
+
+
+def dist_range(n_points, rank, world):
+    lo, hi = ctypes.c_uint64(), ctypes.c_uint64()
+    rc = load_library().zk_dist_range(n_points, rank, world, ctypes.byref(lo), ctypes.byref(hi))
+    if rc:
+        raise ZkError(rc)
+    return lo.value, hi.value
 
 
 def rows_per_compression(rounds):
@@ -161,6 +181,17 @@ class Context:
         out = ctypes.c_double()
         self._check(self.lib.zk_bench_int_pipe(self.h, mode, iters, ctypes.byref(out)))
         return out.value
+
+    # ---- one MSM split across GPUs (zk_dist_*) -------------------------------------------
+    def dist_init(self, unique_id, rank, world):
+        """Joins the NCCL group described by `unique_id` (128 bytes from dist_unique_id() on
+        rank 0, shared by the caller); must precede params_* on this context."""
+        self._check(self.lib.zk_dist_init(self.h, bytes(unique_id), rank, world))
+
+    def dist_info(self):
+        r, w = ctypes.c_int32(), ctypes.c_int32()
+        self._check(self.lib.zk_dist_info(self.h, ctypes.byref(r), ctypes.byref(w)))
+        return r.value, w.value
 
     # ---- params / keygen / prove ---------------------------------------------------------
     def params_generate_substitute(self, k, seed):

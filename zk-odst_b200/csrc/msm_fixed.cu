@@ -98,8 +98,8 @@ __device__ __forceinline__ uint32_t aggregated_add(uint32_t* counters, uint32_t 
 }
 
 // entries_tmp[((job * nwin + w) * stride) + t] = bucket + 1 | sign << 31   (0 = no entry)
-__global__ void fixed_digits_kernel(DevJobs jobs, uint64_t count, const Fp* __restrict__ extra, int c, int nwin,
-                                    uint64_t stride, uint32_t B, uint32_t* __restrict__ entries_tmp,
+__global__ void fixed_digits_kernel(DevJobs jobs, uint64_t count, uint64_t lo, const Fp* __restrict__ extra, int c,
+                                    int nwin, uint64_t stride, uint32_t B, uint32_t* __restrict__ entries_tmp,
                                     uint32_t* __restrict__ counts) {
   const int job = blockIdx.y;
   uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -110,9 +110,9 @@ __global__ void fixed_digits_kernel(DevJobs jobs, uint64_t count, const Fp* __re
   if (t < count) {
     // optional support mask (IPA rounds): keep index t only if ((t & mask) != 0) == side_select
     const uint32_t mask = jobs.side_mask[job];
-    if (mask && (((t & mask) != 0) != (jobs.side_select[job] != 0))) zero = true;
+    if (mask && ((((lo + t) & mask) != 0) != (jobs.side_select[job] != 0))) zero = true;
     if (!zero) {
-      Fp v = jobs.scalars[job][t];
+      Fp v = jobs.scalars[job][lo + t];
       zero = v.is_zero();
       if (!zero) v.to_canonical(s);
     }
@@ -230,7 +230,7 @@ __global__ void fixed_scatter_kernel(DevJobs jobs, const uint32_t* __restrict__ 
   uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   const uint64_t total = count + jobs.n_extra[job];
   if (t >= total) return;
-  const uint32_t point = t < count ? (uint32_t)t : extra_index[job * 4 + (t - count)];
+  const uint32_t point = t < count ? (uint32_t)t : extra_index[job * 4 + (t - count)];  // local indices
   const uint32_t* my_tmp = entries_tmp + (size_t)job * nwin * stride + t;
   uint32_t* my_cursor = cursor + (size_t)job * B;
   const uint32_t* my_offsets = offsets + (size_t)job * B;
@@ -421,14 +421,25 @@ int fixed_window_bits(uint64_t npoints) {
   return 16;
 }
 
-int32_t fixed_base_build(zk_ctx* ctx, const Affine* d_bases, uint64_t npoints, FixedBase* out) {
+int32_t fixed_base_build(zk_ctx* ctx, const Affine* d_bases, uint64_t total_main, uint64_t n_extra,
+                         FixedBase* out) {
   FixedBase fb;
-  fb.c = fixed_window_bits(npoints);
+  fb.c = fixed_window_bits(total_main + n_extra);
   fb.nwin = (255 + fb.c - 1) / fb.c + ((255 % fb.c) == 0 ? 1 : 0);
-  fb.npoints = npoints;
+  uint64_t hi = 0;
+  dist_range(total_main, ctx->dist_rank, ctx->dist_world, &fb.lo, &hi);
+  fb.nmain = hi - fb.lo;
+  fb.total_main = total_main;
+  fb.nextra = ctx->dist_rank == 0 ? n_extra : 0;
+  fb.npoints = fb.nmain + fb.nextra;
+  const uint64_t npoints = fb.npoints;
   if ((uint64_t)fb.nwin * npoints >= 0x7fffffffull) return set_error(ctx, ZK_E_INVALID, "msm table too large");
   ZK_CUDA(ctx, cudaMalloc((void**)&fb.table, (size_t)fb.nwin * npoints * sizeof(Affine)));
-  ZK_CUDA(ctx, cudaMemcpyAsync(fb.table, d_bases, npoints * sizeof(Affine), cudaMemcpyDeviceToDevice, ctx->stream));
+  ZK_CUDA(ctx, cudaMemcpyAsync(fb.table, d_bases + fb.lo, fb.nmain * sizeof(Affine), cudaMemcpyDeviceToDevice,
+                               ctx->stream));
+  if (fb.nextra)
+    ZK_CUDA(ctx, cudaMemcpyAsync(fb.table + fb.nmain, d_bases + total_main, fb.nextra * sizeof(Affine),
+                                 cudaMemcpyDeviceToDevice, ctx->stream));
   for (int w = 1; w < fb.nwin; w++) {
     table_next_kernel<<<(unsigned)((npoints + 127) / 128), 128, 0, ctx->stream>>>(
         fb.table + (size_t)(w - 1) * npoints, fb.table + (size_t)w * npoints, npoints, fb.c);
@@ -444,11 +455,17 @@ void fixed_base_free(FixedBase& fb) {
   fb = FixedBase();
 }
 
-int32_t msm_fixed_batch(zk_ctx* ctx, const FixedBase& fb, const MsmJob* jobs, int nb, uint64_t count,
+int32_t msm_fixed_batch(zk_ctx* ctx, const FixedBase& fb, const MsmJob* jobs, int nb, uint64_t global_count,
                         XYZZ* results) {
-  if (nb < 1 || nb > MSM_MAX_BATCH || count > fb.npoints) return set_error(ctx, ZK_E_INVALID, "msm_fixed: bad sizes");
-  for (int m = 0; m < nb; m++)
+  if (nb < 1 || nb > MSM_MAX_BATCH || global_count > fb.total_main)
+    return set_error(ctx, ZK_E_INVALID, "msm_fixed: bad sizes");
+  for (int m = 0; m < nb; m++) {
     if (jobs[m].n_extra < 0 || jobs[m].n_extra > 4) return set_error(ctx, ZK_E_INVALID, "msm_fixed: bad extras");
+    for (int e = 0; e < jobs[m].n_extra; e++)
+      if (jobs[m].extra_index[e] < fb.total_main) return set_error(ctx, ZK_E_INVALID, "msm_fixed: extra index");
+  }
+  // this rank's share of the terms: global indices [lo, lo + count)
+  const uint64_t count = global_count <= fb.lo ? 0 : std::min<uint64_t>(global_count - fb.lo, fb.nmain);
   cudaStream_t st = ctx->stream;
   const int c = fb.c, nwin = fb.nwin;
   const uint32_t B = 1u << (c - 1);
@@ -516,12 +533,13 @@ int32_t msm_fixed_batch(zk_ctx* ctx, const FixedBase& fb, const MsmJob* jobs, in
     dj.scalars[m] = j.scalars;
     dj.side_mask[m] = j.side_mask;
     dj.side_select[m] = j.side_select;
-    dj.n_extra[m] = m < nb ? j.n_extra : 0;
+    const int ne = (m < nb && fb.nextra) ? j.n_extra : 0;  // extras live on rank 0 only
+    dj.n_extra[m] = ne;
     for (int e = 0; e < 4; e++) {
-      h_extra[m * 4 + e] = (m < nb && e < j.n_extra) ? j.extra[e] : Fp::zero();
-      h_eidx[m * 4 + e] = (m < nb && e < j.n_extra) ? j.extra_index[e] : 0;
+      h_extra[m * 4 + e] = e < ne ? j.extra[e] : Fp::zero();
+      h_eidx[m * 4 + e] = e < ne ? (uint32_t)(j.extra_index[e] - fb.total_main + fb.nmain) : 0;
     }
-    if (m < nb && j.n_extra) any_extra = true;
+    if (ne) any_extra = true;
   }
   if (any_extra) {
     // pageable copies: the runtime stages them before returning, so the stack arrays may go away
@@ -534,7 +552,7 @@ int32_t msm_fixed_batch(zk_ctx* ctx, const FixedBase& fb, const MsmJob* jobs, in
     KernelTimer timer(ctx, KC_MSM);
     const int T = 256;
     const dim3 gt((unsigned)((stride + T - 1) / T), (unsigned)nb);
-    fixed_digits_kernel<<<gt, T, 0, st>>>(dj, count, d_extra, c, nwin, stride, B, tmp, counts);
+    fixed_digits_kernel<<<gt, T, 0, st>>>(dj, count, fb.lo, d_extra, c, nwin, stride, B, tmp, counts);
     fscan_tiles_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(counts, offsets, tiles, NB);
     fscan_sums_kernel<<<1, 1024, 0, st>>>(tiles, ntiles);
     fscan_add_kernel<<<(NB + T - 1) / T, T, 0, st>>>(offsets, tiles, counts, NB, resident, plan);
@@ -571,6 +589,10 @@ int32_t msm_fixed_batch(zk_ctx* ctx, const FixedBase& fb, const MsmJob* jobs, in
     }
     for (int d = 0; (1 << d) < SEG; d++) weighted = weighted.dbl();
     results[m] = sm[0].add(weighted);
+  }
+  if (ctx->dist_world > 1) {
+    int32_t drc = dist_sum_points(ctx, results, nb);
+    if (drc) return drc;
   }
   if (trace) {
     double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();

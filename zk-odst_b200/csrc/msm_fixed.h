@@ -7,12 +7,20 @@ namespace zkodst {
 
 struct FixedBase {
   int c = 0, nwin = 0;
-  uint64_t npoints = 0;
-  Affine* table = nullptr;  // [nwin][npoints]: table[w][i] = 2^(c w) * base_i
+  uint64_t npoints = 0;     // local table width = nmain + nextra
+  uint64_t lo = 0;          // global index of the first main point held here
+  uint64_t nmain = 0;       // main points held here: global indices [lo, lo + nmain)
+  uint64_t total_main = 0;  // main points of the whole base; extras have global index >= total_main
+  uint64_t nextra = 0;      // extra points (W, U) held here: all of them on rank 0, none elsewhere
+  Affine* table = nullptr;  // [nwin][npoints]: table[w][i] = 2^(c w) * local point i
 };
 
 int fixed_window_bits(uint64_t npoints);
-int32_t fixed_base_build(zk_ctx* ctx, const Affine* d_bases, uint64_t npoints, FixedBase* out);
+// d_bases: total_main main points followed by n_extra extra points (global indexing).  With the
+// context in a multi-GPU group (dist.cu) only this rank's contiguous range of the main points is
+// tabulated (and the extras on rank 0).
+int32_t fixed_base_build(zk_ctx* ctx, const Affine* d_bases, uint64_t total_main, uint64_t n_extra,
+                         FixedBase* out);
 void fixed_base_free(FixedBase& fb);
 
 constexpr int MSM_MAX_BATCH = 16;

@@ -200,9 +200,9 @@ int32_t install_params(zk_ctx* ctx, int k, Affine* g, Affine* g_lagrange, const 
   ZK_CUDA(ctx, cudaMemcpyAsync(g + n, &S->params.w, sizeof(Affine), cudaMemcpyHostToDevice, ctx->stream));
   ZK_CUDA(ctx, cudaMemcpyAsync(g + n + 1, &S->params.u, sizeof(Affine), cudaMemcpyHostToDevice, ctx->stream));
   ZK_CUDA(ctx, cudaMemcpyAsync(g_lagrange + n, &S->params.w, sizeof(Affine), cudaMemcpyHostToDevice, ctx->stream));
-  int32_t rc = fixed_base_build(ctx, g, n + 2, &S->params.fb_g);
+  int32_t rc = fixed_base_build(ctx, g, n, 2, &S->params.fb_g);
   if (rc) return rc;
-  rc = fixed_base_build(ctx, g_lagrange, n + 1, &S->params.fb_gl);
+  rc = fixed_base_build(ctx, g_lagrange, n, 1, &S->params.fb_gl);
   if (rc) return rc;
   ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   S->has_params = true;

@@ -62,6 +62,10 @@ struct zk_ctx {
   std::map<int, zkodst::NttTables> ntt_tables;
   int* d_status = nullptr;  // device-side error flag (bad EIP-152 record seen by a kernel)
   int sm_count = 148;
+  // MSM split across GPUs (dist.cu): NCCL communicator (ncclComm_t), this rank, group size
+  void* nccl_comm = nullptr;
+  int dist_rank = 0, dist_world = 1;
+  zkodst::DevBuf dist_buf;
   bool xs_table_loaded = false;  // XorShift jump matrices resident in misc_ws (prover.cu)
 };
 
@@ -98,6 +102,12 @@ struct KernelTimer {  // CUDA-event bracket on the context's stream, only when t
     int32_t _rc = zkodst::check_cuda((ctx), (call), #call);       \
     if (_rc) return _rc;                                          \
   } while (0)
+
+// dist.cu
+struct XYZZ;
+void dist_range(uint64_t n, int rank, int world, uint64_t* lo, uint64_t* hi);
+int32_t dist_sum_points(zk_ctx* ctx, XYZZ* results, int nb);
+void dist_free(zk_ctx* ctx);
 
 // witness.cu
 int32_t launch_witness(zk_ctx* ctx, int32_t k, uint32_t rounds, const uint8_t* d_inputs,
