@@ -157,6 +157,21 @@ int32_t zk_create_proof(zk_ctx* ctx, const uint8_t* inputs, uint64_t n_compressi
 int32_t zk_create_proof_device_inputs(zk_ctx* ctx, const uint8_t* d_inputs, uint64_t n_compressions,
                                       const uint8_t seed[16], uint8_t* proof_out, uint64_t* proof_len);
 
+/* verify_proof with the SingleVerifier strategy (blake2f-circuit/benches/blake2f.rs:138-144:
+ * `verify_proof(&params, pk.get_vk(), SingleVerifier::new(&params), &[&[]], &mut Blake2bRead)`)
+ * against the context's params and keys.  ZK_OK = accepted; ZK_E_VERIFY = rejected (reason in
+ * zk_last_error: malformed encoding, truncated / trailing bytes, final MSM not the identity). */
+int32_t zk_verify_proof(zk_ctx* ctx, const uint8_t* proof, uint64_t proof_len);
+
+/* `MockProver::run(k, &circuit, vec![]).verify()` (blake2f/table16/spread_table.rs:759-763) for the
+ * BLAKE2f circuit of the context's keys: every gate on every usable row, every lookup input against
+ * the spread table, every copy constraint.  The witness comes from `inputs` (n_compressions x 213 B,
+ * host) or, when advice_override is not NULL, from that host buffer (ZK_NUM_ADVICE x 2^k x 32 B,
+ * column-major Montgomery cells, the layout of zk_blake2f_witness_batch).  ZK_E_VERIFY on the first
+ * failure, described in failure[3] = {kind (1 gate, 2 lookup, 3 copy), row, gate / copy index}. */
+int32_t zk_mock_verify(zk_ctx* ctx, const uint8_t* inputs, uint64_t n_compressions,
+                       const void* advice_override, uint64_t failure[3]);
+
 /* ---- one MSM split across the GPUs of a box (BASELINE configs[3]) --------------
  * The reference is single-threaded and has no counterpart; these calls are what a multi-process
  * Rust harness (one process per GPU) adds around `Params::new` / `create_proof`

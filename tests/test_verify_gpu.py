@@ -1,0 +1,90 @@
+"""verify_proof and the MockProver-equivalent checker through the C ABI (zk_verify_proof,
+zk_mock_verify), cross-checked against the oracle: each side must accept the other's proofs and
+both must reject the same tampered ones."""
+import numpy as np
+import pytest
+
+import oracle_lib
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def setup(oracle, zk):
+    seed = zk.REFERENCE_SEED
+    ctx = zk.Context(0)
+    ctx.params_generate_substitute(17, seed)
+    ctx.keygen(12, 2)
+    op = oracle_lib.OracleProver(oracle, k=17, seed=seed)
+    op.keygen(12, 2)
+    inputs = zk.synthetic_inputs(2)
+    yield ctx, op, seed, inputs
+    op.close()
+    ctx.close()
+
+
+def test_device_verifier_accepts_device_and_oracle_proofs(setup):
+    ctx, op, seed, inputs = setup
+    proof = ctx.create_proof(inputs, 2, seed)
+    assert ctx.verify_proof(proof), ctx.last_error()
+    assert op.verify(proof)[0] == 0
+    ref = op.create_proof(inputs, 2, bytes(range(16)))  # a different prover seed
+    assert ref != proof
+    assert ctx.verify_proof(ref), ctx.last_error()
+
+
+def test_tampering_is_rejected_like_the_oracle(setup):
+    ctx, op, seed, inputs = setup
+    proof = ctx.create_proof(inputs, 2, seed)
+    n_points_head = 12 + 2 + 4 + 1 + 1 + 3  # commitments before the evaluations
+    offsets = [5, 32 * 13 + 3, 32 * n_points_head + 7, 32 * (n_points_head + 30) + 1,
+               len(proof) - 40, len(proof) - 1]
+    for off in offsets:
+        bad = bytearray(proof)
+        bad[off] ^= 0x04
+        mine = ctx.verify_proof(bytes(bad))
+        theirs = op.verify(bytes(bad))[0] == 0
+        assert not mine and not theirs, off
+    assert not ctx.verify_proof(proof[:-32])            # truncated
+    assert not ctx.verify_proof(proof + b"\x00" * 32)   # trailing bytes
+    assert ctx.verify_proof(proof)                        # the context is still usable
+
+
+def test_wrong_statement_is_rejected(setup, zk):
+    ctx, op, seed, inputs = setup
+    proof = ctx.create_proof(inputs, 2, seed)
+    ctx.keygen(12, 1)   # a different circuit (vk) at the same params
+    try:
+        assert not ctx.verify_proof(proof)
+    finally:
+        ctx.keygen(12, 2)
+
+
+def test_mock_verify_passes_and_locates_failures(setup, oracle, zk):
+    ctx, op, seed, inputs = setup
+    assert ctx.mock_verify(inputs, 2) is None
+    adv, _, _ = oracle.witness(17, 12, inputs, 2)
+    adv = np.ascontiguousarray(adv)
+    assert ctx.mock_verify(None, 2, advice_override=adv) is None
+    R = zk.rows_per_compression(12)
+    one = oracle_lib.Oracle._limbs(oracle.field_op(0, 4, 1)[1])
+    # break a lookup row: dense cell (halo2 column 8) of some row inside region 1
+    bad = adv.copy()
+    row = R + 100
+    bad[8, row] = (bad[8, row] + np.array([1, 0, 0, 0], dtype=np.uint64))
+    fail = ctx.mock_verify(None, 2, advice_override=bad)
+    assert fail is not None and fail[0] in (1, 2) and abs(int(fail[1]) - row) <= 1
+    rc, _ = oracle.mock_verify_mont(17, 12, 2, bad)
+    assert rc != 0
+    # tamper single cells of the equality-enabled columns: the device checker and the oracle's
+    # MockProver-equivalent must agree on every one, and copy constraints must be among the failures
+    kinds = set()
+    for col, r in [(8, 3), (9, 4), (1, 2), (2, 2), (0, 5), (3, 7), (4, 9), (5, 9), (4, 40), (5, 41), (1, 120)]:
+        bad = adv.copy()
+        bad[col, r] = bad[col, r] ^ np.array([2, 0, 0, 0], dtype=np.uint64)
+        fail = ctx.mock_verify(None, 2, advice_override=bad)
+        ref_fails = oracle.mock_verify_mont(17, 12, 2, bad)[0] != 0
+        assert (fail is not None) == ref_fails, (col, r, fail)
+        if fail is not None:
+            kinds.add(int(fail[0]))
+    assert 3 in kinds or 1 in kinds

@@ -58,6 +58,8 @@ def load_library():
             "zk_ntt_fp": (i32, [vp, vp, i32, i32, i32]),
             "zk_blake2f_witness_batch": (i32, [vp, i32, u32, vp, u64, vp, vp]),
             "zk_blake2f_witness_batch_device": (i32, [vp, i32, u32, vp, u64, vp, vp]),
+            "zk_verify_proof": (i32, [vp, c.c_char_p, u64]),
+            "zk_mock_verify": (i32, [vp, vp, u64, vp, c.POINTER(u64)]),
             "zk_dist_unique_id": (i32, [c.c_char_p]),
             "zk_dist_init": (i32, [vp, c.c_char_p, i32, i32]),
             "zk_dist_info": (i32, [vp, c.POINTER(i32), c.POINTER(i32)]),
@@ -226,6 +228,29 @@ class Context:
         self._check(fn(self.h, _ptr(keep), n_compressions, bytes(seed),
                        ctypes.cast(buf, ctypes.c_void_p), ctypes.byref(ln)))
         return buf.raw[:ln.value]
+
+    def verify_proof(self, proof):
+        """True if accepted; False (reason in .last_error()) if rejected."""
+        rc = self.lib.zk_verify_proof(self.h, bytes(proof), len(proof))
+        if rc == 0:
+            return True
+        if rc == -7:
+            return False
+        self._check(rc)
+
+    def last_error(self):
+        return self.lib.zk_last_error(self.h).decode()
+
+    def mock_verify(self, inputs, n_compressions, advice_override=None):
+        """None if every constraint holds, else (kind, row, index) of the first failure."""
+        keep = bytes(inputs) if isinstance(inputs, (bytes, bytearray)) else inputs
+        fail = (ctypes.c_uint64 * 3)()
+        rc = self.lib.zk_mock_verify(self.h, _ptr(keep), n_compressions, _ptr(advice_override), fail)
+        if rc == 0:
+            return None
+        if rc == -7:
+            return (fail[0], fail[1], fail[2])
+        self._check(rc)
 
     # ---- K2/K3, K4/K5 ------------------------------------------------------------------
     def msm(self, scalars, bases, n, out_affine, on_device=False):

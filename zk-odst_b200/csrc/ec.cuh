@@ -111,4 +111,63 @@ struct XYZZ {  // 128 bytes; identity has zz == 0
   }
 };
 
+// (t - 1) / 2 with q - 1 = 2^32 * t: the fixed exponent of Tonelli-Shanks in Fq
+ZK_HD void fq_sqrt_exponent(uint64_t e[4]) {
+  const uint64_t qm1[4] = {FqParams::MOD[0] - 1, FqParams::MOD[1], FqParams::MOD[2], FqParams::MOD[3]};
+  uint64_t t[4];
+  for (int i = 0; i < 4; i++) t[i] = (qm1[i] >> 32) | (i < 3 ? qm1[i + 1] << 32 : 0);
+  t[0] -= 1;  // t is odd, no borrow
+  for (int i = 0; i < 4; i++) e[i] = (t[i] >> 1) | (i < 3 ? t[i + 1] << 63 : 0);
+}
+// Tonelli-Shanks in Fq (2-adicity 32), exponent (t - 1) / 2 passed in
+ZK_HD bool fq_sqrt(const Fq& a, const uint64_t tm1o2[4], Fq& out) {
+  if (a.is_zero()) {
+    out = a;
+    return true;
+  }
+  Fq w = a.pow256(tm1o2);
+  Fq v = a * w, b = v * w, z = Fq::root_of_unity(), x = v;
+  int vexp = 32;
+  while (b != Fq::one()) {
+    int k = 0;
+    Fq b2 = b;
+    while (b2 != Fq::one()) {
+      b2 = b2.sqr();
+      k++;
+      if (k == vexp) return false;
+    }
+    Fq ww = z;
+    for (int i = 0; i < vexp - k - 1; i++) ww = ww.sqr();
+    z = ww.sqr();
+    b = b * z;
+    x = x * ww;
+    vexp = k;
+  }
+  out = x;
+  return x.sqr() == a;
+}
+// group::GroupEncoding::from_bytes for vesta::Affine: x little-endian canonical, bit 255 = y is odd,
+// 32 zero bytes = identity.  false: not a canonical encoding of a curve point.
+ZK_HD bool decompress_point(const uint8_t* p, const uint64_t tm1o2[4], Affine& out) {
+  uint64_t c[4];
+  for (int l = 0; l < 4; l++) {
+    uint64_t w = 0;
+    for (int b = 0; b < 8; b++) w |= (uint64_t)p[8 * l + b] << (8 * b);
+    c[l] = w;
+  }
+  const bool ysign = c[3] >> 63;
+  c[3] &= 0x7fffffffffffffffULL;
+  if (!(c[0] | c[1] | c[2] | c[3])) {
+    out = Affine::identity();
+    return !ysign;
+  }
+  if (Fq::geq_mod(c)) return false;
+  Fq x = Fq::from_canonical(c);
+  Fq rhs = x.sqr() * x + Fq::from_u64(5), y;
+  if (!fq_sqrt(rhs, tm1o2, y)) return false;
+  if (y.is_odd() != ysign) y = y.neg();
+  out = Affine{x, y};
+  return true;
+}
+
 }  // namespace zkodst

@@ -602,10 +602,10 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
     for (int i = 1; i < NUM_PERM; i++) qa.delta_pow[i] = qa.delta_pow[i - 1] * Fp::delta();
     for (int i = 0; i < 4; i++) {
       qa.t_inv[i] = K.t_inv[i];
-      qa.small[i] = Fp::from_u64(i);
+      qa.k.small[i] = Fp::from_u64(i);
     }
-    qa.pow2[0] = Fp::one();
-    for (int e = 1; e < 127; e++) qa.pow2[e] = qa.pow2[e - 1].dbl();
+    qa.k.pow2[0] = Fp::one();
+    for (int e = 1; e < 127; e++) qa.k.pow2[e] = qa.k.pow2[e - 1].dbl();
     if ((rc = quotient_run(ctx, qa, en))) return rc;
     // extended_to_coeff: inverse NTT, 1/en scaling, undo the coset, keep 3n coefficients
     NttOptions o;
@@ -637,9 +637,6 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
   phase.mark("h commit");
   // ---- evaluations (K9) -----------------------------------------------------------------------------------------
   // advice_queries / fixed_queries in first-use order of `configure` (docs/CIRCUIT.md §Queries)
-  static const int ADVICE_QUERIES[24][2] = {{7, 0}, {8, 0},  {9, 0},  {1, 0},  {8, -1}, {8, 1},  {2, 0}, {7, 1},
-                                            {9, 1}, {0, 0},  {1, -1}, {2, -1}, {0, -1}, {3, -1}, {4, -1}, {5, -1},
-                                            {3, 0}, {4, 0},  {5, 0},  {1, 1},  {6, 0},  {9, -1}, {2, 1}, {0, 1}};
   auto point_of = [&](int rot) { return rot == 0 ? x : (rot == 1 ? x_next : x_prev); };
   // h_poly = sum_p x^(n p) h_piece_p, h_blind likewise
   {

@@ -21,6 +21,11 @@ constexpr int CS_DEGREE = 4;
 // halo2 advice column index of each permutation column, in enable_equality order
 static const int PERM_COLUMNS[NUM_PERM] = {8, 9, 1, 2, 0, 3, 4, 5};
 
+// advice_queries in first-use order of `configure` (docs/CIRCUIT.md §Queries): (advice column, rotation)
+static const int ADVICE_QUERIES[24][2] = {{7, 0}, {8, 0},  {9, 0},  {1, 0},  {8, -1}, {8, 1},  {2, 0}, {7, 1},
+                                          {9, 1}, {0, 0},  {1, -1}, {2, -1}, {0, -1}, {3, -1}, {4, -1}, {5, -1},
+                                          {3, 0}, {4, 0},  {5, 0},  {1, 1},  {6, 0},  {9, -1}, {2, 1}, {0, 1}};
+
 struct SelectorExpr {  // compress_selectors result: selector = q * prod_{r != root} (r - q)
   int fixed_col, root, len;
 };

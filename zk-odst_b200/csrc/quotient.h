@@ -1,5 +1,6 @@
 // Arguments of the fused quotient kernel (quotient.cu).  Product code.
 #pragma once
+#include "gates.cuh"
 #include "prover_state.h"
 
 namespace zkodst {
@@ -17,8 +18,7 @@ struct QuotientArgs {
   Fp theta, beta, gamma, y, zeta;
   Fp delta_pow[NUM_PERM];
   Fp t_inv[4];
-  Fp small[4];     // 0, 1, 2, 3
-  Fp pow2[127];    // 2^e
+  GateConsts k;    // small integers and powers of two
 };
 
 int32_t quotient_run(zk_ctx* ctx, const QuotientArgs& args, uint64_t en);

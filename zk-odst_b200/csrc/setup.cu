@@ -78,34 +78,6 @@ fixed_base_mul_kernel(const Fp* __restrict__ scalars, const Affine* __restrict__
   out[i] = xyzz_to_affine_dev(acc);
 }
 
-// Tonelli-Shanks in Fq (2-adicity 32), exponent (t - 1) / 2 passed in
-__device__ bool fq_sqrt(const Fq& a, const uint64_t tm1o2[4], Fq& out) {
-  if (a.is_zero()) {
-    out = a;
-    return true;
-  }
-  Fq w = a.pow256(tm1o2);
-  Fq v = a * w, b = v * w, z = Fq::root_of_unity(), x = v;
-  int vexp = 32;
-  while (b != Fq::one()) {
-    int k = 0;
-    Fq b2 = b;
-    while (b2 != Fq::one()) {
-      b2 = b2.sqr();
-      k++;
-      if (k == vexp) return false;
-    }
-    Fq ww = z;
-    for (int i = 0; i < vexp - k - 1; i++) ww = ww.sqr();
-    z = ww.sqr();
-    b = b * z;
-    x = x * ww;
-    vexp = k;
-  }
-  out = x;
-  return x.sqr() == a;
-}
-
 struct U256 {
   uint64_t v[4];
 };
@@ -114,32 +86,12 @@ decompress_kernel(const uint8_t* __restrict__ bytes, uint64_t n, U256 tm1o2, Aff
                   int* __restrict__ bad) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  uint64_t c[4];
-  const uint8_t* p = bytes + 32 * i;
-  for (int l = 0; l < 4; l++) {
-    uint64_t w = 0;
-    for (int b = 0; b < 8; b++) w |= (uint64_t)p[8 * l + b] << (8 * b);
-    c[l] = w;
-  }
-  bool ysign = c[3] >> 63;
-  c[3] &= 0x7fffffffffffffffULL;
-  if (!(c[0] | c[1] | c[2] | c[3])) {
-    if (ysign) *bad = 1;
-    out[i] = Affine::identity();
-    return;
-  }
-  if (Fq::geq_mod(c)) {
+  Affine p;
+  if (!decompress_point(bytes + 32 * i, tm1o2.v, p)) {
     *bad = 1;
     return;
   }
-  Fq x = Fq::from_canonical(c);
-  Fq rhs = x.sqr() * x + Fq::from_u64(5), y;
-  if (!fq_sqrt(rhs, tm1o2.v, y)) {
-    *bad = 1;
-    return;
-  }
-  if (y.is_odd() != ysign) y = y.neg();
-  out[i] = Affine{x, y};
+  out[i] = p;
 }
 __global__ void compress_kernel(const Affine* __restrict__ pts, uint64_t n, uint8_t* __restrict__ bytes) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -323,17 +275,8 @@ extern "C" int32_t zk_params_load(zk_ctx* ctx, const uint8_t* bytes, uint64_t le
   ZK_CUDA(ctx, cudaMalloc((void**)&d_bad, sizeof(int)));
   ZK_CUDA(ctx, cudaMemsetAsync(d_bad, 0, sizeof(int), st));
   ZK_CUDA(ctx, cudaMemcpyAsync(d_bytes, bytes + 4, len - 4, cudaMemcpyHostToDevice, st));
-  // (t - 1) / 2 with t = (q - 1) >> 32
   U256 e;
-  {
-    u128 borrow;
-    uint64_t qm1[4] = {FqParams::MOD[0] - 1, FqParams::MOD[1], FqParams::MOD[2], FqParams::MOD[3]};
-    uint64_t t[4];
-    for (int i = 0; i < 4; i++) t[i] = (qm1[i] >> 32) | (i < 3 ? qm1[i + 1] << 32 : 0);
-    t[0] -= 1;  // t is odd, no borrow
-    (void)borrow;
-    for (int i = 0; i < 4; i++) e.v[i] = (t[i] >> 1) | (i < 3 ? t[i + 1] << 63 : 0);
-  }
+  fq_sqrt_exponent(e.v);
   const unsigned T = 128;
   decompress_kernel<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(d_bytes, n, e, g, d_bad);
   decompress_kernel<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(d_bytes + 32 * n, n, e, gl, d_bad);

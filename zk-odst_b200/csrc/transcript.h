@@ -157,6 +157,61 @@ class TranscriptWriter {  // Blake2bWrite<Vec<u8>, EqAffine, Challenge255<EqAffi
   std::vector<uint8_t> proof_;
 };
 
+class TranscriptReader {  // Blake2bRead<&[u8], EqAffine, Challenge255<EqAffine>>
+ public:
+  TranscriptReader(const uint8_t* proof, size_t len) : st_("Halo2-Transcript"), in_(proof), len_(len), pos_(0) {
+    fq_sqrt_exponent(tm1o2_);
+  }
+  void common_scalar(const Fp& s) {
+    uint8_t b[33];
+    b[0] = 2;
+    fe_to_repr(s, b + 1);
+    st_.update(b, 33);
+  }
+  void common_point(const Affine& p) {
+    if (p.is_identity()) throw std::runtime_error("point at infinity in the transcript");
+    uint8_t b[65];
+    b[0] = 1;
+    fq_to_repr(p.x, b + 1);
+    fq_to_repr(p.y, b + 33);
+    st_.update(b, 65);
+  }
+  Affine read_point() {
+    if (pos_ + 32 > len_) throw std::runtime_error("proof truncated");
+    Affine p;
+    if (!decompress_point(in_ + pos_, tm1o2_, p)) throw std::runtime_error("invalid point encoding in proof");
+    pos_ += 32;
+    common_point(p);
+    return p;
+  }
+  Fp read_scalar() {
+    if (pos_ + 32 > len_) throw std::runtime_error("proof truncated");
+    uint64_t c[4];
+    memcpy(c, in_ + pos_, 32);
+    if (Fp::geq_mod(c)) throw std::runtime_error("invalid field element encoding in proof");
+    pos_ += 32;
+    Fp s = Fp::from_canonical(c);
+    common_scalar(s);
+    return s;
+  }
+  Fp squeeze_challenge() {
+    uint8_t z = 0;
+    st_.update(&z, 1);
+    uint8_t out[64];
+    st_.finalize(out);
+    uint64_t w[8];
+    memcpy(w, out, 64);
+    return Fp::from_u512(w);
+  }
+  bool exhausted() const { return pos_ == len_; }
+
+ private:
+  Blake2bState st_;
+  const uint8_t* in_;
+  size_t len_, pos_;
+  uint64_t tm1o2_[4];
+};
+
 class XorShift {  // rand_xorshift 0.3.0
  public:
   explicit XorShift(const uint8_t seed[16]) {
