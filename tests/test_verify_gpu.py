@@ -76,15 +76,18 @@ def test_mock_verify_passes_and_locates_failures(setup, oracle, zk):
     assert fail is not None and fail[0] in (1, 2) and abs(int(fail[1]) - row) <= 1
     rc, _ = oracle.mock_verify_mont(17, 12, 2, bad)
     assert rc != 0
-    # tamper single cells of the equality-enabled columns: the device checker and the oracle's
-    # MockProver-equivalent must agree on every one, and copy constraints must be among the failures
+    # tamper single cells (small value, so the cell stays a valid 64-bit word): the device checker
+    # and the oracle's MockProver-equivalent must agree on every one
+    val = np.array(oracle_lib.Oracle._limbs(oracle.field_op(0, 4, 12345)[1]), dtype=np.uint64)
     kinds = set()
-    for col, r in [(8, 3), (9, 4), (1, 2), (2, 2), (0, 5), (3, 7), (4, 9), (5, 9), (4, 40), (5, 41), (1, 120)]:
+    cells = [(8, 3), (9, 4), (1, 2), (0, 5), (4, 9), (1, 300), (4, 299), (4, 308), (4, 311), (4, 332), (0, 401),
+             (1, 293), (8, 290), (8, 377), (4, R + 700), (2, 2000), (5, 4000), (10, 5)]
+    for col, r in cells:
         bad = adv.copy()
-        bad[col, r] = bad[col, r] ^ np.array([2, 0, 0, 0], dtype=np.uint64)
+        bad[col, r] = val
         fail = ctx.mock_verify(None, 2, advice_override=bad)
         ref_fails = oracle.mock_verify_mont(17, 12, 2, bad)[0] != 0
         assert (fail is not None) == ref_fails, (col, r, fail)
         if fail is not None:
             kinds.add(int(fail[0]))
-    assert 3 in kinds or 1 in kinds
+    assert {1, 2} <= kinds

@@ -1,3 +1,4 @@
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/pytest_gpu.log
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:fixed_accumulate_kernel -s 21 -c 1 -o gpurun_out/prof_fixed_accumulate_v2 -f python tools/profile_proof.py 19 64 1 > gpurun_out/ncu2.log 2>&1; echo "ncu-full rc=$?"
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -8 gpurun_out/pytest_gpu.log
+ZK_PHASE_TRACE=1 ZK_MSM_TRACE=1 timeout 300 python tools/profile_proof.py 19 64 1 > gpurun_out/phase.log 2>&1; echo "phase rc=$?"; grep -E "phase|proof_wall" gpurun_out/phase.log | tail -13; grep msm_fixed gpurun_out/phase.log | tail -16
+timeout 300 python tools/profile_proof.py 19 64 5 2>&1 | tail -1

@@ -422,9 +422,9 @@ int fixed_window_bits(uint64_t npoints) {
 }
 
 int32_t fixed_base_build(zk_ctx* ctx, const Affine* d_bases, uint64_t total_main, uint64_t n_extra,
-                         FixedBase* out) {
+                         FixedBase* out, int force_c) {
   FixedBase fb;
-  fb.c = fixed_window_bits(total_main + n_extra);
+  fb.c = force_c ? force_c : fixed_window_bits(total_main + n_extra);
   fb.nwin = (255 + fb.c - 1) / fb.c + ((255 % fb.c) == 0 ? 1 : 0);
   uint64_t hi = 0;
   dist_range(total_main, ctx->dist_rank, ctx->dist_world, &fb.lo, &hi);

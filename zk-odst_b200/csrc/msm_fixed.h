@@ -20,7 +20,13 @@ int fixed_window_bits(uint64_t npoints);
 // context in a multi-GPU group (dist.cu) only this rank's contiguous range of the main points is
 // tabulated (and the extras on rank 0).
 int32_t fixed_base_build(zk_ctx* ctx, const Affine* d_bases, uint64_t total_main, uint64_t n_extra,
-                         FixedBase* out);
+                         FixedBase* out, int force_c = 0);
+// ipa_fold.cu: the IPA generators after r folds (needs a c = 8 table over all points), and a window
+// table built in caller-owned storage in a single launch
+size_t ipa_fold_workspace_bytes(uint64_t len);
+int32_t ipa_fold_generators(zk_ctx* ctx, const FixedBase& fb8, const Fp* u, int r, void* workspace, Affine* out);
+int32_t fixed_base_build_inplace(zk_ctx* ctx, uint64_t total_main, uint64_t n_extra, int c, Affine* storage,
+                                 void* tmp, FixedBase* out);
 void fixed_base_free(FixedBase& fb);
 
 constexpr int MSM_MAX_BATCH = 16;

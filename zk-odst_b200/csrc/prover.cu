@@ -38,7 +38,10 @@ struct ProofWorkspace {
   Fp *random_poly = nullptr, *s_poly = nullptr, *q_prime = nullptr, *p_poly = nullptr, *b_vec = nullptr;
   Fp* q_polys[8] = {};
   Fp* h_poly = nullptr;
-  Affine* g_fold = nullptr;  // n
+  // IPA second stage (allocated on first use): folding scratch, table over the folded generators
+  void* fold_ws = nullptr;
+  Affine* h_table = nullptr;
+  void* h_tmp = nullptr;
   // lookup permutation tables
   Fp* table_vals = nullptr;      // 65536 compressed table values
   Fp* table_sorted = nullptr;    // ascending
@@ -93,13 +96,25 @@ int32_t get_workspace(zk_ctx* ctx, DeviceKeys& K, ProofWorkspace** out) {
     A(h, en); A(h_coeffs, en);
     A(random_poly, n); A(s_poly, n); A(q_prime, n); A(p_poly, n); A(b_vec, n); A(h_poly, n);
     for (int s = 0; s < 8; s++) A(q_polys[s], n);
-    A(g_fold, n);
     A(table_vals, 65536); A(table_sorted, 65536);
     A(rank_of, 65536); A(counts, 65536 + 8); A(offsets, 65536 + 8); A(left_cnt, 65536 + 8); A(left_off, 65536 + 8);
     A(first_flag_scan, n + 8); A(left_rank, n + 8);
 #undef A
   }
   *out = (ProofWorkspace*)K.workspace;
+  return ZK_OK;
+}
+
+int32_t ensure_fold_workspace(zk_ctx* ctx, ProofWorkspace* W, uint64_t len) {
+  if (W->fold_ws) return ZK_OK;
+  const int nwin = (255 + IPA_STAGE2_C - 1) / IPA_STAGE2_C + ((255 % IPA_STAGE2_C) == 0 ? 1 : 0);
+  const size_t pts = (size_t)nwin * (len + 2);
+  ZK_CUDA(ctx, cudaMalloc(&W->fold_ws, ipa_fold_workspace_bytes(len)));
+  W->all.push_back(W->fold_ws);
+  ZK_CUDA(ctx, cudaMalloc((void**)&W->h_table, pts * sizeof(Affine)));
+  W->all.push_back(W->h_table);
+  ZK_CUDA(ctx, cudaMalloc(&W->h_tmp, pts * (sizeof(XYZZ) + sizeof(Fq))));
+  W->all.push_back(W->h_tmp);
   return ZK_OK;
 }
 
@@ -342,25 +357,6 @@ __global__ void scan_u32_kernel(const uint32_t* __restrict__ in, uint32_t* __res
     __syncthreads();
   }
   if (threadIdx.x == 0 && total) *total = carry;
-}
-
-// ---- IPA helpers ---------------------------------------------------------------------------------------
-// G'_i <- affine(G_lo_i + [u] G_hi_i): shared scalar, one thread per point
-struct ScalarBits {
-  uint64_t v[4];
-};
-__global__ void __launch_bounds__(128)
-generator_collapse_kernel(Affine* __restrict__ g, uint64_t half, ScalarBits u) {
-  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i >= half) return;
-  const Affine hi = g[i + half];
-  XYZZ acc = XYZZ::identity();
-  for (int bit = 254; bit >= 0; bit--) {
-    acc = acc.dbl();
-    if ((u.v[bit >> 6] >> (bit & 63)) & 1) acc = acc.add_affine(hi);
-  }
-  acc = acc.add_affine(g[i]);
-  g[i] = acc.to_affine();
 }
 
 }  // namespace
@@ -820,19 +816,37 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
     // b = powers of x3
     Fp* b = W->b_vec;
     if ((rc = affine_scan(ctx, nullptr, x3, nullptr, n, Fp::one(), b))) return rc;
-    // The folded generators G' are never materialised.  After j rounds
-    //     G'_i = sum_m [m = i mod len] s_m g_m,   s_m = prod_{r < j} u_r^(bit_{k-1-r}(m)),
+    // Two stages.  For the first r rounds the folded generators are not materialised: after j rounds
+    //     G'_i = sum_m [m = i mod len] s_m g_m,   s_m = prod_{t < j} u_t^(bit_{k-1-t}(m)),
     // so L_j = <p'_hi, G'_lo> and R_j = <p'_lo, G'_hi> are MSMs over the ORIGINAL g with scalars
-    // c_m = p'[(m mod len) +- half] * s_m, supported on bit_{k-1-j}(m) = 0 (L) or 1 (R).  This keeps
-    // every MSM on the precomputed fixed-base tables and replaces halo2's
-    // `parallel_generator_collapse` (n scalar multiplications per proof) by elementwise updates of s.
+    // c_m = p'[(m mod len) +- half] * s_m, supported on bit_{k-1-j}(m) = 0 (L) or 1 (R): every MSM stays
+    // on the precomputed fixed-base tables.  After r rounds the generators are folded once
+    // (ipa_fold.cu: H_i = sum_q s_q g_{q len + i}, the shared scalars' digits sorted on the host), a
+    // window table is built over H, and the remaining k - r rounds run the same scheme against H at
+    // 2^-r of the cost.  halo2's `parallel_generator_collapse` (n scalar multiplications per proof,
+    // latency-bound on a GPU) never runs.
     Fp* svec = W->tmp_a;
     Fp* cvec = W->tmp_b;
+    const bool two_stage = P.fb_g8.table != nullptr && k > IPA_FOLD_ROUNDS + 8;
+    const int fold_at = two_stage ? IPA_FOLD_ROUNDS : k;
+    const FixedBase* fb = &P.fb_g;
+    FixedBase fb_h;
+    uint64_t base_n = n;  // size of the current generator vector (n, then n >> r)
     launch_map(ctx, n, [=] __device__(uint64_t m) { svec[m] = Fp::one(); });
-    const uint32_t idx_w = (uint32_t)n, idx_u = (uint32_t)n + 1;
+    std::vector<Fp> us;
     for (int j = 0; j < k; j++) {
       const uint64_t half = 1ull << (k - j - 1);
-      launch_map(ctx, n, [=] __device__(uint64_t m) {
+      if (j == fold_at) {
+        base_n = n >> fold_at;
+        if ((rc = ensure_fold_workspace(ctx, W, base_n))) return rc;
+        if ((rc = ipa_fold_generators(ctx, P.fb_g8, us.data(), fold_at, W->fold_ws, W->h_table))) return rc;
+        ZK_CUDA(ctx, cudaMemcpyAsync(W->h_table + base_n, P.g + n, 2 * sizeof(Affine), cudaMemcpyDeviceToDevice, st));
+        if ((rc = fixed_base_build_inplace(ctx, base_n, 2, IPA_STAGE2_C, W->h_table, W->h_tmp, &fb_h))) return rc;
+        fb = &fb_h;
+        launch_map(ctx, base_n, [=] __device__(uint64_t m) { svec[m] = Fp::one(); });
+      }
+      const uint64_t bn = base_n;
+      launch_map(ctx, bn, [=] __device__(uint64_t m) {
         uint64_t i = m & (2 * half - 1);
         cvec[m] = (i < half ? pp[i + half] : pp[i - half]) * svec[m];
       });
@@ -847,22 +861,23 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
         lr[side].n_extra = 2;
         lr[side].extra[0] = (side == 0 ? vl : vr) * z;
         lr[side].extra[1] = side == 0 ? l_rand : r_rand;
-        lr[side].extra_index[0] = idx_u;
-        lr[side].extra_index[1] = idx_w;
+        lr[side].extra_index[0] = (uint32_t)bn + 1;  // U
+        lr[side].extra_index[1] = (uint32_t)bn;      // W
         lr[side].side_mask = (uint32_t)half;
         lr[side].side_select = side;
       }
       XYZZ lrj[2];
-      if ((rc = msm_fixed_batch(ctx, P.fb_g, lr, 2, n, lrj))) return rc;
+      if ((rc = msm_fixed_batch(ctx, *fb, lr, 2, bn, lrj))) return rc;
       tr.write_point(lrj[0].to_affine());
       tr.write_point(lrj[1].to_affine());
       const Fp u = tr.squeeze_challenge();
       const Fp u_inv = u.inv();
+      us.push_back(u);
       launch_map(ctx, half, [=] __device__(uint64_t i) {
         pp[i] = pp[i] + pp[i + half] * u_inv;
         b[i] = b[i] + b[i + half] * u;
       });
-      launch_map(ctx, n, [=] __device__(uint64_t m) {
+      launch_map(ctx, bn, [=] __device__(uint64_t m) {
         if (m & half) svec[m] = svec[m] * u;
       });
       f = f + l_rand * u_inv + r_rand * u;

@@ -17,6 +17,8 @@ constexpr int NUM_PERM = 8;     // equality-enabled columns a_1..a_8 (table16.rs
 constexpr int NUM_SETS = 4;     // permutation grand products: chunks of degree - 2 = 2 columns
 constexpr int BLINDING = 5;     // ConstraintSystem::blinding_factors() for this circuit
 constexpr int CS_DEGREE = 4;
+constexpr int IPA_FOLD_ROUNDS = 5;   // IPA rounds on the original generators before they are folded once
+constexpr int IPA_STAGE2_C = 12;     // window bits of the table over the folded generators
 
 // halo2 advice column index of each permutation column, in enable_equality order
 static const int PERM_COLUMNS[NUM_PERM] = {8, 9, 1, 2, 0, 3, 4, 5};
@@ -37,6 +39,7 @@ struct DeviceParams {
   Affine* g_lagrange = nullptr;  // n + 1 entries: g_lagrange[0..n), then w
   Affine w, u;
   FixedBase fb_g, fb_gl;         // window tables over the two arrays above
+  FixedBase fb_g8;               // 8-bit windows over g: folds the IPA generators (ipa_fold.cu); single GPU only
 };
 
 struct DeviceKeys {

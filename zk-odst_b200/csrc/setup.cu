@@ -27,6 +27,7 @@ static void free_state(void* p) {
   cudaFree(s->params.g_lagrange);
   fixed_base_free(s->params.fb_g);
   fixed_base_free(s->params.fb_gl);
+  fixed_base_free(s->params.fb_g8);
   free_keys(s->keys);
   delete s;
 }
@@ -139,6 +140,7 @@ int32_t install_params(zk_ctx* ctx, int k, Affine* g, Affine* g_lagrange, const 
   cudaFree(S->params.g_lagrange);
   fixed_base_free(S->params.fb_g);
   fixed_base_free(S->params.fb_gl);
+  fixed_base_free(S->params.fb_g8);
   S->has_params = false;
   S->params.k = k;
   S->params.n = 1ull << k;
@@ -156,6 +158,10 @@ int32_t install_params(zk_ctx* ctx, int k, Affine* g, Affine* g_lagrange, const 
   if (rc) return rc;
   rc = fixed_base_build(ctx, g_lagrange, n, 1, &S->params.fb_gl);
   if (rc) return rc;
+  if (ctx->dist_world == 1 && k >= 15) {
+    rc = fixed_base_build(ctx, g, n, 2, &S->params.fb_g8, 8);
+    if (rc) return rc;
+  }
   ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   S->has_params = true;
   return ZK_OK;
