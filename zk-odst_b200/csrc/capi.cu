@@ -97,6 +97,7 @@ void zk_ctx_destroy(zk_ctx* ctx) {
   cudaFree(ctx->scan_ws.ptr);
   cudaFree(ctx->eval_ws.ptr);
   cudaFree(ctx->misc_ws.ptr);
+  cudaFree(ctx->inv_ws.ptr);
   dist_free(ctx);
   if (ctx->prover_state && ctx->prover_state_free) ctx->prover_state_free(ctx->prover_state);
   for (auto& kv : ctx->ntt_tables) {

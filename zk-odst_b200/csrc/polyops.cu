@@ -115,28 +115,26 @@ int32_t affine_scan(zk_ctx* ctx, const Fp* m, const Fp& m_const, const Fp* a, ui
 
 // ---- batched inversion ---------------------------------------------------------------------------
 namespace {
-constexpr int INV_CH = 8;
-__global__ void __launch_bounds__(128) batch_invert_kernel(Fp* __restrict__ data, uint64_t n) {
+// Montgomery's trick over chunks of INV_CH elements per thread (one Fermat inversion, ~380
+// multiplications, per chunk); the prefix products live in a scratch vector so the chunk can be long.
+constexpr int INV_CH = 32;
+__global__ void __launch_bounds__(128) batch_invert_kernel(Fp* __restrict__ data, Fp* __restrict__ pre, uint64_t n) {
   uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   uint64_t lo = c * INV_CH;
   if (lo >= n) return;
-  int cnt = (int)(n - lo < INV_CH ? n - lo : INV_CH);
-  Fp x[INV_CH], pre[INV_CH];
+  const uint64_t hi = lo + INV_CH < n ? lo + INV_CH : n;
   Fp acc = Fp::one();
-#pragma unroll
-  for (int i = 0; i < INV_CH; i++) {
-    if (i < cnt) {
-      x[i] = data[lo + i];
-      pre[i] = acc;
-      if (!x[i].is_zero()) acc = acc * x[i];
-    }
+  for (uint64_t i = lo; i < hi; i++) {
+    pre[i] = acc;
+    const Fp x = data[i];
+    if (!x.is_zero()) acc = acc * x;
   }
   acc = acc.inv();
-#pragma unroll
-  for (int i = INV_CH - 1; i >= 0; i--) {
-    if (i < cnt && !x[i].is_zero()) {
-      data[lo + i] = acc * pre[i];
-      acc = acc * x[i];
+  for (uint64_t i = hi; i-- > lo;) {
+    const Fp x = data[i];
+    if (!x.is_zero()) {
+      data[i] = acc * pre[i];
+      acc = acc * x;
     }
   }
 }
@@ -196,7 +194,9 @@ inner_product_kernel(const Fp* __restrict__ a, const Fp* __restrict__ b, uint64_
 int32_t batch_invert(zk_ctx* ctx, Fp* data, uint64_t n) {
   if (!n) return ZK_OK;
   uint64_t chunks = (n + INV_CH - 1) / INV_CH;
-  batch_invert_kernel<<<(unsigned)((chunks + 127) / 128), 128, 0, ctx->stream>>>(data, n);
+  int32_t rc = ensure_buf(ctx, ctx->inv_ws, n * sizeof(Fp));
+  if (rc) return rc;
+  batch_invert_kernel<<<(unsigned)((chunks + 127) / 128), 128, 0, ctx->stream>>>(data, (Fp*)ctx->inv_ws.ptr, n);
   ctx->launches++;
   ZK_CUDA(ctx, cudaGetLastError());
   return ZK_OK;

@@ -216,51 +216,56 @@ __global__ void lookup_compress_kernel(const Fp* __restrict__ c0, const Fp* __re
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i < n) out[i] = (c0[i] * theta + c1[i]) * theta + c2[i];
 }
-// Ascending order of the 65536 compressed table rows (field `Ord` = canonical integer order):
-// rank by counting, top limbs staged through shared memory; equal top limbs (probability ~2^-30
-// per proof) fall back to a full comparison, equal values raise status 3 (theta collision).
-__global__ void table_keys_kernel(const Fp* __restrict__ vals, uint64_t* __restrict__ keys) {
+// Ascending order of the 65536 compressed table rows (field `Ord` = canonical integer order).
+// The values are uniform, so a bucket by the top 14 bits of the canonical integer (< 2^254) holds
+// ~4 of them: histogram, scan, then each value ranks itself against its bucket with a full
+// 256-bit comparison.  Equal values raise status 3 (theta collision).
+constexpr uint32_t RANK_BUCKETS = 1u << 14;
+__global__ void table_keys_kernel(const Fp* __restrict__ vals, uint64_t* __restrict__ keys,
+                                  uint32_t* __restrict__ hist) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 65536) return;
   uint64_t c[4];
   vals[i].to_canonical(c);
 #pragma unroll
   for (int l = 0; l < 4; l++) keys[(size_t)l * 65536 + i] = c[l];  // limb-major
+  atomicAdd(&hist[(uint32_t)(c[3] >> 48)], 1u);
 }
-constexpr int RANK_TILE = 2048;
-__global__ void __launch_bounds__(256)
-table_rank_kernel(const uint64_t* __restrict__ keys, const Fp* __restrict__ vals, uint32_t* __restrict__ rank_of,
-                  Fp* __restrict__ sorted, int* __restrict__ status) {
-  __shared__ uint64_t top[RANK_TILE];
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint64_t* k3 = keys + (size_t)3 * 65536;
-  const uint64_t mine = k3[i];
-  uint32_t cnt = 0;
-  for (uint32_t base = 0; base < 65536; base += RANK_TILE) {
-    __syncthreads();
-    for (uint32_t j = threadIdx.x; j < RANK_TILE; j += blockDim.x) top[j] = k3[base + j];
-    __syncthreads();
-#pragma unroll 8
-    for (uint32_t j = 0; j < RANK_TILE; j++) {
-      const uint64_t t = top[j];
-      cnt += t < mine ? 1u : 0u;
-      if (t == mine && base + j != i) {  // rare: decide on the lower limbs
-        const uint32_t o = base + j;
-        bool less = false, equal = true;
-        for (int l = 2; l >= 0 && equal; l--) {
-          const uint64_t a = keys[(size_t)l * 65536 + o], b = keys[(size_t)l * 65536 + i];
-          if (a != b) {
-            equal = false;
-            less = a < b;
-          }
-        }
-        if (equal) atomicExch(status, 3);
-        cnt += less ? 1u : 0u;
+__global__ void table_members_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ offsets,
+                                     uint32_t* __restrict__ cursor, uint32_t* __restrict__ members) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 65536) return;
+  const uint32_t bkt = (uint32_t)(keys[(size_t)3 * 65536 + i] >> 48);
+  members[offsets[bkt] + atomicAdd(&cursor[bkt], 1u)] = i;
+}
+__global__ void table_rank_kernel(const uint64_t* __restrict__ keys, const Fp* __restrict__ vals,
+                                  const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ hist,
+                                  const uint32_t* __restrict__ members, uint32_t* __restrict__ rank_of,
+                                  Fp* __restrict__ sorted, int* __restrict__ status) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 65536) return;
+  uint64_t mine[4];
+#pragma unroll
+  for (int l = 0; l < 4; l++) mine[l] = keys[(size_t)l * 65536 + i];
+  const uint32_t bkt = (uint32_t)(mine[3] >> 48);
+  const uint32_t first = offsets[bkt], cnt = hist[bkt];
+  uint32_t rank = first;
+  for (uint32_t j = 0; j < cnt; j++) {
+    const uint32_t o = members[first + j];
+    if (o == i) continue;
+    bool less = false, equal = true;
+    for (int l = 3; l >= 0 && equal; l--) {
+      const uint64_t a = keys[(size_t)l * 65536 + o];
+      if (a != mine[l]) {
+        equal = false;
+        less = a < mine[l];
       }
     }
+    if (equal) atomicExch(status, 3);
+    rank += less ? 1u : 0u;
   }
-  rank_of[i] = cnt;
-  sorted[cnt < 65536 ? cnt : 0] = vals[i];
+  rank_of[i] = rank;
+  sorted[rank < 65536 ? rank : 0] = vals[i];
 }
 __global__ void lookup_count_kernel(const Fp* __restrict__ dense_col, const Fp* __restrict__ cin,
                                     const Fp* __restrict__ table_vals, const uint32_t* __restrict__ rank_of,
@@ -433,9 +438,16 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
                                                     n, W->ctab);
     ctx->launches += 2;
     // table values = compressed table rows 0..65535, ranked on the device
-    uint64_t* keys = (uint64_t*)W->tmp_a;  // 65536 x 4 limbs, limb-major (tmp_a holds n >= 2^16 elements)
-    table_keys_kernel<<<256, 256, 0, st>>>(W->ctab, keys);
-    table_rank_kernel<<<256, 256, 0, st>>>(keys, W->ctab, W->rank_of, W->table_sorted, ctx->d_status);
+    uint64_t* keys = (uint64_t*)W->tmp_a;  // 65536 x 4 limbs, limb-major (tmp_a holds n >= 2^17 elements)
+    uint32_t* hist = (uint32_t*)(keys + 4 * 65536);  // RANK_BUCKETS counts, offsets, cursors; 65536 members
+    uint32_t *boff = hist + RANK_BUCKETS, *bcur = boff + RANK_BUCKETS, *members = bcur + RANK_BUCKETS;
+    ZK_CUDA(ctx, cudaMemsetAsync(hist, 0, 3 * RANK_BUCKETS * 4, st));
+    table_keys_kernel<<<256, 256, 0, st>>>(W->ctab, keys, hist);
+    scan_u32_kernel<<<1, 1024, 0, st>>>(hist, boff, RANK_BUCKETS, nullptr);
+    table_members_kernel<<<256, 256, 0, st>>>(keys, boff, bcur, members);
+    table_rank_kernel<<<256, 256, 0, st>>>(keys, W->ctab, boff, hist, members, W->rank_of, W->table_sorted,
+                                           ctx->d_status);
+    ctx->launches += 2;
     ZK_CUDA(ctx, cudaMemcpyAsync(W->table_vals, W->ctab, 65536 * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
     ctx->launches += 2;
     const uint32_t zero_rank = 0;  // table row 0 = (0,0,0) compresses to 0, the minimum
@@ -600,6 +612,8 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
       qa.t_inv[i] = K.t_inv[i];
       qa.k.small[i] = Fp::from_u64(i);
     }
+    qa.ypow[NUM_GATE_POLYS - 1] = Fp::one();
+    for (int e = NUM_GATE_POLYS - 2; e >= 0; e--) qa.ypow[e] = qa.ypow[e + 1] * y;
     qa.k.pow2[0] = Fp::one();
     for (int e = 1; e < 127; e++) qa.k.pow2[e] = qa.k.pow2[e - 1].dbl();
     if ((rc = quotient_run(ctx, qa, en))) return rc;

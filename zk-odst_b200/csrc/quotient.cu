@@ -18,54 +18,106 @@ namespace zkodst {
 namespace {
 
 __constant__ QuotientArgs qa;
+// halo2 advice column of permutation column ci (PERM_COLUMNS, prover_state.h), usable in device code
+#define PERM_COLUMNS_DEV(ci) ((ci) == 0 ? 8 : (ci) == 1 ? 9 : (ci) == 2 ? 1 : (ci) == 3 ? 2 : (ci) == 4 ? 0 : (ci) == 5 ? 3 : (ci) == 6 ? 4 : 5)
 
 struct Horner {
   Fp h, y;
   __device__ __forceinline__ void fold(const Fp& v) { h = h * y + v; }
 };
 
-__global__ void __launch_bounds__(128) quotient_kernel(uint64_t en, uint64_t mask) {
+// The quotient is evaluated in three launches that hand the Horner accumulator through h[]: one kernel
+// holding all 61 coset values of a row needs 255 registers (2 warps per scheduler, latency-bound);
+// split, each part fits 4 blocks per SM.
+constexpr int Q_MINB = 4;
+
+// part 1: the 23 gate polynomials.  sum_k y^(22-k) sel_k e_k (what Horner over the gate list yields) is
+// regrouped by expression — gates that share a polynomial (a1/a2, c1/c2, d1/d2) share its evaluation —
+// and every cell and selector is fetched where it is used, which keeps the live set small.  The order
+// of evaluation does not matter: field arithmetic is exact, the value equals fold_gates (gates.cuh).
+__global__ void __launch_bounds__(128, Q_MINB) quotient_gates_kernel(uint64_t en, uint64_t mask) {
   const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= en) return;
   const uint64_t ip = (i - 4) & mask, in = (i + 4) & mask;  // rotation by one row = 4 steps
   // advice by a-number: a0..a9 -> halo2 columns 7,8,9,1,2,0,3,4,5,6
-  const Fp* A0 = qa.advice[7];
-  const Fp* A1 = qa.advice[8];
-  const Fp* A2 = qa.advice[9];
-  const Fp* A3 = qa.advice[1];
-  const Fp* A4 = qa.advice[2];
-  const Fp* A5 = qa.advice[0];
-  const Fp* A6 = qa.advice[3];
-  const Fp* A7 = qa.advice[4];
-  const Fp* A8 = qa.advice[5];
-  const Fp* A9 = qa.advice[6];
-  GateCells v;
-  v.a0c = A0[i], v.a0n = A0[in];
-  v.a1p = A1[ip], v.a1c = A1[i], v.a1n = A1[in];
-  v.a2p = A2[ip], v.a2c = A2[i], v.a2n = A2[in];
-  v.a3p = A3[ip], v.a3c = A3[i], v.a3n = A3[in];
-  v.a4p = A4[ip], v.a4c = A4[i], v.a4n = A4[in];
-  v.a5p = A5[ip], v.a5c = A5[i], v.a5n = A5[in];
-  v.a6p = A6[ip], v.a6c = A6[i];
-  v.a7p = A7[ip], v.a7c = A7[i];
-  v.a8p = A8[ip], v.a8c = A8[i];
-  v.a9c = A9[i];
-  Fp sel[NUM_SELECTORS];
-  {
-    Fp q[NUM_FIXED];
-#pragma unroll
-    for (int c = 3; c < NUM_FIXED; c++) q[c] = qa.fixed[c][i];
-#pragma unroll
-    for (int s = 0; s < NUM_SELECTORS; s++)
-      sel[s] = selector_expr(q[qa.sel[s].fixed_col], qa.sel[s].root, qa.sel[s].len, qa.k.small);
-  }
+  const Fp* const A0 = qa.advice[7];
+  const Fp* const A1 = qa.advice[8];
+  const Fp* const A2 = qa.advice[9];
+  const Fp* const A3 = qa.advice[1];
+  const Fp* const A4 = qa.advice[2];
+  const Fp* const A5 = qa.advice[0];
+  const Fp* const A6 = qa.advice[3];
+  const Fp* const A7 = qa.advice[4];
+  const Fp* const A8 = qa.advice[5];
+  const Fp* const A9 = qa.advice[6];
+  auto SEL = [&](int s) {
+    return selector_expr(qa.fixed[qa.sel[s].fixed_col][i], qa.sel[s].root, qa.sel[s].len, qa.k.small);
+  };
+  const Fp* const YP = qa.ypow;  // YP[k] = y^(22 - k)
+  const Fp* const P = qa.k.pow2;
   const Fp one = Fp::one();
-  Horner H{Fp::zero(), qa.y};
+  Fp acc;
+  {  // decompose ABCD (k = 0)
+    acc = SEL(SEL_ABCD) * YP[0] * (A3[i] - A1[ip] - A1[i] * P[16] - A1[in] * P[32] - A4[i] * P[48]);
+  }
+  {  // Decompose EFGH: tag_p0, tag_p4, dense, spread (k = 1..4)
+    Fp t = A0[i] * YP[1] + A0[in] * YP[2];
+    t = t + (A3[i] - A1[in] - A1[i] * P[8]) * YP[3];
+    t = t + (A4[i] - A2[in] - A2[i] * P[16]) * YP[4];
+    acc = acc + SEL(SEL_EFGH) * t;
+  }
+  {  // Decompose IJKL: tag_q0, bit, dense, spread (k = 5..8)
+    const Fp a0c = A0[i], a5c = A5[i];
+    Fp t = a0c * (a0c - one) * YP[5] + a5c * (a5c - one) * YP[6];
+    t = t + (A3[i] - a5c - A1[i] * P[1]) * YP[7];
+    t = t + (A4[i] - a5c - A2[i] * P[2]) * YP[8];
+    acc = acc + SEL(SEL_IJKL) * t;
+  }
+  // shared window sums: X = a3..a6[prev], Y = a7,a8[prev], a3,a4[cur]
+  const Fp s0 = A3[ip] + A7[ip], s1 = A4[ip] + A8[ip], s2 = A5[ip] + A3[i], s3 = A6[ip] + A4[i];
+  {  // add2_lin (c1: k = 12, c2: k = 18), add3_lin (a1: k = 9, a2: k = 15)
+    const Fp sum_tail = A1[ip] + A1[i] * P[16] + A1[in] * P[32] + A3[in] * P[48] + A9[i] * P[64];
+    const Fp add2_lin = s0 + s1 * P[16] + s2 * P[32] + s3 * P[48] - sum_tail;
+    acc = acc + add2_lin * (SEL(SEL_C1) * YP[12] + SEL(SEL_C2) * YP[18]);
+    const Fp add3_lin = add2_lin + A5[i] + A6[i] * P[16] + A7[i] * P[32] + A8[i] * P[48];
+    acc = acc + add3_lin * (SEL(SEL_A1) * YP[9] + SEL(SEL_A2) * YP[15]);
+  }
+  {  // carries: carry3 (a1: 10, a2: 16), carry2 (c1: 13, c2: 19)
+    const Fp a9c = A9[i];
+    const Fp carry2 = a9c * (a9c - one);
+    acc = acc + carry2 * (SEL(SEL_C1) * YP[13] + SEL(SEL_C2) * YP[19]);
+    acc = acc + carry2 * (a9c - qa.k.small[2]) * (SEL(SEL_A1) * YP[10] + SEL(SEL_A2) * YP[16]);
+  }
+  {  // xor_limb (d1: 11, d2: 17)
+    const Fp xor_limb = A3[i] + A4[i] - A2[i] - A2[in] * P[1];
+    acc = acc + xor_limb * (SEL(SEL_D1) * YP[11] + SEL(SEL_D2) * YP[17]);
+  }
+  {  // b1 (14), b2 (20), digest xor (21): all start from the 32-bit-limb accumulation of the window
+    const Fp acc32 = s0 + s1 * P[32] + s2 * P[64] + s3 * P[96];
+    const Fp odd_w = (A2[ip] + A2[i] * P[32] + A2[in] * P[64] + A4[in] * P[96]) * P[1];
+    const Fp a5c = A5[i], a6c = A6[i], a7c = A7[i], a8c = A8[i], a3n = A3[in];
+    // even pieces at bit offsets 0, 8, 24, 40, 56
+    acc = acc + (acc32 - (a5c + a6c * P[16] + a7c * P[48] + a8c * P[80] + a3n * P[112]) - odd_w) *
+                    (SEL(SEL_B1) * YP[14]);
+    // even pieces at bit offsets 0, 15, 31, 47, 63
+    acc = acc + (acc32 - (a5c + a6c * P[30] + a7c * P[62] + a8c * P[94] + a3n * P[126]) - odd_w) *
+                    (SEL(SEL_B2) * YP[20]);
+    // s_digest: xor (21), word (22)
+    Fp t = (acc32 - (A2[ip] + A2[i] * P[32] + A2[in] * P[64] + a5c * P[96]) -
+            (a6c + a7c * P[32] + a8c * P[64] + a3n * P[96]) * P[1]) * YP[21];
+    t = t + (A5[in] - A1[ip] - A1[i] * P[16] - A1[in] * P[32] - A4[in] * P[48]);  // YP[22] = 1
+    acc = acc + SEL(SEL_DIGEST) * t;
+  }
+  qa.h[i] = acc;
+}
 
-  // ---- gates, in declaration order (gates.cuh) --------------------------------------------------
-  fold_gates(H, v, sel, qa.k);
-
-  // ---- permutation argument -------------------------------------------------------------------
+// part 2: the permutation argument (columns in enable_equality order: a1,a2 | a3,a4 | a5,a6 | a7,a8)
+__global__ void __launch_bounds__(128, Q_MINB) quotient_perm_kernel(uint64_t en, uint64_t mask) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= en) return;
+  const uint64_t in = (i + 4) & mask;
+  const Fp one = Fp::one();
+  Horner H{qa.h[i], qa.y};
   const Fp l0 = qa.l0[i], l_last = qa.l_last[i], l_active = qa.l_active[i];
   const uint64_t ilast = (i - 4 * (BLINDING + 1)) & mask;
   Fp z[NUM_SETS];
@@ -75,38 +127,43 @@ __global__ void __launch_bounds__(128) quotient_kernel(uint64_t en, uint64_t mas
   H.fold((z[NUM_SETS - 1] * z[NUM_SETS - 1] - z[NUM_SETS - 1]) * l_last);
 #pragma unroll
   for (int s = 1; s < NUM_SETS; s++) H.fold((z[s] - qa.perm_z[s - 1][ilast]) * l0);
-  {
-    // coset point X = zeta * omega_ext^i
-    const uint64_t half = en >> 1;
-    Fp w = i < half ? qa.tw_ext[i] : qa.tw_ext[i - half].neg();
-    const Fp bx = qa.beta * qa.zeta * w;
-    // permutation columns in enable_equality order: a1,a2 | a3,a4 | a5,a6 | a7,a8 (all cur)
-    const Fp vals[NUM_PERM] = {v.a1c, v.a2c, v.a3c, v.a4c, v.a5c, v.a6c, v.a7c, v.a8c};
+  // coset point X = zeta * omega_ext^i
+  const uint64_t half = en >> 1;
+  const Fp w = i < half ? qa.tw_ext[i] : qa.tw_ext[i - half].neg();
+  const Fp bx = qa.beta * qa.zeta * w;
 #pragma unroll
-    for (int s = 0; s < NUM_SETS; s++) {
-      Fp left = qa.perm_z[s][in];
-      Fp right = z[s];
+  for (int s = 0; s < NUM_SETS; s++) {
+    Fp left = qa.perm_z[s][in];
+    Fp right = z[s];
 #pragma unroll
-      for (int j = 0; j < 2; j++) {
-        const int ci = 2 * s + j;
-        left = left * (vals[ci] + qa.beta * qa.sigma[ci][i] + qa.gamma);
-        right = right * (vals[ci] + bx * qa.delta_pow[ci] + qa.gamma);
-      }
-      H.fold((left - right) * l_active);
+    for (int j = 0; j < 2; j++) {
+      const int ci = 2 * s + j;
+      const Fp val = qa.advice[PERM_COLUMNS_DEV(ci)][i];
+      left = left * (val + qa.beta * qa.sigma[ci][i] + qa.gamma);
+      right = right * (val + bx * qa.delta_pow[ci] + qa.gamma);
     }
+    H.fold((left - right) * l_active);
   }
-  // ---- lookup argument ---------------------------------------------------------------------------
-  {
-    const Fp zl = qa.lookup_z[i], zl_next = qa.lookup_z[in];
-    const Fp pin = qa.lookup_in[i], pin_prev = qa.lookup_in[ip], ptab = qa.lookup_tab[i];
-    const Fp cin = (v.a0c * qa.theta + v.a1c) * qa.theta + v.a2c;
-    const Fp ctab = (qa.fixed[0][i] * qa.theta + qa.fixed[1][i]) * qa.theta + qa.fixed[2][i];
-    H.fold((one - zl) * l0);
-    H.fold((zl * zl - zl) * l_last);
-    H.fold((zl_next * (pin + qa.beta) * (ptab + qa.gamma) - zl * (cin + qa.beta) * (ctab + qa.gamma)) * l_active);
-    H.fold((pin - ptab) * l0);
-    H.fold((pin - ptab) * (pin - pin_prev) * l_active);
-  }
+  qa.h[i] = H.h;
+}
+
+// part 3: the lookup argument, then the division by X^n - 1
+__global__ void __launch_bounds__(128, Q_MINB) quotient_lookup_kernel(uint64_t en, uint64_t mask) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= en) return;
+  const uint64_t ip = (i - 4) & mask, in = (i + 4) & mask;
+  const Fp one = Fp::one();
+  Horner H{qa.h[i], qa.y};
+  const Fp l0 = qa.l0[i], l_last = qa.l_last[i], l_active = qa.l_active[i];
+  const Fp zl = qa.lookup_z[i], zl_next = qa.lookup_z[in];
+  const Fp pin = qa.lookup_in[i], pin_prev = qa.lookup_in[ip], ptab = qa.lookup_tab[i];
+  const Fp cin = (qa.advice[7][i] * qa.theta + qa.advice[8][i]) * qa.theta + qa.advice[9][i];
+  const Fp ctab = (qa.fixed[0][i] * qa.theta + qa.fixed[1][i]) * qa.theta + qa.fixed[2][i];
+  H.fold((one - zl) * l0);
+  H.fold((zl * zl - zl) * l_last);
+  H.fold((zl_next * (pin + qa.beta) * (ptab + qa.gamma) - zl * (cin + qa.beta) * (ctab + qa.gamma)) * l_active);
+  H.fold((pin - ptab) * l0);
+  H.fold((pin - ptab) * (pin - pin_prev) * l_active);
   qa.h[i] = H.h * qa.t_inv[i & 3];
 }
 
@@ -115,8 +172,11 @@ __global__ void __launch_bounds__(128) quotient_kernel(uint64_t en, uint64_t mas
 int32_t quotient_run(zk_ctx* ctx, const QuotientArgs& args, uint64_t en) {
   ZK_CUDA(ctx, cudaMemcpyToSymbolAsync(qa, &args, sizeof(QuotientArgs), 0, cudaMemcpyHostToDevice, ctx->stream));
   KernelTimer timer(ctx, KC_QUOTIENT);
-  quotient_kernel<<<(unsigned)((en + 127) / 128), 128, 0, ctx->stream>>>(en, en - 1);
-  ctx->launches++;
+  const unsigned grid = (unsigned)((en + 127) / 128);
+  quotient_gates_kernel<<<grid, 128, 0, ctx->stream>>>(en, en - 1);
+  quotient_perm_kernel<<<grid, 128, 0, ctx->stream>>>(en, en - 1);
+  quotient_lookup_kernel<<<grid, 128, 0, ctx->stream>>>(en, en - 1);
+  ctx->launches += 3;
   ZK_CUDA(ctx, cudaGetLastError());
   return ZK_OK;
 }

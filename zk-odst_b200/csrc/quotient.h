@@ -19,6 +19,7 @@ struct QuotientArgs {
   Fp delta_pow[NUM_PERM];
   Fp t_inv[4];
   GateConsts k;    // small integers and powers of two
+  Fp ypow[NUM_GATE_POLYS];  // ypow[k] = y^(NUM_GATE_POLYS - 1 - k)
 };
 
 int32_t quotient_run(zk_ctx* ctx, const QuotientArgs& args, uint64_t en);

@@ -56,7 +56,7 @@ struct zk_ctx {
   bool last_valid[zkodst::KC_COUNT] = {};
   std::map<uint32_t, zkodst::DeviceRegionLayout> layouts;
   zkodst::DevBuf scratch_inputs, scratch_advice, scratch_digests;
-  zkodst::DevBuf scratch_a, scratch_b, msm_ws, msm_out, ntt_tmp, scan_ws, eval_ws, misc_ws;
+  zkodst::DevBuf scratch_a, scratch_b, msm_ws, msm_out, ntt_tmp, scan_ws, eval_ws, misc_ws, inv_ws;
   void* prover_state = nullptr;  // zkodst::ProverState (params, keys), owned; see prover_state.h
   void (*prover_state_free)(void*) = nullptr;
   std::map<int, zkodst::NttTables> ntt_tables;
