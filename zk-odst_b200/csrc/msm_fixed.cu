@@ -248,6 +248,16 @@ __device__ __forceinline__ Affine load_entry(const Affine* __restrict__ table, u
   return p;
 }
 
+// the bucket containing sorted position `pos`: first b in [lo, hi] with offsets[b + 1] > pos
+__device__ __forceinline__ uint32_t bucket_of_position(const uint32_t* __restrict__ offsets, uint32_t lo,
+                                                       uint32_t hi, uint32_t pos) {
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (offsets[mid + 1] <= pos) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
 // ---- accumulation: one chunk of `plan->chunk` consecutive sorted entries per thread -------------------
 __global__ void __launch_bounds__(ACC_THREADS, ACC_MIN_BLOCKS)
 fixed_accumulate_kernel(const Affine* __restrict__ table, const uint32_t* __restrict__ sorted,
@@ -258,13 +268,8 @@ fixed_accumulate_kernel(const Affine* __restrict__ table, const uint32_t* __rest
        chunk += gridDim.x * ACC_THREADS) {
     const uint32_t start = chunk * L;
     const uint32_t end = start + L < entries ? start + L : entries;
-    // bucket containing `start`: first b with offsets[b + 1] > start
-    uint32_t lo = 0, hi = nbuckets - 1;
-    while (lo < hi) {
-      uint32_t mid = (lo + hi) >> 1;
-      if (offsets[mid + 1] <= start) lo = mid + 1; else hi = mid;
-    }
-    uint32_t b = lo, boundary = offsets[b + 1];
+    uint32_t b = bucket_of_position(offsets, 0, nbuckets - 1, start);
+    uint32_t boundary = offsets[b + 1];
     bool first = true;
     XYZZ acc = XYZZ::identity();
     Affine nxt = load_entry(table, sorted[start]);
@@ -275,10 +280,14 @@ fixed_accumulate_kernel(const Affine* __restrict__ table, const uint32_t* __rest
         if (first) heads[chunk] = acc; else buckets[b] = acc;
         first = false;
         acc = XYZZ::identity();
-        do {
-          b++;
+        // next non-empty bucket: usually b + 1; small-value columns leave long runs of empty
+        // buckets, which a linear walk would cross one dependent load at a time
+        b++;
+        boundary = offsets[b + 1];
+        if (pos >= boundary) {
+          b = bucket_of_position(offsets, b + 1, nbuckets - 1, pos);
           boundary = offsets[b + 1];
-        } while (pos >= boundary);
+        }
       }
       acc = acc.add_affine(cur);
     }
