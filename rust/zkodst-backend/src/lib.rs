@@ -103,6 +103,40 @@ impl GpuProver {
         Ok(proof)
     }
 
+    /// `verify_proof(&params, vk, SingleVerifier::new(&params), &[&[]], &mut Blake2bRead::init(proof))`
+    /// (benches/blake2f.rs:138-144) against this prover's params and keys.
+    pub fn verify_proof(&mut self, proof: &[u8]) -> Result<bool, Error> {
+        match unsafe { sys::zk_verify_proof(self.ctx, proof.as_ptr(), proof.len() as u64) } {
+            sys::ZK_OK => Ok(true),
+            sys::ZK_E_VERIFY => Ok(false),
+            rc => self.check(rc).map(|_| false),
+        }
+    }
+
+    /// `MockProver::run(k, &circuit, vec![]).verify()` (table16/spread_table.rs:759-763):
+    /// `Ok(None)` when every constraint holds, else the first failure (kind, row, index).
+    pub fn mock_verify(&mut self, inputs: &[Blake2fWitness]) -> Result<Option<(u64, u64, u64)>, Error> {
+        let mut flat = Vec::with_capacity(inputs.len() * sys::ZK_BLAKE2F_INPUT_BYTES);
+        for w in inputs {
+            flat.extend_from_slice(&w.to_eip152());
+        }
+        let mut fail = [0u64; 3];
+        match unsafe {
+            sys::zk_mock_verify(self.ctx, flat.as_ptr(), inputs.len() as u64, ptr::null(), fail.as_mut_ptr())
+        } {
+            sys::ZK_OK => Ok(None),
+            sys::ZK_E_VERIFY => Ok(Some((fail[0], fail[1], fail[2]))),
+            rc => self.check(rc).map(|_| None),
+        }
+    }
+
+    /// Joins a group of `world` processes (one per GPU) that split every MSM by point range
+    /// (BASELINE configs[3]).  `id` comes from `zk_dist_unique_id` on rank 0; call before
+    /// `load_params`.  All ranks must then prove the same inputs with the same seed.
+    pub fn join_group(&mut self, id: &[u8; sys::ZK_DIST_ID_BYTES], rank: i32, world: i32) -> Result<(), Error> {
+        self.check(unsafe { sys::zk_dist_init(self.ctx, id.as_ptr(), rank, world) })
+    }
+
     /// `Circuit::synthesize` for the GPU path: fills all advice columns of the batch.
     /// `advice` must hold 12 * 2^k field elements (column-major, Montgomery form — the memory
     /// image of halo2's `Polynomial<Fp, LagrangeCoeff>` values).

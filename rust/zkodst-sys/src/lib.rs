@@ -40,4 +40,14 @@ extern "C" {
     pub fn zk_vk_repr_override(ctx: *mut zk_ctx, repr: *const u8) -> i32;
     pub fn zk_create_proof(ctx: *mut zk_ctx, inputs: *const u8, n_compressions: u64,
         seed: *const u8, proof_out: *mut u8, proof_len: *mut u64) -> i32;
+    pub fn zk_create_proof_device_inputs(ctx: *mut zk_ctx, d_inputs: *const u8, n_compressions: u64,
+        seed: *const u8, proof_out: *mut u8, proof_len: *mut u64) -> i32;
+    pub fn zk_verify_proof(ctx: *mut zk_ctx, proof: *const u8, proof_len: u64) -> i32;
+    pub fn zk_mock_verify(ctx: *mut zk_ctx, inputs: *const u8, n_compressions: u64,
+        advice_override: *const c_void, failure: *mut u64) -> i32;
+    pub fn zk_dist_unique_id(out: *mut u8) -> i32;
+    pub fn zk_dist_init(ctx: *mut zk_ctx, id: *const u8, rank: i32, world: i32) -> i32;
+    pub fn zk_dist_info(ctx: *const zk_ctx, rank: *mut i32, world: *mut i32) -> i32;
+    pub fn zk_dist_range(n_points: u64, rank: i32, world: i32, lo: *mut u64, hi: *mut u64) -> i32;
 }
+pub const ZK_DIST_ID_BYTES: usize = 128;

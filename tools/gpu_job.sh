@@ -1,6 +1,7 @@
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
-ZK_PHASE_TRACE=1 timeout 300 python tools/profile_proof.py 19 64 1 > gpurun_out/phase.log 2>&1; echo "phase rc=$?"; grep -E "phase|proof_wall" gpurun_out/phase.log | tail -12
-timeout 300 python tools/profile_proof.py 19 64 5 2>&1 | tail -1
-timeout 300 python tools/profile_proof.py 17 26 5 2>&1 | tail -1
-timeout 300 python tools/profile_proof.py 21 256 3 2>&1 | tail -1
+for S in 4 6; do
+timeout 600 python bench.py --steps 12 --warmup 3 --streams $S --no-cpu-baseline > gpurun_out/bench_s$S.json 2> gpurun_out/bench_s$S.err; echo "bench S=$S rc=$?"; python -c "
+import json;d=json.load(open('gpurun_out/bench_s$S.json'));print(d['value'],d['ms_per_step'],d['single_stream_ms_per_proof'],d['e2e']['value'],d['roofline']['frac'],d['gpu_launches'])"; tail -2 gpurun_out/bench_s$S.err
+done
+timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench default rc=$?"; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
+timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2

@@ -115,7 +115,7 @@ extern "C" int32_t zk_bench_int_pipe(zk_ctx* ctx, int32_t mode, uint32_t iters,
                                      double* instr_per_sec) {
   if (!ctx || !instr_per_sec || mode < 0 || mode > 8) return ZK_E_INVALID;
   ZK_CUDA(ctx, cudaSetDevice(ctx->device));
-  const int blocks = ctx->sm_count * 120, threads = mode >= 3 ? 128 : 256;
+  const int blocks = ctx->sm_count * (mode >= 3 ? 120 : 8), threads = mode >= 3 ? 128 : 256;
   int32_t rc = ensure_buf(ctx, ctx->scratch_digests, (size_t)blocks * threads * 8);
   if (rc) return rc;
   uint32_t* out = (uint32_t*)ctx->scratch_digests.ptr;

@@ -18,7 +18,6 @@ struct MockArgs {
   SelectorExpr sel[NUM_SELECTORS];
   GateConsts k;
 };
-__constant__ MockArgs ma;
 
 struct Checker {  // accumulator policy for fold_gates: remembers the first non-zero polynomial
   int idx = 0, bad = -1;
@@ -33,7 +32,8 @@ __device__ __forceinline__ void report(unsigned long long* first, uint64_t kind,
   atomicMin(first, (unsigned long long)((kind << 56) | (row << 16) | (index & 0xffff)));
 }
 
-__global__ void __launch_bounds__(128) mock_rows_kernel(uint64_t n, uint64_t usable, unsigned long long* first) {
+__global__ void __launch_bounds__(128) mock_rows_kernel(const __grid_constant__ MockArgs ma, uint64_t n, uint64_t usable,
+                                                        unsigned long long* first) {
   const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (r >= usable) return;
   const uint64_t rp = (r + n - 1) & (n - 1), rn = (r + 1) & (n - 1);
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(128) mock_rows_kernel(uint64_t n, uint64_t usa
 struct DevCopy {
   uint32_t lcol, lrow, rcol, rrow;
 };
-__global__ void mock_copies_kernel(const DevCopy* __restrict__ copies, uint32_t ncopies, uint64_t n_regions,
+__global__ void mock_copies_kernel(const __grid_constant__ MockArgs ma, const DevCopy* __restrict__ copies, uint32_t ncopies, uint64_t n_regions,
                                    uint64_t region_rows, unsigned long long* first) {
   const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (t >= n_regions * ncopies) return;
@@ -123,7 +123,6 @@ extern "C" int32_t zk_mock_verify(zk_ctx* ctx, const uint8_t* inputs, uint64_t n
   for (int i = 0; i < 4; i++) args.k.small[i] = Fp::from_u64(i);
   args.k.pow2[0] = Fp::one();
   for (int e = 1; e < 127; e++) args.k.pow2[e] = args.k.pow2[e - 1].dbl();
-  ZK_CUDA(ctx, cudaMemcpyToSymbolAsync(ma, &args, sizeof args, 0, cudaMemcpyHostToDevice, st));
   DeviceRegionLayout* L = nullptr;
   if ((rc = get_layout(ctx, K.rounds, &L))) return rc;
   const uint32_t ncopies = (uint32_t)L->host.copies.size();
@@ -138,11 +137,11 @@ extern "C" int32_t zk_mock_verify(zk_ctx* ctx, const uint8_t* inputs, uint64_t n
   DevCopy* d_copies = (DevCopy*)((char*)ctx->scratch_a.ptr + 64);
   ZK_CUDA(ctx, cudaMemsetAsync(d_first, 0xff, 8, st));
   if (ncopies) ZK_CUDA(ctx, cudaMemcpyAsync(d_copies, hc.data(), (size_t)ncopies * sizeof(DevCopy), cudaMemcpyHostToDevice, st));
-  mock_rows_kernel<<<(unsigned)((usable + 127) / 128), 128, 0, st>>>(n, usable, d_first);
+  mock_rows_kernel<<<(unsigned)((usable + 127) / 128), 128, 0, st>>>(args, n, usable, d_first);
   ctx->launches++;
   const uint64_t total = n_compressions * ncopies;
   if (total) {
-    mock_copies_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_copies, ncopies, n_compressions, K.region_rows,
+    mock_copies_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(args, d_copies, ncopies, n_compressions, K.region_rows,
                                                                        d_first);
     ctx->launches++;
   }

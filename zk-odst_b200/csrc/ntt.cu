@@ -75,21 +75,26 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(NttPassArgs a) {
     sm[e] = v;
   }
   __syncthreads();
-  // ---- stages
-  for (int r = 0; r < S; r++) {
-    const int s = a.s0 + r + 1;  // global stage, half size m = 2^(s-1)
-    const uint32_t nbf = tile_elems >> 1;
-    for (uint32_t b = threadIdx.x; b < nbf; b += blockDim.x) {
-      uint32_t l = b & (W - 1), tb = b >> logW;          // tb in [0, 2^(S-1))
-      uint32_t tlo = tb & ((1u << r) - 1), thi = tb >> r;
-      uint32_t t0 = (thi << (r + 1)) | tlo, t1 = t0 | (1u << r);
-      uint32_t j = (tlo << a.s0) | (lo0 + l);            // index within the half
-      Fp w = a.tw[(size_t)j << (L - s)];
-      Fp x = sm[(t0 << logW) | l], y = sm[(t1 << logW) | l] * w;
+  // ---- stages: one butterfly per thread (blockDim = tile_elems / 2); the twiddle of the next stage is
+  // requested before the barrier so that its latency overlaps the wait
+  {
+    const uint32_t b = threadIdx.x;
+    const uint32_t l = b & (W - 1), tb = b >> logW;  // tb in [0, 2^(S-1))
+    auto twiddle_index = [&](int r) {
+      const uint32_t tlo = tb & ((1u << r) - 1);
+      const uint32_t j = (tlo << a.s0) | (lo0 + l);  // index within the half
+      return (size_t)j << (L - (a.s0 + r + 1));
+    };
+    Fp w = a.tw[twiddle_index(0)];
+    for (int r = 0; r < S; r++) {
+      const uint32_t tlo = tb & ((1u << r) - 1), thi = tb >> r;
+      const uint32_t t0 = (thi << (r + 1)) | tlo, t1 = t0 | (1u << r);
+      const Fp x = sm[(t0 << logW) | l], y = sm[(t1 << logW) | l] * w;
       sm[(t0 << logW) | l] = x + y;
       sm[(t1 << logW) | l] = x - y;
+      if (r + 1 < S) w = a.tw[twiddle_index(r + 1)];
+      __syncthreads();
     }
-    __syncthreads();
   }
   // ---- store
   for (uint32_t e = threadIdx.x; e < tile_elems; e += blockDim.x) {
@@ -185,7 +190,7 @@ int32_t ntt_run(zk_ctx* ctx, const Fp* in, uint32_t n_in, Fp* out, int log_n, co
     uint32_t tile_elems = 1u << (S + logW);
     uint32_t tiles = N / tile_elems;
     size_t smem = (size_t)tile_elems * sizeof(Fp);
-    ntt_pass_kernel<<<tiles, 256, smem, ctx->stream>>>(a);
+    ntt_pass_kernel<<<tiles, tile_elems / 2, smem, ctx->stream>>>(a);
     ctx->launches++;
     s0 += S;
   }

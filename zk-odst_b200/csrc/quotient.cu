@@ -17,7 +17,8 @@
 namespace zkodst {
 namespace {
 
-__constant__ QuotientArgs qa;
+// The arguments travel as a (6 KB) __grid_constant__ kernel parameter rather than a __constant__
+// symbol: contexts of different host threads may run quotient kernels on the same device concurrently.
 // halo2 advice column of permutation column ci (PERM_COLUMNS, prover_state.h), usable in device code
 #define PERM_COLUMNS_DEV(ci) ((ci) == 0 ? 8 : (ci) == 1 ? 9 : (ci) == 2 ? 1 : (ci) == 3 ? 2 : (ci) == 4 ? 0 : (ci) == 5 ? 3 : (ci) == 6 ? 4 : 5)
 
@@ -35,7 +36,7 @@ constexpr int Q_MINB = 4;
 // regrouped by expression — gates that share a polynomial (a1/a2, c1/c2, d1/d2) share its evaluation —
 // and every cell and selector is fetched where it is used, which keeps the live set small.  The order
 // of evaluation does not matter: field arithmetic is exact, the value equals fold_gates (gates.cuh).
-__global__ void __launch_bounds__(128, Q_MINB) quotient_gates_kernel(uint64_t en, uint64_t mask) {
+__global__ void __launch_bounds__(128, Q_MINB) quotient_gates_kernel(const __grid_constant__ QuotientArgs qa, uint64_t en, uint64_t mask) {
   const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= en) return;
   const uint64_t ip = (i - 4) & mask, in = (i + 4) & mask;  // rotation by one row = 4 steps
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(128, Q_MINB) quotient_gates_kernel(uint64_t en
 }
 
 // part 2: the permutation argument (columns in enable_equality order: a1,a2 | a3,a4 | a5,a6 | a7,a8)
-__global__ void __launch_bounds__(128, Q_MINB) quotient_perm_kernel(uint64_t en, uint64_t mask) {
+__global__ void __launch_bounds__(128, Q_MINB) quotient_perm_kernel(const __grid_constant__ QuotientArgs qa, uint64_t en, uint64_t mask) {
   const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= en) return;
   const uint64_t in = (i + 4) & mask;
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(128, Q_MINB) quotient_perm_kernel(uint64_t en,
 }
 
 // part 3: the lookup argument, then the division by X^n - 1
-__global__ void __launch_bounds__(128, Q_MINB) quotient_lookup_kernel(uint64_t en, uint64_t mask) {
+__global__ void __launch_bounds__(128, Q_MINB) quotient_lookup_kernel(const __grid_constant__ QuotientArgs qa, uint64_t en, uint64_t mask) {
   const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= en) return;
   const uint64_t ip = (i - 4) & mask, in = (i + 4) & mask;
@@ -170,12 +171,11 @@ __global__ void __launch_bounds__(128, Q_MINB) quotient_lookup_kernel(uint64_t e
 }  // namespace
 
 int32_t quotient_run(zk_ctx* ctx, const QuotientArgs& args, uint64_t en) {
-  ZK_CUDA(ctx, cudaMemcpyToSymbolAsync(qa, &args, sizeof(QuotientArgs), 0, cudaMemcpyHostToDevice, ctx->stream));
   KernelTimer timer(ctx, KC_QUOTIENT);
   const unsigned grid = (unsigned)((en + 127) / 128);
-  quotient_gates_kernel<<<grid, 128, 0, ctx->stream>>>(en, en - 1);
-  quotient_perm_kernel<<<grid, 128, 0, ctx->stream>>>(en, en - 1);
-  quotient_lookup_kernel<<<grid, 128, 0, ctx->stream>>>(en, en - 1);
+  quotient_gates_kernel<<<grid, 128, 0, ctx->stream>>>(args, en, en - 1);
+  quotient_perm_kernel<<<grid, 128, 0, ctx->stream>>>(args, en, en - 1);
+  quotient_lookup_kernel<<<grid, 128, 0, ctx->stream>>>(args, en, en - 1);
   ctx->launches += 3;
   ZK_CUDA(ctx, cudaGetLastError());
   return ZK_OK;
