@@ -163,7 +163,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--compressions", type=int, default=N_COMPRESSIONS)
-    ap.add_argument("--streams", type=int, default=3,
+    ap.add_argument("--streams", type=int, default=4,
                     help="concurrent proof streams per GPU (one context and host thread each)")
     ap.add_argument("--msm-split", action="store_true",
                     help="configs[3]: ONE proof stream, every MSM split by point range across the "

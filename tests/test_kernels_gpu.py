@@ -100,10 +100,11 @@ def test_ntt_matches_oracle(ctx, oracle, log_n, inverse):
     assert np.array_equal(got, ref)
 
 
-def test_ntt_roundtrip_large(ctx, oracle):
-    """Full-size property: iNTT(NTT(x)) == x at the extended-domain size of config 3 (2^21)."""
+@pytest.mark.parametrize("log_n", [21, 22, 24, 25])
+def test_ntt_roundtrip_large(ctx, oracle, log_n):
+    """Full-size property: iNTT(NTT(x)) == x at the extended-domain sizes of configs 3 and 4
+    (2^21 .. 2^25; 22 and 24 split into 8-stage passes, the others into 7- and 6-stage ones)."""
     import torch
-    log_n = 21
     n = 1 << log_n
     data = oracle_lib.random_fields(oracle, SEED, 1 << 12)
     big = np.tile(data, (n >> 12, 1))

@@ -169,6 +169,7 @@ int32_t ntt_run(zk_ctx* ctx, const Fp* in, uint32_t n_in, Fp* out, int log_n, co
     int remaining = log_n - s0, passes = (remaining + MAXS - 1) / MAXS;
     S = (remaining + passes - 1) / passes;
     int logW = s0 == 0 ? 0 : (s0 < 2 ? s0 : 2);
+    if (S + logW > 9) logW = 9 - S;  // one butterfly per thread, at most 256 threads
     a.in = s0 == 0 ? src : out;
     a.out = out;
     a.tw = opt.inverse ? T->tw_inv : T->tw_fwd;
