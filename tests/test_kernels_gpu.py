@@ -89,7 +89,7 @@ def test_msm_linearity(ctx, oracle, urs):
     assert np.array_equal(out_sum, out_ab)
 
 
-@pytest.mark.parametrize("log_n", [0, 1, 3, 8, 9, 13, 17])
+@pytest.mark.parametrize("log_n", [0, 1, 3, 8, 9, 13, 16, 17])
 @pytest.mark.parametrize("inverse", [False, True])
 def test_ntt_matches_oracle(ctx, oracle, log_n, inverse):
     n = 1 << log_n
