@@ -83,6 +83,21 @@ int32_t zk_blake2f_min_k(uint32_t rounds, uint64_t n_compressions, int32_t* k);
 int32_t zk_blake2f_layout_hash(uint32_t rounds, uint64_t* copies_hash, uint64_t* selectors_hash,
                                uint64_t* n_copies);
 
+/* ---- EIP-152 wire format and the multi-block hashing driver (host-only helpers) ------------------
+ * zk_eip152_validate: the precompile's input checks — length must be 213, f must be 0 or 1
+ * (ZK_E_INPUT otherwise); writes the big-endian round count.
+ * zk_blake2f_compress: F on one record (the function the circuit proves), 64-byte h' out.
+ * zk_blake2b_records: replaces the streaming gadget `Blake2f::{new, update, finalize, digest}`
+ * (blake2f-circuit/src/blake2f.rs:88-181): the unkeyed BLAKE2b-512 of `msg` as the chain of
+ * ceil(len / 128) (at least 1) EIP-152 records — chaining value, block, byte counter, final flag —
+ * ready for zk_blake2f_witness_batch / zk_create_proof; rounds = 12 for real BLAKE2b.
+ * *n_records: in = capacity of records_out in records, out = records needed (ZK_E_BUFFER if short;
+ * records_out and digest_out NULL = size query).  digest_out: the 64-byte hash, or NULL. */
+int32_t zk_eip152_validate(const uint8_t* input, uint64_t len, uint32_t* rounds);
+int32_t zk_blake2f_compress(const uint8_t input[ZK_BLAKE2F_INPUT_BYTES], uint8_t out[64]);
+int32_t zk_blake2b_records(const uint8_t* msg, uint64_t len, uint32_t rounds, uint8_t* records_out,
+                           uint64_t* n_records, uint8_t digest_out[64]);
+
 /* ---- K1: batched witness generation ------------------------------------------------------
  * Replaces `Circuit::synthesize` for the BLAKE2f circuit: Table16Chip::compress
  * (blake2f-circuit/src/blake2f/table16.rs:361-373, `todo!()` upstream),

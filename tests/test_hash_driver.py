@@ -1,0 +1,68 @@
+"""EIP-152 wire format and the multi-block hashing driver (host-only entry points of the C ABI;
+the reference's `Blake2f::{update, finalize}`, blake2f-circuit/src/blake2f.rs:88-181)."""
+import hashlib
+import json
+import os
+
+import pytest
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+VECS = json.load(open(os.path.join(G, "eip152.json")))
+
+
+@pytest.mark.parametrize("idx", range(len(VECS)))
+def test_compress_matches_eip152_vectors(zk, idx):
+    v = VECS[idx]
+    assert zk.blake2f_compress(bytes.fromhex(v["input"])).hex() == v["output"]
+
+
+def test_eip152_rejections(zk):
+    rec = bytes.fromhex(VECS[1]["input"])
+    assert zk.eip152_validate(rec) == int.from_bytes(rec[:4], "big")
+    for bad in (rec[:-1], rec + b"\x00", b"", rec[:212] + b"\x02"):   # EIP-152 vectors 0-3
+        with pytest.raises(zk.ZkError) as e:
+            zk.eip152_validate(bad)
+        assert e.value.code == -5
+
+
+@pytest.mark.parametrize("length", [0, 1, 3, 127, 128, 129, 255, 256, 257, 1000, 4096])
+def test_record_chain_hashes_like_hashlib(zk, oracle, length):
+    msg = bytes((i * 7 + 3) & 0xFF for i in range(length))
+    records, digest = zk.blake2b_records(msg)
+    assert digest == hashlib.blake2b(msg).digest()
+    n = len(records) // 213
+    assert n == max(1, (length + 127) // 128)
+    # replay the chain with the ORACLE's F: every record's h is the previous record's output
+    h = None
+    for i in range(n):
+        rec = records[213 * i: 213 * (i + 1)]
+        assert rec[:4] == (12).to_bytes(4, "big") and rec[212] == (1 if i == n - 1 else 0)
+        if h is not None:
+            assert rec[4:68] == h
+        h = oracle.blake2f(rec)
+    assert h == digest
+
+
+@pytest.mark.gpu
+def test_prove_a_multi_block_hash(zk, ctx, oracle):
+    """A 3-block message proved as one circuit; the digest cells hold BLAKE2b-512(msg)."""
+    import numpy as np
+    import oracle_lib
+    msg = b"zk-odst" * 50
+    records, digest = zk.blake2b_records(msg)
+    n = len(records) // 213
+    assert n == 3
+    adv = np.empty((12, 1 << 17, 4), dtype=np.uint64)
+    dig = np.empty((n, 8), dtype=np.uint64)
+    ctx.witness_batch(17, 12, records, n, adv, dig)
+    assert dig[n - 1].tobytes() == digest == hashlib.blake2b(msg).digest()
+    seed = zk.REFERENCE_SEED
+    ctx.params_generate_substitute(17, seed)
+    ctx.keygen(12, n)
+    assert ctx.mock_verify(records, n) is None
+    proof = ctx.create_proof(records, n, seed)
+    assert ctx.verify_proof(proof)
+    op = oracle_lib.OracleProver(oracle, params_bytes=ctx.params_write())
+    op.keygen(12, n)
+    assert op.verify(proof)[0] == 0
+    op.close()

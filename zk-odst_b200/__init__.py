@@ -13,6 +13,9 @@ from .binding import (  # noqa: F401
     min_k,
     layout_hash,
     dist_unique_id,
+    eip152_validate,
+    blake2f_compress,
+    blake2b_records,
     dist_range,
 )
 from .inputs import eip152_record, synthetic_inputs, XorShiftRng, REFERENCE_SEED  # noqa: F401

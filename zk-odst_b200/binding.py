@@ -58,6 +58,9 @@ def load_library():
             "zk_ntt_fp": (i32, [vp, vp, i32, i32, i32]),
             "zk_blake2f_witness_batch": (i32, [vp, i32, u32, vp, u64, vp, vp]),
             "zk_blake2f_witness_batch_device": (i32, [vp, i32, u32, vp, u64, vp, vp]),
+            "zk_eip152_validate": (i32, [c.c_char_p, u64, c.POINTER(u32)]),
+            "zk_blake2f_compress": (i32, [c.c_char_p, c.c_char_p]),
+            "zk_blake2b_records": (i32, [c.c_char_p, u64, u32, c.c_char_p, c.POINTER(u64), c.c_char_p]),
             "zk_verify_proof": (i32, [vp, c.c_char_p, u64]),
             "zk_mock_verify": (i32, [vp, vp, u64, vp, c.POINTER(u64)]),
             "zk_dist_unique_id": (i32, [c.c_char_p]),
@@ -71,6 +74,39 @@ def load_library():
             fn.argtypes = args
         _LIB = lib
     return _LIB
+
+
+def eip152_validate(record):
+    """Round count of a well-formed EIP-152 input; raises ZkError(ZK_E_INPUT) otherwise."""
+    r = ctypes.c_uint32()
+    rc = load_library().zk_eip152_validate(bytes(record), len(record), ctypes.byref(r))
+    if rc:
+        raise ZkError(rc, "malformed EIP-152 input")
+    return r.value
+
+
+def blake2f_compress(record):
+    out = ctypes.create_string_buffer(64)
+    rc = load_library().zk_blake2f_compress(bytes(record), out)
+    if rc:
+        raise ZkError(rc, "malformed EIP-152 input")
+    return out.raw
+
+
+def blake2b_records(msg, rounds=12):
+    """(records, digest): the EIP-152 record chain whose proof is a proof of BLAKE2b-512(msg)."""
+    lib = load_library()
+    msg = bytes(msg)
+    n = ctypes.c_uint64(0)
+    rc = lib.zk_blake2b_records(msg, len(msg), rounds, None, ctypes.byref(n), None)
+    if rc:
+        raise ZkError(rc)
+    buf = ctypes.create_string_buffer(n.value * 213)
+    dig = ctypes.create_string_buffer(64)
+    rc = lib.zk_blake2b_records(msg, len(msg), rounds, buf, ctypes.byref(n), dig)
+    if rc:
+        raise ZkError(rc)
+    return buf.raw, dig.raw
 
 
 def dist_unique_id():
