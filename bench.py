@@ -309,7 +309,11 @@ def main():
         roofline = {
             "kernel": "fixed_accumulate_kernel (+ heavy-bucket kernels)", "bound": "int_pipe",
             "achieved": achieved, "peak": int_peak / 1e12, "unit": "TMAC/s",
-            "frac": achieved / (int_peak / 1e12) if achieved else None, "traffic": None,
+            "frac": achieved / (int_peak / 1e12) if achieved else None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of one full-width launch (8.39 M sorted
+            # entries, k = 19) from the ncu --set full capture profiles/r01_fixed_accumulate_ncu_full_v2.txt;
+            # algorithmic bytes of that launch: 8.39 M x (64 B point + 4 B index) = 0.57 GB
+            "traffic": 1.073e9 if k == 19 else None,
             "peak_source": "zk_bench_int_pipe mode 1 (mad.wide.u32) measured in this run; "
                            "MEASURED_PEAKS.json has no integer peak",
             "launches_per_proof": acc_launches, "avg_launch_ms": acc_ms / acc_launches if acc_launches else None,
