@@ -165,6 +165,9 @@ def main():
     ap.add_argument("--compressions", type=int, default=N_COMPRESSIONS)
     ap.add_argument("--streams", type=int, default=4,
                     help="concurrent proof streams per GPU (one context and host thread each)")
+    ap.add_argument("--blocking-sync", type=int, default=-1,
+                    help="1: host threads sleep while waiting for the device, 0: spin, -1: sleep only "
+                         "when ranks x streams would oversubscribe the cores")
     ap.add_argument("--msm-split", action="store_true",
                     help="configs[3]: ONE proof stream, every MSM split by point range across the "
                          "ranks (NCCL all-gather of partial points); strong scaling")
@@ -200,6 +203,11 @@ def main():
     torch.cuda.set_stream(ev_stream)
     ctxs = [zk.Context(local_rank) for _ in range(S)]
     ctx = ctxs[0]
+    # host threads of this box: world x S; they wait on blocking events instead of spinning when the
+    # cores would be oversubscribed
+    blocking = args.blocking_sync == 1 or (args.blocking_sync < 0 and world * S * 2 > (os.cpu_count() or 1))
+    for c in ctxs:
+        c.set_blocking_sync(blocking)
     if split:
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
@@ -345,7 +353,7 @@ def main():
             "dtype": "u64 (4x64-bit Montgomery limbs)",
             "data": "synthetic", "config": workload_config(k, n, split, world),
             "proofs_per_sec": jobs / (ms_per_step * 1e-3), "proof_bytes": len(proof),
-            "streams_per_gpu": S, "single_stream_ms_per_proof": single_ms,
+            "streams_per_gpu": S, "single_stream_ms_per_proof": single_ms, "blocking_sync": bool(blocking),
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": len(inputs),

@@ -51,6 +51,10 @@ const char* zk_last_error(const zk_ctx* ctx);
  * NULL restores the private stream. */
 int32_t zk_ctx_set_stream(zk_ctx* ctx, void* cuda_stream);
 int32_t zk_ctx_synchronize(zk_ctx* ctx);
+/* How the host thread waits for the device inside the library's calls: 0 = spin (lowest latency,
+ * the default), 1 = sleep on a blocking event — for several contexts per CPU core (e.g. 8 GPUs x 4
+ * proof streams).  Environment ZK_BLOCKING_SYNC=1 sets the default for new contexts. */
+int32_t zk_ctx_set_blocking_sync(zk_ctx* ctx, int32_t on);
 /* Number of kernels this context has launched so far (bench.py `gpu_launches`). */
 uint64_t zk_ctx_launch_count(const zk_ctx* ctx);
 /* Milliseconds the most recent launch of the named kernel class took, measured with CUDA

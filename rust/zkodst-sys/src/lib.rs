@@ -24,6 +24,7 @@ extern "C" {
     pub fn zk_last_error(ctx: *const zk_ctx) -> *const c_char;
     pub fn zk_ctx_set_stream(ctx: *mut zk_ctx, cuda_stream: *mut c_void) -> i32;
     pub fn zk_ctx_synchronize(ctx: *mut zk_ctx) -> i32;
+    pub fn zk_ctx_set_blocking_sync(ctx: *mut zk_ctx, on: i32) -> i32;
     pub fn zk_ctx_launch_count(ctx: *const zk_ctx) -> u64;
     pub fn zk_blake2f_rows_per_compression(rounds: u32, rows: *mut u64) -> i32;
     pub fn zk_blake2f_min_k(rounds: u32, n_compressions: u64, k: *mut i32) -> i32;

@@ -38,6 +38,7 @@ def load_library():
             "zk_last_error": (c.c_char_p, [vp]),
             "zk_ctx_set_stream": (i32, [vp, vp]),
             "zk_ctx_synchronize": (i32, [vp]),
+            "zk_ctx_set_blocking_sync": (i32, [vp, i32]),
             "zk_ctx_launch_count": (u64, [vp]),
             "zk_ctx_last_kernel_ms": (i32, [vp, i32, c.POINTER(c.c_float)]),
             "zk_ctx_enable_timing": (i32, [vp, i32]),
@@ -193,6 +194,9 @@ class Context:
 
     def set_stream(self, cuda_stream_ptr):
         self._check(self.lib.zk_ctx_set_stream(self.h, cuda_stream_ptr))
+
+    def set_blocking_sync(self, on=True):
+        self._check(self.lib.zk_ctx_set_blocking_sync(self.h, 1 if on else 0))
 
     def synchronize(self):
         self._check(self.lib.zk_ctx_synchronize(self.h))

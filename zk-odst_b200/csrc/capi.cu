@@ -1,4 +1,5 @@
 // extern "C" entry points of include/zkodst.h: context management and the K1 witness path.
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -17,10 +18,21 @@ int32_t check_cuda(zk_ctx* ctx, cudaError_t e, const char* what) {
   return set_error(ctx, e == cudaErrorMemoryAllocation ? ZK_E_NOMEM : ZK_E_CUDA, msg);
 }
 
+cudaError_t zk_stream_sync(zk_ctx* ctx) {
+  if (!ctx->blocking_sync) return cudaStreamSynchronize(ctx->stream);
+  if (!ctx->sync_event) {
+    cudaError_t e = cudaEventCreateWithFlags(&ctx->sync_event, cudaEventBlockingSync | cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
+  }
+  cudaError_t e = cudaEventRecord(ctx->sync_event, ctx->stream);
+  if (e != cudaSuccess) return e;
+  return cudaEventSynchronize(ctx->sync_event);
+}
+
 int32_t ensure_buf(zk_ctx* ctx, DevBuf& b, size_t bytes) {
   if (b.cap >= bytes) return ZK_OK;
   if (b.ptr) {
-    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZK_CUDA(ctx, zk_stream_sync(ctx));
     ZK_CUDA(ctx, cudaFree(b.ptr));
     b.ptr = nullptr;
     b.cap = 0;
@@ -43,7 +55,7 @@ int32_t get_layout(zk_ctx* ctx, uint32_t rounds, DeviceRegionLayout** out) {
     ZK_CUDA(ctx, cudaMalloc((void**)&L.d_desc, bytes));
     ZK_CUDA(ctx, cudaMemcpyAsync(L.d_desc, L.host.desc.data(), bytes, cudaMemcpyHostToDevice,
                                  ctx->stream));
-    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZK_CUDA(ctx, zk_stream_sync(ctx));
     it = ctx->layouts.emplace(rounds, std::move(L)).first;
   }
   *out = &it->second;
@@ -71,6 +83,10 @@ int32_t zk_ctx_create(int32_t device_id, zk_ctx** out) {
     return ZK_E_CUDA;
   }
   ctx->stream = ctx->own_stream;
+  {
+    const char* e = getenv("ZK_BLOCKING_SYNC");
+    ctx->blocking_sync = e && e[0] == '1';
+  }
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device_id);
   if (cudaMalloc((void**)&ctx->d_status, sizeof(int)) != cudaSuccess ||
       cudaMemset(ctx->d_status, 0, sizeof(int)) != cudaSuccess) {
@@ -105,6 +121,7 @@ void zk_ctx_destroy(zk_ctx* ctx) {
     cudaFree(kv.second.tw_inv);
   }
   cudaFree(ctx->d_status);
+  if (ctx->sync_event) cudaEventDestroy(ctx->sync_event);
   for (auto& e : ctx->ev_pool)
     if (e) cudaEventDestroy(e);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -119,10 +136,16 @@ int32_t zk_ctx_set_stream(zk_ctx* ctx, void* cuda_stream) {
   return ZK_OK;
 }
 
+int32_t zk_ctx_set_blocking_sync(zk_ctx* ctx, int32_t on) {
+  if (!ctx) return ZK_E_INVALID;
+  ctx->blocking_sync = on != 0;
+  return ZK_OK;
+}
+
 int32_t zk_ctx_synchronize(zk_ctx* ctx) {
   if (!ctx) return ZK_E_INVALID;
   ZK_CUDA(ctx, cudaSetDevice(ctx->device));
-  ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ZK_CUDA(ctx, zk_stream_sync(ctx));
   int st = 0;
   ZK_CUDA(ctx, cudaMemcpy(&st, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost));
   if (st) {
@@ -143,7 +166,7 @@ int32_t zk_ctx_enable_timing(zk_ctx* ctx, int32_t on) {
 // Sums the timed regions recorded since the previous report, per kernel class.
 int32_t zk_ctx_timing_report(zk_ctx* ctx, float* ms_per_class, uint32_t* launches_per_class) {
   if (!ctx) return ZK_E_INVALID;
-  ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ZK_CUDA(ctx, zk_stream_sync(ctx));
   float acc[KC_COUNT] = {};
   uint32_t cnt[KC_COUNT] = {};
   for (auto& t : ctx->timed) {

@@ -73,7 +73,7 @@ int32_t dist_sum_points(zk_ctx* ctx, XYZZ* results, int nb) {
   if (r != ncclSuccess) return nccl_error(ctx, r, "ncclAllGather");
   std::vector<XYZZ> all((size_t)nb * world);
   ZK_CUDA(ctx, cudaMemcpyAsync(all.data(), recv, bytes * world, cudaMemcpyDeviceToHost, ctx->stream));
-  ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ZK_CUDA(ctx, zk_stream_sync(ctx));
   for (int m = 0; m < nb; m++) {
     XYZZ acc = all[m];
     for (int q = 1; q < world; q++) acc = acc.add(all[(size_t)q * nb + m]);

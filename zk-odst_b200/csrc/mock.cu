@@ -148,7 +148,7 @@ extern "C" int32_t zk_mock_verify(zk_ctx* ctx, const uint8_t* inputs, uint64_t n
   ZK_CUDA(ctx, cudaGetLastError());
   unsigned long long first = 0;
   ZK_CUDA(ctx, cudaMemcpyAsync(&first, d_first, 8, cudaMemcpyDeviceToHost, st));
-  ZK_CUDA(ctx, cudaStreamSynchronize(st));
+  ZK_CUDA(ctx, zk_stream_sync(ctx));
   if (first == ~0ull) {
     if (failure) failure[0] = failure[1] = failure[2] = 0;
     return ZK_OK;

@@ -341,7 +341,7 @@ int32_t msm_device(zk_ctx* ctx, const Fp* d_scalars, const Fp* d_extra, const Af
   // heavy path: sizes are data dependent, so read the two counters back
   uint32_t hc[2];
   ZK_CUDA(ctx, cudaMemcpyAsync(hc, hcount, 8, cudaMemcpyDeviceToHost, st));
-  ZK_CUDA(ctx, cudaStreamSynchronize(st));
+  ZK_CUDA(ctx, zk_stream_sync(ctx));
   if (hc[0] > max_heavy_items) return set_error(ctx, ZK_E_NOMEM, "msm: heavy work list overflow");
   if (hc[0]) {
     msm_heavy_accumulate_kernel<<<hc[0], HEAVY_THREADS, 0, st>>>(d_bases, sorted, hitems, hpartials);
@@ -384,20 +384,20 @@ int32_t msm_run(zk_ctx* ctx, const Fp* d_scalars, const Affine* d_bases, uint64_
   static const bool trace = getenv("ZK_MSM_TRACE") != nullptr;
   std::chrono::steady_clock::time_point t0;
   if (trace) {
-    cudaStreamSynchronize(ctx->stream);
+    zk_stream_sync(ctx);
     t0 = std::chrono::steady_clock::now();
   }
   rc = msm_device(ctx, d_scalars, d_extra, d_bases, n, c, &nwin, (XYZZ*)ctx->msm_out.ptr);
   if (rc) return rc;
   if (trace) {
-    cudaStreamSynchronize(ctx->stream);
+    zk_stream_sync(ctx);
     double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     fprintf(stderr, "[msm] n=%llu c=%d nwin=%d device_ms=%.3f\n", (unsigned long long)n, c, nwin, ms);
   }
   XYZZ sums[48];
   ZK_CUDA(ctx, cudaMemcpyAsync(sums, ctx->msm_out.ptr, (size_t)nwin * sizeof(XYZZ),
                                cudaMemcpyDeviceToHost, ctx->stream));
-  ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ZK_CUDA(ctx, zk_stream_sync(ctx));
   XYZZ total = XYZZ::identity();
   for (int w = nwin - 1; w >= 0; w--) {
     for (int i = 0; i < c; i++) total = total.dbl();

@@ -530,7 +530,7 @@ int32_t msm_fixed_batch(zk_ctx* ctx, const FixedBase& fb, const MsmJob* jobs, in
   static const bool trace = getenv("ZK_MSM_TRACE") != nullptr;
   std::chrono::steady_clock::time_point t0;
   if (trace) {
-    cudaStreamSynchronize(st);
+    zk_stream_sync(ctx);
     t0 = std::chrono::steady_clock::now();
   }
   DevJobs dj;
@@ -586,7 +586,7 @@ int32_t msm_fixed_batch(zk_ctx* ctx, const FixedBase& fb, const MsmJob* jobs, in
   Plan hp;
   ZK_CUDA(ctx, cudaMemcpyAsync(sums.data(), out, sums.size() * sizeof(XYZZ), cudaMemcpyDeviceToHost, st));
   ZK_CUDA(ctx, cudaMemcpyAsync(&hp, plan, sizeof(Plan), cudaMemcpyDeviceToHost, st));
-  ZK_CUDA(ctx, cudaStreamSynchronize(st));
+  ZK_CUDA(ctx, zk_stream_sync(ctx));
   if (hp.overflow) return set_error(ctx, ZK_E_NOMEM, "msm_fixed: heavy work list overflow");
   for (int m = 0; m < nb; m++) {
     const XYZZ* sm = &sums[(size_t)m * nout];

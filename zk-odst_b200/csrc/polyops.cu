@@ -218,7 +218,7 @@ int32_t poly_eval_batch(zk_ctx* ctx, const EvalJob* jobs, int njobs, uint64_t n,
     ctx->launches += 2;
     ZK_CUDA(ctx, cudaGetLastError());
     ZK_CUDA(ctx, cudaMemcpyAsync(results_host + base, results, (size_t)cnt * sizeof(Fp), cudaMemcpyDeviceToHost, st));
-    ZK_CUDA(ctx, cudaStreamSynchronize(st));
+    ZK_CUDA(ctx, zk_stream_sync(ctx));
   }
   return ZK_OK;
 }
@@ -237,7 +237,7 @@ int32_t inner_product(zk_ctx* ctx, const Fp* a, const Fp* b, uint64_t n, Fp* res
   ctx->launches += 2;
   ZK_CUDA(ctx, cudaGetLastError());
   ZK_CUDA(ctx, cudaMemcpyAsync(result_host, result, sizeof(Fp), cudaMemcpyDeviceToHost, st));
-  ZK_CUDA(ctx, cudaStreamSynchronize(st));
+  ZK_CUDA(ctx, zk_stream_sync(ctx));
   return ZK_OK;
 }
 

@@ -469,7 +469,7 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
     ZK_CUDA(ctx, cudaMemcpyAsync(&n_repeated, d_total, 4, cudaMemcpyDeviceToHost, st));
     int status = 0;
     ZK_CUDA(ctx, cudaMemcpyAsync(&status, ctx->d_status, 4, cudaMemcpyDeviceToHost, st));
-    ZK_CUDA(ctx, cudaStreamSynchronize(st));
+    ZK_CUDA(ctx, zk_stream_sync(ctx));
     if (status) {
       cudaMemsetAsync(ctx->d_status, 0, 4, st);
       return set_error(ctx, ZK_E_VERIFY, status == 3 ? "theta collision in the spread table"
@@ -530,7 +530,7 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
       if ((rc = upload_fp(ctx, z + n - BLINDING, tails, BLINDING))) return rc;
       if (s + 1 < NUM_SETS) {  // the next set starts from this set's last usable value
         ZK_CUDA(ctx, cudaMemcpyAsync(&last_z, z + n - (BLINDING + 1), sizeof(Fp), cudaMemcpyDeviceToHost, st));
-        ZK_CUDA(ctx, cudaStreamSynchronize(st));
+        ZK_CUDA(ctx, zk_stream_sync(ctx));
       }
       z_blinds[s] = tape.next();
     }
@@ -898,7 +898,7 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
     }
     Fp c;
     ZK_CUDA(ctx, cudaMemcpyAsync(&c, pp, sizeof(Fp), cudaMemcpyDeviceToHost, st));
-    ZK_CUDA(ctx, cudaStreamSynchronize(st));
+    ZK_CUDA(ctx, zk_stream_sync(ctx));
     tr.write_scalar(c);
     tr.write_scalar(f);
   }

@@ -162,7 +162,7 @@ int32_t install_params(zk_ctx* ctx, int k, Affine* g, Affine* g_lagrange, const 
     rc = fixed_base_build(ctx, g, n, 2, &S->params.fb_g8, 8);
     if (rc) return rc;
   }
-  ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ZK_CUDA(ctx, zk_stream_sync(ctx));
   S->has_params = true;
   return ZK_OK;
 }
@@ -253,7 +253,7 @@ extern "C" int32_t zk_params_generate_substitute(zk_ctx* ctx, int32_t k, const u
   fixed_base_mul_kernel<<<blocks, T, 0, st>>>(d_sl, d_table, n, gl);
   ctx->launches++;
   ZK_CUDA(ctx, cudaGetLastError());
-  ZK_CUDA(ctx, cudaStreamSynchronize(st));
+  ZK_CUDA(ctx, zk_stream_sync(ctx));
   cudaFree(d_raw);
   cudaFree(d_s);
   cudaFree(d_sl);
@@ -292,7 +292,7 @@ extern "C" int32_t zk_params_load(zk_ctx* ctx, const uint8_t* bytes, uint64_t le
   Affine wu[2];
   ZK_CUDA(ctx, cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
   ZK_CUDA(ctx, cudaMemcpyAsync(wu, d_wu, sizeof wu, cudaMemcpyDeviceToHost, st));
-  ZK_CUDA(ctx, cudaStreamSynchronize(st));
+  ZK_CUDA(ctx, zk_stream_sync(ctx));
   cudaFree(d_bytes);
   cudaFree(d_wu);
   cudaFree(d_bad);
@@ -325,7 +325,7 @@ extern "C" int32_t zk_params_write(zk_ctx* ctx, uint8_t* out, uint64_t* len) {
   uint32_t k = (uint32_t)S->params.k;
   memcpy(out, &k, 4);
   ZK_CUDA(ctx, cudaMemcpyAsync(out + 4, d_bytes, 64 * n, cudaMemcpyDeviceToHost, st));
-  ZK_CUDA(ctx, cudaStreamSynchronize(st));
+  ZK_CUDA(ctx, zk_stream_sync(ctx));
   cudaFree(d_bytes);
   point_to_bytes(S->params.w, out + 4 + 64 * n);
   point_to_bytes(S->params.u, out + 4 + 64 * n + 32);
@@ -607,12 +607,12 @@ extern "C" int32_t zk_blake2f_keygen(zk_ctx* ctx, uint32_t rounds, uint64_t n_co
     if ((rc = build(1, K.l_last))) return rc;
     if ((rc = build(2, lblind))) return rc;
     combine_active(ctx, K, lblind);
-    ZK_CUDA(ctx, cudaStreamSynchronize(st));
+    ZK_CUDA(ctx, zk_stream_sync(ctx));
     cudaFree(tmp);
     cudaFree(tmp2);
     cudaFree(lblind);
   }
-  ZK_CUDA(ctx, cudaStreamSynchronize(st));
+  ZK_CUDA(ctx, zk_stream_sync(ctx));
   cudaFree(d_tmpl);
   cudaFree(d_map);
   // vk.transcript_repr: substitute for the Rust `{:?}` rendering of vk.pinned():

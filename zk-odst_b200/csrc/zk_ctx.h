@@ -66,6 +66,9 @@ struct zk_ctx {
   void* nccl_comm = nullptr;
   int dist_rank = 0, dist_world = 1;
   zkodst::DevBuf dist_buf;
+  // host waits: spin (cudaStreamSynchronize) or sleep on a blocking event (many contexts per core)
+  bool blocking_sync = false;
+  cudaEvent_t sync_event = nullptr;
   bool xs_table_loaded = false;  // XorShift jump matrices resident in misc_ws (prover.cu)
 };
 
@@ -74,6 +77,8 @@ namespace zkodst {
 int32_t set_error(zk_ctx* ctx, int32_t code, const std::string& msg);
 int32_t check_cuda(zk_ctx* ctx, cudaError_t e, const char* what);
 int32_t ensure_buf(zk_ctx* ctx, DevBuf& b, size_t bytes);
+// waits for the context's stream; sleeps instead of spinning when ctx->blocking_sync is set
+cudaError_t zk_stream_sync(zk_ctx* ctx);
 int32_t get_layout(zk_ctx* ctx, uint32_t rounds, DeviceRegionLayout** out);
 
 struct KernelTimer {  // CUDA-event bracket on the context's stream, only when timing is on
