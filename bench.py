@@ -307,7 +307,7 @@ def main():
         # products, random, 3 h pieces, q', s), 12 advice columns (<= 32-bit cells), and the IPA: 5 rounds
         # of n terms on the original generators, then k - 5 rounds of n / 32 terms on the folded ones
         # (halo2's schedule would be 2n MSM terms plus n generator-folding scalar multiplications)
-        fold = 5 if (k > 13 and not split) else k
+        fold = 5 if (k > 13 and (not split or 32 % world == 0)) else k
         ipa_terms = fold + (k - fold) / float(1 << fold)
         full_terms = 13 + ipa_terms
         mac_per_proof = nrows * (full_terms * MAC_FULL + 12 * MAC_SMALL)

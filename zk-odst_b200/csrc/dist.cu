@@ -82,6 +82,12 @@ int32_t dist_sum_points(zk_ctx* ctx, XYZZ* results, int nb) {
   return ZK_OK;
 }
 
+int32_t dist_allgather_device(zk_ctx* ctx, const void* send, void* recv, size_t bytes) {
+  ncclResult_t r = nccl().AllGather(send, recv, bytes, ncclUint8, (ncclComm_t)ctx->nccl_comm, ctx->stream);
+  if (r != ncclSuccess) return nccl_error(ctx, r, "ncclAllGather");
+  return ZK_OK;
+}
+
 void dist_free(zk_ctx* ctx) {
   if (ctx->nccl_comm) {
     nccl().CommDestroy((ncclComm_t)ctx->nccl_comm);

@@ -27,7 +27,8 @@ struct FoldLists {  // bucket b (|digit| = b + 1): entries[offset[b] .. offset[b
 // buckets[b][i] = sum over the bucket's entries (q, w, sign) of +-T8[w][q * len + i]
 __global__ void __launch_bounds__(128)
 fold_accumulate_kernel(const Affine* __restrict__ table, uint64_t table_width, FoldLists lists,
-                       const uint32_t* __restrict__ entries, uint32_t len, XYZZ* __restrict__ buckets) {
+                       const uint32_t* __restrict__ entries, uint32_t len, uint32_t q_lo,
+                       XYZZ* __restrict__ buckets) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t b = blockIdx.y;
   if (i >= len) return;
@@ -35,7 +36,7 @@ fold_accumulate_kernel(const Affine* __restrict__ table, uint64_t table_width, F
   for (uint32_t e = lists.offset[b]; e < lists.offset[b + 1]; e++) {
     const uint32_t v = entries[e];  // q << 8 | w << 1 | sign
     const uint32_t q = v >> 8, w = (v >> 1) & 0x7f;
-    Affine p = table[(size_t)w * table_width + (size_t)q * len + i];
+    Affine p = table[(size_t)w * table_width + (size_t)(q - q_lo) * len + i];  // the table starts at q_lo
     if (v & 1) p.y = p.y.neg();
     acc = acc.add_affine(p);
   }
@@ -56,9 +57,9 @@ fold_segments_kernel(const XYZZ* __restrict__ buckets, uint32_t len, XYZZ* __res
   A[(size_t)s * len + i] = acc;
   S[(size_t)s * len + i] = running;
 }
-// H_i = sum_s A_s + 8 * sum_s s * S_s, normalised to affine
+// partial_i = sum_s A_s + 8 * sum_s s * S_s  (this rank's share of H_i)
 __global__ void __launch_bounds__(128)
-fold_finish_kernel(const XYZZ* __restrict__ A, const XYZZ* __restrict__ S, uint32_t len, Affine* __restrict__ out) {
+fold_finish_kernel(const XYZZ* __restrict__ A, const XYZZ* __restrict__ S, uint32_t len, XYZZ* __restrict__ out) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= len) return;
   XYZZ running = XYZZ::identity(), weighted = XYZZ::identity();
@@ -70,7 +71,16 @@ fold_finish_kernel(const XYZZ* __restrict__ A, const XYZZ* __restrict__ S, uint3
   for (int d = 0; (1 << d) < FOLD_SEG; d++) weighted = weighted.dbl();
 #pragma unroll 1
   for (int s = 0; s < FOLD_NSEG; s++) weighted = weighted.add(A[(size_t)s * len + i]);
-  out[i] = weighted.to_affine();
+  out[i] = weighted;
+}
+// H_i = sum over ranks of their partials, normalised to affine
+__global__ void __launch_bounds__(128)
+fold_combine_kernel(const XYZZ* __restrict__ parts, uint32_t nparts, uint32_t len, Affine* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= len) return;
+  XYZZ acc = parts[i];
+  for (uint32_t r = 1; r < nparts; r++) acc = acc.add(parts[(size_t)r * len + i]);
+  out[i] = acc.to_affine();
 }
 
 // window table of `npoints` affine points in one launch: the doubling chain per point, then ONE
@@ -106,17 +116,23 @@ table_build_kernel(Affine* __restrict__ table, uint64_t npoints, int c, int nwin
 
 }  // namespace
 
-size_t ipa_fold_workspace_bytes(uint64_t len) {
-  return (size_t)(FOLD_BUCKETS + 2 * FOLD_NSEG) * len * sizeof(XYZZ) + (size_t)(1u << 16) * 4;
+// buckets, segment sums, the entry list, this rank's partials and (multi-GPU) every rank's partials
+size_t ipa_fold_workspace_bytes(uint64_t len, int world) {
+  return (size_t)(FOLD_BUCKETS + 2 * FOLD_NSEG + 1 + world) * len * sizeof(XYZZ) + (size_t)(1u << 16) * 4;
 }
 
 // out[0 .. len): the generators after r folds with challenges u[0 .. r)  (len = fb8.total_main >> r)
 int32_t ipa_fold_generators(zk_ctx* ctx, const FixedBase& fb8, const Fp* u, int r, void* workspace, Affine* out) {
-  if (fb8.c != FOLD_C || fb8.nwin != FOLD_WINDOWS || fb8.lo != 0 || fb8.nmain != fb8.total_main || r < 1 || r > 8)
+  if (fb8.c != FOLD_C || fb8.nwin != FOLD_WINDOWS || r < 1 || r > 8)
     return set_error(ctx, ZK_E_INVALID, "ipa_fold_generators: unsupported table or round count");
   const uint64_t n = fb8.total_main;
   const uint32_t len = (uint32_t)(n >> r);
   const uint32_t nq = 1u << r;
+  const int world = ctx->dist_world;
+  // this rank's table covers points [lo, lo + nmain) = q in [q_lo, q_hi)
+  if (fb8.lo % len || fb8.nmain % len || (world == 1 && fb8.nmain != n))
+    return set_error(ctx, ZK_E_INVALID, "ipa_fold_generators: point range is not a whole number of blocks");
+  const uint32_t q_lo = (uint32_t)(fb8.lo / len), q_hi = (uint32_t)((fb8.lo + fb8.nmain) / len);
   // digits of the 2^r shared scalars, bucket-sorted on the host
   std::vector<uint32_t> bucket_of((size_t)nq * FOLD_WINDOWS), packed((size_t)nq * FOLD_WINDOWS);
   FoldLists lists;
@@ -139,6 +155,7 @@ int32_t ipa_fold_generators(zk_ctx* ctx, const FixedBase& fb8, const Fp* u, int 
         carry = 0;
         if (d) e = (d - 1) << 1;
       }
+      if (q < q_lo || q >= q_hi) e = 0xffffffffu;  // another rank's points
       bucket_of[(size_t)q * FOLD_WINDOWS + w] = e;
       if (e != 0xffffffffu) counts[e >> 1]++;
     }
@@ -157,17 +174,25 @@ int32_t ipa_fold_generators(zk_ctx* ctx, const FixedBase& fb8, const Fp* u, int 
   XYZZ* buckets = (XYZZ*)workspace;
   XYZZ* A = buckets + (size_t)FOLD_BUCKETS * len;
   XYZZ* S = A + (size_t)FOLD_NSEG * len;
-  uint32_t* d_entries = (uint32_t*)(S + (size_t)FOLD_NSEG * len);
-  ZK_CUDA(ctx, cudaMemcpyAsync(d_entries, packed.data(), (size_t)lists.offset[FOLD_BUCKETS] * 4,
-                               cudaMemcpyHostToDevice, st));
+  XYZZ* mine = S + (size_t)FOLD_NSEG * len;
+  XYZZ* all = mine + len;
+  uint32_t* d_entries = (uint32_t*)(all + (size_t)world * len);
+  if (lists.offset[FOLD_BUCKETS])
+    ZK_CUDA(ctx, cudaMemcpyAsync(d_entries, packed.data(), (size_t)lists.offset[FOLD_BUCKETS] * 4,
+                                 cudaMemcpyHostToDevice, st));
   const unsigned bx = (len + 127) / 128;
   {
     KernelTimer timer(ctx, KC_COLLAPSE);
-    fold_accumulate_kernel<<<dim3(bx, FOLD_BUCKETS), 128, 0, st>>>(fb8.table, fb8.npoints, lists, d_entries, len,
+    fold_accumulate_kernel<<<dim3(bx, FOLD_BUCKETS), 128, 0, st>>>(fb8.table, fb8.npoints, lists, d_entries, len, q_lo,
                                                                   buckets);
     fold_segments_kernel<<<dim3(bx, FOLD_NSEG), 128, 0, st>>>(buckets, len, A, S);
-    fold_finish_kernel<<<bx, 128, 0, st>>>(A, S, len, out);
-    ctx->launches += 3;
+    fold_finish_kernel<<<bx, 128, 0, st>>>(A, S, len, world > 1 ? mine : all);
+    if (world > 1) {
+      int32_t rc = dist_allgather_device(ctx, mine, all, (size_t)len * sizeof(XYZZ));
+      if (rc) return rc;
+    }
+    fold_combine_kernel<<<bx, 128, 0, st>>>(all, (uint32_t)world, len, out);
+    ctx->launches += 4;
   }
   ZK_CUDA(ctx, cudaGetLastError());
   return ZK_OK;
@@ -183,6 +208,7 @@ int32_t fixed_base_build_inplace(zk_ctx* ctx, uint64_t total_main, uint64_t n_ex
   fb.lo = 0;
   fb.nmain = fb.total_main = total_main;
   fb.nextra = n_extra;
+  fb.split = false;  // every rank holds the whole table: results are complete, not partial sums
   fb.npoints = total_main + n_extra;
   fb.table = storage;
   XYZZ* t = (XYZZ*)tmp;

@@ -440,6 +440,7 @@ int32_t fixed_base_build(zk_ctx* ctx, const Affine* d_bases, uint64_t total_main
   fb.nmain = hi - fb.lo;
   fb.total_main = total_main;
   fb.nextra = ctx->dist_rank == 0 ? n_extra : 0;
+  fb.split = ctx->dist_world > 1;
   fb.npoints = fb.nmain + fb.nextra;
   const uint64_t npoints = fb.npoints;
   if ((uint64_t)fb.nwin * npoints >= 0x7fffffffull) return set_error(ctx, ZK_E_INVALID, "msm table too large");
@@ -599,7 +600,7 @@ int32_t msm_fixed_batch(zk_ctx* ctx, const FixedBase& fb, const MsmJob* jobs, in
     for (int d = 0; (1 << d) < SEG; d++) weighted = weighted.dbl();
     results[m] = sm[0].add(weighted);
   }
-  if (ctx->dist_world > 1) {
+  if (ctx->dist_world > 1 && fb.split) {
     int32_t drc = dist_sum_points(ctx, results, nb);
     if (drc) return drc;
   }

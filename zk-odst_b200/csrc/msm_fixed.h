@@ -12,6 +12,7 @@ struct FixedBase {
   uint64_t nmain = 0;       // main points held here: global indices [lo, lo + nmain)
   uint64_t total_main = 0;  // main points of the whole base; extras have global index >= total_main
   uint64_t nextra = 0;      // extra points (W, U) held here: all of them on rank 0, none elsewhere
+  bool split = false;       // built over this rank's range of a multi-GPU group: results are partial sums
   Affine* table = nullptr;  // [nwin][npoints]: table[w][i] = 2^(c w) * local point i
 };
 
@@ -23,7 +24,9 @@ int32_t fixed_base_build(zk_ctx* ctx, const Affine* d_bases, uint64_t total_main
                          FixedBase* out, int force_c = 0);
 // ipa_fold.cu: the IPA generators after r folds (needs a c = 8 table over all points), and a window
 // table built in caller-owned storage in a single launch
-size_t ipa_fold_workspace_bytes(uint64_t len);
+size_t ipa_fold_workspace_bytes(uint64_t len, int world);
+// fb8 may cover only this rank's range of the points (MSM split): the partial sums are exchanged with
+// one all-gather and added, so every rank ends with all folded generators
 int32_t ipa_fold_generators(zk_ctx* ctx, const FixedBase& fb8, const Fp* u, int r, void* workspace, Affine* out);
 int32_t fixed_base_build_inplace(zk_ctx* ctx, uint64_t total_main, uint64_t n_extra, int c, Affine* storage,
                                  void* tmp, FixedBase* out);

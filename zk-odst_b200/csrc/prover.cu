@@ -109,7 +109,7 @@ int32_t ensure_fold_workspace(zk_ctx* ctx, ProofWorkspace* W, uint64_t len) {
   if (W->fold_ws) return ZK_OK;
   const int nwin = (255 + IPA_STAGE2_C - 1) / IPA_STAGE2_C + ((255 % IPA_STAGE2_C) == 0 ? 1 : 0);
   const size_t pts = (size_t)nwin * (len + 2);
-  ZK_CUDA(ctx, cudaMalloc(&W->fold_ws, ipa_fold_workspace_bytes(len)));
+  ZK_CUDA(ctx, cudaMalloc(&W->fold_ws, ipa_fold_workspace_bytes(len, ctx->dist_world)));
   W->all.push_back(W->fold_ws);
   ZK_CUDA(ctx, cudaMalloc((void**)&W->h_table, pts * sizeof(Affine)));
   W->all.push_back(W->h_table);

@@ -158,7 +158,9 @@ int32_t install_params(zk_ctx* ctx, int k, Affine* g, Affine* g_lagrange, const 
   if (rc) return rc;
   rc = fixed_base_build(ctx, g_lagrange, n, 1, &S->params.fb_gl);
   if (rc) return rc;
-  if (ctx->dist_world == 1 && k >= 15) {
+  // 8-bit windows for the IPA generator fold (ipa_fold.cu); in a multi-GPU group the fold needs every
+  // rank's range to be a whole number of n / 2^r blocks
+  if (k >= 15 && (1 << IPA_FOLD_ROUNDS) % ctx->dist_world == 0) {
     rc = fixed_base_build(ctx, g, n, 2, &S->params.fb_g8, 8);
     if (rc) return rc;
   }
