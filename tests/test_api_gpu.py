@@ -1,0 +1,94 @@
+"""Error behaviour and threading of the C ABI on a device (every export returns a
+status, nothing unwinds, contexts are independent)."""
+import ctypes
+import threading
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_call_order_and_argument_errors(zk):
+    ctx = zk.Context(0)
+    seed = zk.REFERENCE_SEED
+    inputs = zk.synthetic_inputs(2)
+    for call in (lambda: ctx.keygen(12, 2), lambda: ctx.create_proof(inputs, 2, seed),
+                 lambda: ctx.verify_proof(b"\x00" * 4000), lambda: ctx.mock_verify(inputs, 2)):
+        with pytest.raises(zk.ZkError) as e:
+            call()
+        assert e.value.code == -6          # ZK_E_STATE: params / keys missing
+    ctx.params_generate_substitute(17, seed)
+    with pytest.raises(zk.ZkError) as e:
+        ctx.create_proof(inputs, 2, seed)
+    assert e.value.code == -6
+    with pytest.raises(zk.ZkError) as e:
+        ctx.keygen(12, 27)                  # 27 regions do not fit 2^17 rows
+    assert e.value.code == -4               # ZK_E_ROWS
+    ctx.keygen(12, 2)
+    with pytest.raises(zk.ZkError) as e:
+        ctx.create_proof(zk.synthetic_inputs(3), 3, seed)
+    assert e.value.code == -1               # batch size differs from keygen
+    with pytest.raises(zk.ZkError) as e:
+        ctx.dist_init(b"\x00" * 128, 0, 2)  # joining a group after params exist
+    assert e.value.code == -6
+    # proof buffer too small: required size reported, then the call succeeds
+    lib = ctx.lib
+    ln = ctypes.c_uint64(16)
+    small = ctypes.create_string_buffer(16)
+    rc = lib.zk_create_proof(ctx.h, inputs, 2, bytes(seed), ctypes.cast(small, ctypes.c_void_p), ctypes.byref(ln))
+    assert rc == -8 and ln.value == 4000
+    proof = ctx.create_proof(inputs, 2, seed)
+    assert len(proof) == 4000 and ctx.verify_proof(proof)
+    ctx.close()
+
+
+def test_bad_records_are_input_errors(zk):
+    import torch
+    ctx = zk.Context(0)
+    seed = zk.REFERENCE_SEED
+    ctx.params_generate_substitute(17, seed)
+    ctx.keygen(12, 2)
+    good = zk.synthetic_inputs(2)
+    bad = bytearray(good)
+    bad[212 + 213] = 2                      # final-block flag of the second record
+    with pytest.raises(zk.ZkError) as e:
+        ctx.create_proof(bytes(bad), 2, seed)
+    assert e.value.code == -5               # ZK_E_INPUT, checked on the host
+    d_bad = torch.frombuffer(bad, dtype=torch.uint8).cuda()
+    with pytest.raises(zk.ZkError) as e:
+        ctx.create_proof(d_bad, 2, seed, on_device=True)
+    assert e.value.code == -5               # ZK_E_INPUT, raised by the witness kernel
+    wrong_rounds = bytearray(good)
+    wrong_rounds[3] = 11
+    with pytest.raises(zk.ZkError) as e:
+        ctx.create_proof(bytes(wrong_rounds), 2, seed)
+    assert e.value.code == -5
+    assert ctx.verify_proof(ctx.create_proof(good, 2, seed))   # the context recovers
+    ctx.close()
+
+
+def test_contexts_are_independent_across_threads(zk):
+    """Four contexts on one device, four host threads (bench.py --streams): same bytes as alone."""
+    seed = zk.REFERENCE_SEED
+    inputs = zk.synthetic_inputs(3)
+    ctxs = [zk.Context(0) for _ in range(4)]
+    for c in ctxs:
+        c.params_generate_substitute(17, seed)
+        c.keygen(12, 3)
+    alone = ctxs[0].create_proof(inputs, 3, seed)
+    out = [[] for _ in ctxs]
+
+    def work(i):
+        if i % 2:
+            ctxs[i].set_blocking_sync(True)
+        for _ in range(3):
+            out[i].append(ctxs[i].create_proof(inputs, 3, seed))
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(len(ctxs))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert all(p == alone for o in out for p in o)
+    for c in ctxs:
+        c.close()

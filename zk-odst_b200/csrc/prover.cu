@@ -219,7 +219,7 @@ __global__ void lookup_compress_kernel(const Fp* __restrict__ c0, const Fp* __re
 // Ascending order of the 65536 compressed table rows (field `Ord` = canonical integer order).
 // The values are uniform, so a bucket by the top 14 bits of the canonical integer (< 2^254) holds
 // ~4 of them: histogram, scan, then each value ranks itself against its bucket with a full
-// 256-bit comparison.  Equal values raise status 3 (theta collision).
+// 256-bit comparison.  Equal values raise status bit 4 (theta collision).
 constexpr uint32_t RANK_BUCKETS = 1u << 14;
 __global__ void table_keys_kernel(const Fp* __restrict__ vals, uint64_t* __restrict__ keys,
                                   uint32_t* __restrict__ hist) {
@@ -261,7 +261,7 @@ __global__ void table_rank_kernel(const uint64_t* __restrict__ keys, const Fp* _
         less = a < mine[l];
       }
     }
-    if (equal) atomicExch(status, 3);
+    if (equal) atomicOr(status, 4);
     rank += less ? 1u : 0u;
   }
   rank_of[i] = rank;
@@ -275,7 +275,7 @@ __global__ void lookup_count_kernel(const Fp* __restrict__ dense_col, const Fp* 
   uint64_t d[4];
   dense_col[i].to_canonical(d);
   if ((d[1] | d[2] | d[3]) || d[0] >= 65536 || cin[i] != table_vals[d[0]]) {
-    atomicExch(status, 2);
+    atomicOr(status, 2);
     return;
   }
   atomicAdd(&counts[rank_of[d[0]]], 1u);
@@ -470,10 +470,11 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
     int status = 0;
     ZK_CUDA(ctx, cudaMemcpyAsync(&status, ctx->d_status, 4, cudaMemcpyDeviceToHost, st));
     ZK_CUDA(ctx, zk_stream_sync(ctx));
-    if (status) {
+    if (status) {  // bit 1: the witness kernel rejected a record; 2: lookup input not a table row; 4: collision
       cudaMemsetAsync(ctx->d_status, 0, 4, st);
-      return set_error(ctx, ZK_E_VERIFY, status == 3 ? "theta collision in the spread table"
-                                                     : "lookup input not in the spread table (ConstraintSystemFailure)");
+      if (status & 1) return set_error(ctx, ZK_E_INPUT, "EIP-152 record rejected (final flag or round count)");
+      return set_error(ctx, ZK_E_VERIFY, (status & 4) ? "theta collision in the spread table"
+                                                      : "lookup input not in the spread table (ConstraintSystemFailure)");
     }
     lookup_fill_table_kernel<<<blocks(usable), T, 0, st>>>(W->pin, first_flag, W->first_flag_scan, W->left_rank,
                                                            W->table_sorted, usable, n_repeated, W->ptab);

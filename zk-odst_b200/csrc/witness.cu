@@ -156,7 +156,7 @@ blake2f_witness_kernel(const uint8_t* __restrict__ inputs, uint32_t rounds, uint
     } else if (threadIdx.x == 34) {
       uint32_t rr = ((uint32_t)rec[0] << 24) | ((uint32_t)rec[1] << 16) | ((uint32_t)rec[2] << 8) |
                     rec[3];
-      if (rec[212] > 1 || rr != rounds) atomicExch(status, 1);
+      if (rec[212] > 1 || rr != rounds) atomicOr(status, 1);
       trace[TR_FMASK] = rec[212] == 1 ? ~0ull : 0ull;
     }
     __syncthreads();
