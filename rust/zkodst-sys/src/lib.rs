@@ -43,6 +43,10 @@ extern "C" {
         seed: *const u8, proof_out: *mut u8, proof_len: *mut u64) -> i32;
     pub fn zk_create_proof_device_inputs(ctx: *mut zk_ctx, d_inputs: *const u8, n_compressions: u64,
         seed: *const u8, proof_out: *mut u8, proof_len: *mut u64) -> i32;
+    pub fn zk_eip152_validate(input: *const u8, len: u64, rounds: *mut u32) -> i32;
+    pub fn zk_blake2f_compress(input: *const u8, out: *mut u8) -> i32;
+    pub fn zk_blake2b_records(msg: *const u8, len: u64, rounds: u32, records_out: *mut u8,
+        n_records: *mut u64, digest_out: *mut u8) -> i32;
     pub fn zk_verify_proof(ctx: *mut zk_ctx, proof: *const u8, proof_len: u64) -> i32;
     pub fn zk_mock_verify(ctx: *mut zk_ctx, inputs: *const u8, n_compressions: u64,
         advice_override: *const c_void, failure: *mut u64) -> i32;

@@ -1,1 +1,1 @@
-timeout 900 python -m pytest tests/test_api_gpu.py tests/test_hash_driver.py -x -q 2>&1 | tail -15
+timeout 300 python tools/profile_proof.py 19 64 5 2>&1 | tail -1

@@ -43,7 +43,7 @@ struct NttPassArgs {
   Fp cin1, cin2, cout1, cout2, scale;
 };
 
-__global__ void __launch_bounds__(256) ntt_pass_kernel(NttPassArgs a) {
+__global__ void __launch_bounds__(256, 5) ntt_pass_kernel(NttPassArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Fp* sm = reinterpret_cast<Fp*>(smem_raw);
   const int L = a.log_n, S = a.S, logW = a.logW, W = 1 << logW;
