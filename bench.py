@@ -121,8 +121,8 @@ def workload_config(k, n, split=False, world=1):
             "rows_per_compression": 292 + 392 * ROUNDS,
             "params": "substitute URS (zk_params_generate_substitute, reference seed)",
             "l2": "per proof the prover streams > 2 GB of column/coset data (advice cosets alone "
-                  "12 x 2^(k+2) x 32 B = %d MB), far above the 126 MB L2; no explicit flush" %
-                  (12 * (1 << (k + 2)) * 32 >> 20)}
+                  "12 x 3 x 2^k x 32 B = %d MB), far above the 126 MB L2; no explicit flush" %
+                  (12 * 3 * (1 << k) * 32 >> 20)}
 
 
 def run_reference(args, rank):
@@ -330,16 +330,19 @@ def main():
                           "terms the launches process: %.2f n full-width + 12 n advice" % full_terms,
         }
         ntt_ms, ntt_launches = per.get("ntt", (0.0, 0.0))
-        ext = 1 << (k + 2)
-        ntt_bytes = 19 * 64 * nrows + 20 * 64 * ext
-        ntt_mac = (19 * (nrows // 2) * k + 20 * (ext // 2) * (k + 2)) * MAC_PER_FP_MUL
+        # 19 inverse transforms to coefficients, 19 columns x 3 coset transforms, 3 inverse transforms of
+        # h's coset values: all of size n (the quotient lives on three cosets of the n-th roots)
+        ext = 3 * nrows
+        n_transforms = 19 + 19 * 3 + 3
+        ntt_bytes = n_transforms * 64 * nrows
+        ntt_mac = n_transforms * (nrows // 2) * k * MAC_PER_FP_MUL
         wit_ms, _ = per.get("witness", (0.0, 0.0))
         q_ms, _ = per.get("quotient", (0.0, 0.0))
         others = {
             "witness": {"bound": "hbm", "ms_per_proof": wit_ms,
                         "achieved_gbs": n * (R * 12 * 32 + 213) / (wit_ms * 1e-3) / 1e9 if wit_ms else None,
                         "peak_gbs": hbm_peak, "peak_source": hbm_kind},
-            "ntt": {"bound": "int_pipe", "ms_per_proof": ntt_ms, "transforms_per_proof": ntt_launches,
+            "ntt": {"bound": "int_pipe", "ms_per_proof": ntt_ms, "transforms_per_proof": n_transforms, "batched_calls_per_proof": ntt_launches,
                     "achieved_gbs": ntt_bytes / (ntt_ms * 1e-3) / 1e9 if ntt_ms else None,
                     "achieved_tmacs": ntt_mac / (ntt_ms * 1e-3) / 1e12 if ntt_ms else None},
             "quotient": {"bound": "int_pipe", "ms_per_proof": q_ms,

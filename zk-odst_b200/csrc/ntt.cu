@@ -8,8 +8,8 @@
 // a pass loads a tile of 2^S elements x W adjacent columns (W * 32 B contiguous per row), runs
 // S stages out of shared memory and stores the tile back, so a 2^21-point transform touches
 // HBM 3 times instead of 21.  The first pass fuses the bit-reversal gather, zero padding and
-// the coset scaling by zeta^i; the last pass fuses the 1/N scaling and the inverse coset
-// scaling.  Twiddles come from a per-domain table of N/2 powers.
+// an optional per-element input scaling (coset evaluation: c^i from a table); the last pass fuses the
+// 1/N scaling.  Several transforms of one size run as one batch of launches (blockIdx.y).  Twiddles come from a per-domain table of N/2 powers.
 //
 // Roofline: algorithmic bytes 64*N per transform; work (N/2) log2 N Fp multiplications
 // (~20 MAC/B at N = 2^19): integer-pipe bound; both fractions are reported.
@@ -31,16 +31,16 @@ struct NttPassArgs {
   const Fp* in;
   Fp* out;
   const Fp* tw;      // omega^i, i < N/2
+  const Fp* scale_in;  // first pass: optional per-element multiplier
+  size_t in_stride, out_stride, scale_stride;  // per transform of the batch (blockIdx.y)
   int log_n;         // L
   int s0;            // stages already done
   int S;             // stages in this pass
   int logW;          // log2 of adjacent columns per tile (0 for the first pass)
   uint32_t n_in;     // first pass: input length (zero padded above)
   int first, last;
-  int coset_in;      // multiply input i by cin[i % 3]
-  int coset_out;     // multiply output i by cout[i % 3] (after scale)
-  int scale_out;
-  Fp cin1, cin2, cout1, cout2, scale;
+  int scale_out;     // last pass: multiply by `scale` (1/N of the inverse transform)
+  Fp scale;
 };
 
 __global__ void __launch_bounds__(256, 5) ntt_pass_kernel(NttPassArgs a) {
@@ -52,6 +52,8 @@ __global__ void __launch_bounds__(256, 5) ntt_pass_kernel(NttPassArgs a) {
   const uint32_t lo_groups = (1u << a.s0) >> logW;  // number of W-wide lo groups (>= 1)
   const uint32_t tile = blockIdx.x;
   const uint32_t hi = tile / lo_groups, lo0 = (tile % lo_groups) << logW;
+  const Fp* const in = a.in + (a.first ? blockIdx.y * a.in_stride : blockIdx.y * a.out_stride);
+  Fp* const out = a.out + blockIdx.y * a.out_stride;
   // ---- load
   for (uint32_t e = threadIdx.x; e < tile_elems; e += blockDim.x) {
     uint32_t t = e >> logW, l = e & (W - 1);
@@ -60,17 +62,13 @@ __global__ void __launch_bounds__(256, 5) ntt_pass_kernel(NttPassArgs a) {
     if (a.first) {
       uint32_t src = bitrev(idx, L);
       if (src < a.n_in) {
-        v = a.in[src];
-        if (a.coset_in) {
-          uint32_t r = src % 3;
-          if (r == 1) v = v * a.cin1;
-          if (r == 2) v = v * a.cin2;
-        }
+        v = in[src];
+        if (a.scale_in) v = v * a.scale_in[blockIdx.y * a.scale_stride + src];
       } else {
         v = Fp::zero();
       }
     } else {
-      v = a.in[idx];
+      v = in[idx];
     }
     sm[e] = v;
   }
@@ -101,15 +99,8 @@ __global__ void __launch_bounds__(256, 5) ntt_pass_kernel(NttPassArgs a) {
     uint32_t t = e >> logW, l = e & (W - 1);
     uint32_t idx = (hi << (a.s0 + S)) | (t << a.s0) | (lo0 + l);
     Fp v = sm[e];
-    if (a.last) {
-      if (a.scale_out) v = v * a.scale;
-      if (a.coset_out) {
-        uint32_t r = idx % 3;
-        if (r == 1) v = v * a.cout1;
-        if (r == 2) v = v * a.cout2;
-      }
-    }
-    a.out[idx] = v;
+    if (a.last && a.scale_out) v = v * a.scale;
+    out[idx] = v;
   }
 }
 
@@ -147,6 +138,7 @@ int32_t ntt_run(zk_ctx* ctx, const Fp* in, uint32_t n_in, Fp* out, int log_n, co
   if (rc) return rc;
   const uint32_t N = 1u << log_n;
   const Fp* src = in;
+  if (in == out && opt.batch > 1) return set_error(ctx, ZK_E_INVALID, "ntt: batched transforms need distinct buffers");
   if (in == out) {  // bit-reversal gather cannot run in place
     rc = ensure_buf(ctx, ctx->ntt_tmp, (size_t)n_in * sizeof(Fp));
     if (rc) return rc;
@@ -180,18 +172,16 @@ int32_t ntt_run(zk_ctx* ctx, const Fp* in, uint32_t n_in, Fp* out, int log_n, co
     a.n_in = n_in;
     a.first = s0 == 0;
     a.last = s0 + S == log_n;
-    a.coset_in = opt.coset_in;
-    a.coset_out = opt.coset_out;
+    a.scale_in = opt.scale_in;
+    a.in_stride = opt.in_stride;
+    a.out_stride = opt.out_stride;
+    a.scale_stride = opt.scale_stride;
     a.scale_out = opt.inverse;
-    a.cin1 = opt.coset_in_pow[0];
-    a.cin2 = opt.coset_in_pow[1];
-    a.cout1 = opt.coset_out_pow[0];
-    a.cout2 = opt.coset_out_pow[1];
     a.scale = T->n_inv;
     uint32_t tile_elems = 1u << (S + logW);
     uint32_t tiles = N / tile_elems;
     size_t smem = (size_t)tile_elems * sizeof(Fp);
-    ntt_pass_kernel<<<tiles, tile_elems / 2, smem, ctx->stream>>>(a);
+    ntt_pass_kernel<<<dim3(tiles, (unsigned)opt.batch), tile_elems / 2, smem, ctx->stream>>>(a);
     ctx->launches++;
     s0 += S;
   }

@@ -586,8 +586,8 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
     if ((rc = coeff_to_extended(ctx, K, W->zl_poly, W->zl_coset))) return rc;
     if ((rc = coeff_to_extended(ctx, K, W->pin_poly, W->pin_coset))) return rc;
     if ((rc = coeff_to_extended(ctx, K, W->ptab_poly, W->ptab_coset))) return rc;
-    NttTables* TE = nullptr;
-    if ((rc = ntt_tables(ctx, K.ek, &TE))) return rc;
+    NttTables* TNq = nullptr;
+    if ((rc = ntt_tables(ctx, k, &TNq))) return rc;
     QuotientArgs qa;
     for (int c = 0; c < 12; c++) qa.advice[c] = adv_coset(c);
     for (int c = 0; c < NUM_FIXED; c++) qa.fixed[c] = K.fixed_cosets[c];
@@ -599,32 +599,49 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
     qa.l0 = K.l0;
     qa.l_last = K.l_last;
     qa.l_active = K.l_active;
-    qa.tw_ext = TE->tw_fwd;
+    qa.tw_n = TNq->tw_fwd;
     qa.h = W->h;
     for (int s = 0; s < NUM_SELECTORS; s++) qa.sel[s] = K.selectors[s];
     qa.theta = theta;
     qa.beta = beta;
     qa.gamma = gamma;
     qa.y = y;
-    qa.zeta = K.zeta;
+    for (int j = 0; j < NUM_COSETS; j++) {
+      qa.coset_gen[j] = K.coset_gen[j];
+      qa.t_inv[j] = K.t_inv[j];
+    }
     qa.delta_pow[0] = Fp::one();
     for (int i = 1; i < NUM_PERM; i++) qa.delta_pow[i] = qa.delta_pow[i - 1] * Fp::delta();
-    for (int i = 0; i < 4; i++) {
-      qa.t_inv[i] = K.t_inv[i];
-      qa.k.small[i] = Fp::from_u64(i);
-    }
+    for (int i = 0; i < 4; i++) qa.k.small[i] = Fp::from_u64(i);
     qa.ypow[NUM_GATE_POLYS - 1] = Fp::one();
     for (int e = NUM_GATE_POLYS - 2; e >= 0; e--) qa.ypow[e] = qa.ypow[e + 1] * y;
     qa.k.pow2[0] = Fp::one();
     for (int e = 1; e < 127; e++) qa.k.pow2[e] = qa.k.pow2[e - 1].dbl();
-    if ((rc = quotient_run(ctx, qa, en))) return rc;
-    // extended_to_coeff: inverse NTT, 1/en scaling, undo the coset, keep 3n coefficients
+    if ((rc = quotient_run(ctx, qa, n))) return rc;
+    // back to coefficients.  On coset j, h(c_j w^i) = sum_p (c_j^n)^p h_p(c_j w^i): the size-n inverse
+    // transform of the coset's values, unscaled by c_j^-i, is e_j = sum_p gamma_j^p h_p coefficient-wise,
+    // and the 3 x 3 Vandermonde system gives the three pieces h_p (K.h_solve = V^-1).
     NttOptions o;
     o.inverse = true;
-    o.coset_out = 1;
-    o.coset_out_pow[0] = K.zeta_sq;  // zeta^-1
-    o.coset_out_pow[1] = K.zeta;     // zeta^-2
-    if ((rc = ntt_run(ctx, W->h, (uint32_t)en, W->h_coeffs, K.ek, o))) return rc;
+    o.batch = NUM_COSETS;
+    o.in_stride = n;
+    o.out_stride = n;
+    if ((rc = ntt_run(ctx, W->h, (uint32_t)n, W->h_coeffs, k, o))) return rc;
+    {
+      Fp* hc = W->h_coeffs;
+      const Fp* un = K.coset_unscale;
+      Fp m[NUM_COSETS][NUM_COSETS];
+      for (int p = 0; p < NUM_COSETS; p++)
+        for (int j = 0; j < NUM_COSETS; j++) m[p][j] = K.h_solve[p][j];
+      const Fp m00 = m[0][0], m01 = m[0][1], m02 = m[0][2], m10 = m[1][0], m11 = m[1][1], m12 = m[1][2],
+               m20 = m[2][0], m21 = m[2][1], m22 = m[2][2];
+      launch_map(ctx, n, [=] __device__(uint64_t i) {
+        const Fp e0 = hc[i] * un[i], e1 = hc[n + i] * un[n + i], e2 = hc[2 * n + i] * un[2 * n + i];
+        hc[i] = m00 * e0 + m01 * e1 + m02 * e2;
+        hc[n + i] = m10 * e0 + m11 * e1 + m12 * e2;
+        hc[2 * n + i] = m20 * e0 + m21 * e1 + m22 * e2;
+      });
+    }
   }
   phase.mark("cosets + quotient + iNTT");
   Fp h_blinds[3];

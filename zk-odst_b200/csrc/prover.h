@@ -6,11 +6,15 @@
 namespace zkodst {
 
 struct NttOptions {
-  bool inverse = false;        // use omega^-1 and scale the output by 1/N
-  int coset_in = 0;            // multiply input i by coset_in_pow[(i % 3) - 1] before the transform
-  int coset_out = 0;           // multiply output i by coset_out_pow[(i % 3) - 1] after it
-  Fp coset_in_pow[2] = {Fp::zero(), Fp::zero()};
-  Fp coset_out_pow[2] = {Fp::zero(), Fp::zero()};
+  bool inverse = false;         // use omega^-1 and scale the output by 1/N
+  // Batched transforms: `batch` independent transforms in one sequence of launches (blockIdx.y);
+  // transform b reads in + b * in_stride (0: all read the same vector), writes out + b * out_stride.
+  int batch = 1;
+  size_t in_stride = 0, out_stride = 0;
+  // Optional per-element input scaling: input element i of transform b is multiplied by
+  // scale_in[b * scale_stride + i] while it is loaded (coset evaluation: scale_in[i] = c^i).
+  const Fp* scale_in = nullptr;
+  size_t scale_stride = 0;
 };
 
 // ntt.cu

@@ -17,6 +17,7 @@ constexpr int NUM_PERM = 8;     // equality-enabled columns a_1..a_8 (table16.rs
 constexpr int NUM_SETS = 4;     // permutation grand products: chunks of degree - 2 = 2 columns
 constexpr int BLINDING = 5;     // ConstraintSystem::blinding_factors() for this circuit
 constexpr int CS_DEGREE = 4;
+constexpr int NUM_COSETS = 3;        // quotient degree: h = h_0 + X^n h_1 + X^2n h_2
 constexpr int IPA_FOLD_ROUNDS = 5;   // IPA rounds on the original generators before they are folded once
 constexpr int IPA_STAGE2_C = 12;     // window bits of the table over the folded generators
 
@@ -43,8 +44,8 @@ struct DeviceParams {
 };
 
 struct DeviceKeys {
-  int k = 0, ek = 0;
-  uint64_t n = 0, en = 0;
+  int k = 0;
+  uint64_t n = 0, en = 0;   // en = NUM_COSETS * n: the quotient is evaluated on three cosets of the n-th roots
   uint32_t rounds = 0;
   uint64_t n_compressions = 0, region_rows = 0;
   SelectorExpr selectors[NUM_SELECTORS];
@@ -57,8 +58,13 @@ struct DeviceKeys {
   Fp *l0 = nullptr, *l_last = nullptr, *l_active = nullptr;  // extended cosets
   std::vector<Affine> fixed_commitments, sigma_commitments;
   Fp transcript_repr;
-  Fp t_inv[4];  // 1 / (X^n - 1) on the extended coset, period 4
-  Fp zeta, zeta_sq;
+  // Quotient domain: h has degree < 3n, so three cosets c_j <omega_n> (c_j = zeta omega_4n^j, j = 0..2:
+  // three of the four cosets halo2's extended domain consists of) determine it; stored coset-major.
+  Fp coset_gen[NUM_COSETS];     // c_j
+  Fp t_inv[NUM_COSETS];         // 1 / (c_j^n - 1): X^n - 1 is constant on a coset
+  Fp h_solve[NUM_COSETS][NUM_COSETS];  // inverse of V[j][p] = (c_j^n)^p: coset coefficient vectors -> h pieces
+  Fp* coset_scale = nullptr;    // [NUM_COSETS][n]: c_j^i
+  Fp* coset_unscale = nullptr;  // [NUM_COSETS][n]: c_j^-i
   void* workspace = nullptr;  // ProofWorkspace (prover.cu), allocated lazily
 };
 
@@ -77,7 +83,7 @@ int32_t commit(zk_ctx* ctx, const Fp* d_scalars, const FixedBase& fb, uint64_t n
 // the same for nb columns over one base in a single MSM pipeline (nb <= MSM_MAX_BATCH)
 int32_t commit_batch(zk_ctx* ctx, const Fp* const* d_scalars, const FixedBase& fb, uint64_t n, const Fp* blinds,
                      int nb, Affine* out);
-// coefficients (n) -> evaluations on the extended coset zeta * <omega_ext> (en)
+// coefficients (n) -> evaluations on the three cosets c_j <omega_n>, coset-major (en = 3n)
 int32_t coeff_to_extended(zk_ctx* ctx, const DeviceKeys& K, const Fp* coeffs, Fp* out);
 
 }  // namespace zkodst

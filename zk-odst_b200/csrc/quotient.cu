@@ -1,4 +1,4 @@
-// K6 — fused quotient evaluation h(X) on the extended coset.
+// K6 — fused quotient evaluation h(X) on three cosets of the n-th roots of unity.
 //
 // Replaces the `poly::Evaluator` AST walk and `divide_by_vanishing_poly` of halo2_proofs 0.3.0
 // (`vanishing::Argument::construct`, reached from `create_proof`,
@@ -6,7 +6,8 @@
 // row, the 23 custom-gate polynomials of docs/CIRCUIT.md (gate names and order follow
 // compression.rs:605-1056 / compression_gate.rs), the 9 permutation-argument terms and the 5
 // lookup-argument terms, folds them with Horner in y in halo2's order, and multiplies by
-// 1 / (X^n - 1) (four distinct values on the coset).
+// 1 / (X^n - 1), which is constant on a coset.  halo2 evaluates on all four cosets of its extended
+// domain (4n points); h has degree < 3n, so three of them (3n points) determine the same h.
 //
 // Roofline: ~60 coset values read per row (32 B each, rotations hit L2) and ~200 Fp
 // multiplications per row: integer-pipe bound; both fractions are reported by bench.py.
@@ -36,10 +37,11 @@ constexpr int Q_MINB = 4;
 // regrouped by expression — gates that share a polynomial (a1/a2, c1/c2, d1/d2) share its evaluation —
 // and every cell and selector is fetched where it is used, which keeps the live set small.  The order
 // of evaluation does not matter: field arithmetic is exact, the value equals fold_gates (gates.cuh).
-__global__ void __launch_bounds__(128, Q_MINB) quotient_gates_kernel(const __grid_constant__ QuotientArgs qa, uint64_t en, uint64_t mask) {
+__global__ void __launch_bounds__(128, Q_MINB) quotient_gates_kernel(const __grid_constant__ QuotientArgs qa, uint64_t n, uint64_t mask) {
   const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i >= en) return;
-  const uint64_t ip = (i - 4) & mask, in = (i + 4) & mask;  // rotation by one row = 4 steps
+  if (i >= NUM_COSETS * n) return;
+  const uint64_t row = i & mask, base = i - row;  // coset-major: i = coset * n + row
+  const uint64_t ip = base + ((row - 1) & mask), in = base + ((row + 1) & mask);  // rotations stay in the coset
   // advice by a-number: a0..a9 -> halo2 columns 7,8,9,1,2,0,3,4,5,6
   const Fp* const A0 = qa.advice[7];
   const Fp* const A1 = qa.advice[8];
@@ -113,14 +115,15 @@ __global__ void __launch_bounds__(128, Q_MINB) quotient_gates_kernel(const __gri
 }
 
 // part 2: the permutation argument (columns in enable_equality order: a1,a2 | a3,a4 | a5,a6 | a7,a8)
-__global__ void __launch_bounds__(128, Q_MINB) quotient_perm_kernel(const __grid_constant__ QuotientArgs qa, uint64_t en, uint64_t mask) {
+__global__ void __launch_bounds__(128, Q_MINB) quotient_perm_kernel(const __grid_constant__ QuotientArgs qa, uint64_t n, uint64_t mask) {
   const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i >= en) return;
-  const uint64_t in = (i + 4) & mask;
+  if (i >= NUM_COSETS * n) return;
+  const uint64_t row = i & mask, base = i - row;  // coset-major: i = coset * n + row
+  const uint64_t in = base + ((row + 1) & mask);
   const Fp one = Fp::one();
   Horner H{qa.h[i], qa.y};
   const Fp l0 = qa.l0[i], l_last = qa.l_last[i], l_active = qa.l_active[i];
-  const uint64_t ilast = (i - 4 * (BLINDING + 1)) & mask;
+  const uint64_t ilast = base + ((row - (BLINDING + 1)) & mask);
   Fp z[NUM_SETS];
 #pragma unroll
   for (int s = 0; s < NUM_SETS; s++) z[s] = qa.perm_z[s][i];
@@ -128,10 +131,11 @@ __global__ void __launch_bounds__(128, Q_MINB) quotient_perm_kernel(const __grid
   H.fold((z[NUM_SETS - 1] * z[NUM_SETS - 1] - z[NUM_SETS - 1]) * l_last);
 #pragma unroll
   for (int s = 1; s < NUM_SETS; s++) H.fold((z[s] - qa.perm_z[s - 1][ilast]) * l0);
-  // coset point X = zeta * omega_ext^i
-  const uint64_t half = en >> 1;
-  const Fp w = i < half ? qa.tw_ext[i] : qa.tw_ext[i - half].neg();
-  const Fp bx = qa.beta * qa.zeta * w;
+  // point of this row: X = c_coset * omega_n^row
+  const uint32_t coset = (uint32_t)(base / n);
+  const uint64_t half = n >> 1;
+  const Fp w = row < half ? qa.tw_n[row] : qa.tw_n[row - half].neg();
+  const Fp bx = qa.beta * qa.coset_gen[coset] * w;
 #pragma unroll
   for (int s = 0; s < NUM_SETS; s++) {
     Fp left = qa.perm_z[s][in];
@@ -149,10 +153,11 @@ __global__ void __launch_bounds__(128, Q_MINB) quotient_perm_kernel(const __grid
 }
 
 // part 3: the lookup argument, then the division by X^n - 1
-__global__ void __launch_bounds__(128, Q_MINB) quotient_lookup_kernel(const __grid_constant__ QuotientArgs qa, uint64_t en, uint64_t mask) {
+__global__ void __launch_bounds__(128, Q_MINB) quotient_lookup_kernel(const __grid_constant__ QuotientArgs qa, uint64_t n, uint64_t mask) {
   const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i >= en) return;
-  const uint64_t ip = (i - 4) & mask, in = (i + 4) & mask;
+  if (i >= NUM_COSETS * n) return;
+  const uint64_t row = i & mask, base = i - row;  // coset-major: i = coset * n + row
+  const uint64_t ip = base + ((row - 1) & mask), in = base + ((row + 1) & mask);
   const Fp one = Fp::one();
   Horner H{qa.h[i], qa.y};
   const Fp l0 = qa.l0[i], l_last = qa.l_last[i], l_active = qa.l_active[i];
@@ -165,17 +170,17 @@ __global__ void __launch_bounds__(128, Q_MINB) quotient_lookup_kernel(const __gr
   H.fold((zl_next * (pin + qa.beta) * (ptab + qa.gamma) - zl * (cin + qa.beta) * (ctab + qa.gamma)) * l_active);
   H.fold((pin - ptab) * l0);
   H.fold((pin - ptab) * (pin - pin_prev) * l_active);
-  qa.h[i] = H.h * qa.t_inv[i & 3];
+  qa.h[i] = H.h * qa.t_inv[base / n];
 }
 
 }  // namespace
 
-int32_t quotient_run(zk_ctx* ctx, const QuotientArgs& args, uint64_t en) {
+int32_t quotient_run(zk_ctx* ctx, const QuotientArgs& args, uint64_t n) {
   KernelTimer timer(ctx, KC_QUOTIENT);
-  const unsigned grid = (unsigned)((en + 127) / 128);
-  quotient_gates_kernel<<<grid, 128, 0, ctx->stream>>>(args, en, en - 1);
-  quotient_perm_kernel<<<grid, 128, 0, ctx->stream>>>(args, en, en - 1);
-  quotient_lookup_kernel<<<grid, 128, 0, ctx->stream>>>(args, en, en - 1);
+  const unsigned grid = (unsigned)((NUM_COSETS * n + 127) / 128);
+  quotient_gates_kernel<<<grid, 128, 0, ctx->stream>>>(args, n, n - 1);
+  quotient_perm_kernel<<<grid, 128, 0, ctx->stream>>>(args, n, n - 1);
+  quotient_lookup_kernel<<<grid, 128, 0, ctx->stream>>>(args, n, n - 1);
   ctx->launches += 3;
   ZK_CUDA(ctx, cudaGetLastError());
   return ZK_OK;

@@ -12,16 +12,18 @@ struct QuotientArgs {
   const Fp* perm_z[NUM_SETS];
   const Fp *lookup_z, *lookup_in, *lookup_tab;
   const Fp *l0, *l_last, *l_active;
-  const Fp* tw_ext;  // omega_ext^i, i < en / 2
+  const Fp* tw_n;    // omega_n^i, i < n / 2
   Fp* h;
   SelectorExpr sel[NUM_SELECTORS];
-  Fp theta, beta, gamma, y, zeta;
+  Fp theta, beta, gamma, y;
+  Fp coset_gen[NUM_COSETS];  // c_j: the point of extended row (j, i) is c_j omega_n^i
   Fp delta_pow[NUM_PERM];
-  Fp t_inv[4];
+  Fp t_inv[NUM_COSETS];
   GateConsts k;    // small integers and powers of two
   Fp ypow[NUM_GATE_POLYS];  // ypow[k] = y^(NUM_GATE_POLYS - 1 - k)
 };
 
-int32_t quotient_run(zk_ctx* ctx, const QuotientArgs& args, uint64_t en);
+// evaluates h on the NUM_COSETS cosets (coset-major arrays of NUM_COSETS * n elements)
+int32_t quotient_run(zk_ctx* ctx, const QuotientArgs& args, uint64_t n);
 
 }  // namespace zkodst

@@ -54,6 +54,8 @@ void free_keys(DeviceKeys& K) {
   cudaFree(K.l0);
   cudaFree(K.l_last);
   cudaFree(K.l_active);
+  cudaFree(K.coset_scale);
+  cudaFree(K.coset_unscale);
   if (K.workspace) free_workspace(K.workspace);
   K = DeviceKeys();
 }
@@ -198,11 +200,14 @@ int32_t commit_batch(zk_ctx* ctx, const Fp* const* d_scalars, const FixedBase& f
 }
 
 int32_t coeff_to_extended(zk_ctx* ctx, const DeviceKeys& K, const Fp* coeffs, Fp* out) {
+  // three size-n transforms of the coefficients scaled by c_j^i, in one batch of launches
   NttOptions opt;
-  opt.coset_in = 1;
-  opt.coset_in_pow[0] = K.zeta;
-  opt.coset_in_pow[1] = K.zeta_sq;
-  return ntt_run(ctx, coeffs, (uint32_t)K.n, out, K.ek, opt);
+  opt.batch = NUM_COSETS;
+  opt.in_stride = 0;
+  opt.out_stride = K.n;
+  opt.scale_in = K.coset_scale;
+  opt.scale_stride = K.n;
+  return ntt_run(ctx, coeffs, (uint32_t)K.n, out, K.k, opt);
 }
 
 }  // namespace zkodst
@@ -520,22 +525,45 @@ extern "C" int32_t zk_blake2f_keygen(zk_ctx* ctx, uint32_t rounds, uint64_t n_co
   if ((unsigned __int128)L.rows * n_compressions > n - (BLINDING + 1))
     return set_error(ctx, ZK_E_ROWS, "compressions do not fit in 2^k rows");
   K.k = k;
-  K.ek = k + 2;  // degree 4 => quotient degree 3 => extended domain 4n
   K.n = n;
-  K.en = n << 2;
+  K.en = NUM_COSETS * n;
   K.rounds = rounds;
   K.n_compressions = n_compressions;
   K.region_rows = L.rows;
-  K.zeta = Fp::zeta();
-  K.zeta_sq = K.zeta.sqr();
   {
-    NttTables* TE = nullptr;
-    if ((rc = ntt_tables(ctx, K.ek, &TE))) return rc;
-    Fp orig = K.zeta.pow_u64(n), step = TE->omega.pow_u64(n), cur = orig;
-    for (int i = 0; i < 4; i++) {
-      K.t_inv[i] = (cur - Fp::one()).inv();
-      cur = cur * step;
+    // c_j = zeta * omega_4n^j (the first three cosets of halo2's extended domain, degree 4 => 4n)
+    Fp omega_ext = Fp::root_of_unity();
+    for (int i = k + 2; i < 32; i++) omega_ext = omega_ext.sqr();
+    Fp gamma[NUM_COSETS];
+    Fp c = Fp::zeta();
+    cudaFree(K.coset_scale);
+    cudaFree(K.coset_unscale);
+    ZK_CUDA(ctx, cudaMalloc((void**)&K.coset_scale, (size_t)NUM_COSETS * n * sizeof(Fp)));
+    ZK_CUDA(ctx, cudaMalloc((void**)&K.coset_unscale, (size_t)NUM_COSETS * n * sizeof(Fp)));
+    for (int j = 0; j < NUM_COSETS; j++) {
+      K.coset_gen[j] = c;
+      gamma[j] = c.pow_u64(n);
+      K.t_inv[j] = (gamma[j] - Fp::one()).inv();
+      if ((rc = affine_scan(ctx, nullptr, c, nullptr, n, Fp::one(), K.coset_scale + (size_t)j * n))) return rc;
+      if ((rc = affine_scan(ctx, nullptr, c.inv(), nullptr, n, Fp::one(), K.coset_unscale + (size_t)j * n))) return rc;
+      c = c * omega_ext;
     }
+    // inverse of the Vandermonde matrix V[j][p] = gamma_j^p (3 x 3, by cofactors)
+    Fp V[3][3], cof[3][3];
+    for (int j = 0; j < 3; j++) {
+      V[j][0] = Fp::one();
+      V[j][1] = gamma[j];
+      V[j][2] = gamma[j].sqr();
+    }
+    for (int r = 0; r < 3; r++)
+      for (int q = 0; q < 3; q++) {
+        const int r1 = (r + 1) % 3, r2 = (r + 2) % 3, q1 = (q + 1) % 3, q2 = (q + 2) % 3;
+        cof[r][q] = V[r1][q1] * V[r2][q2] - V[r1][q2] * V[r2][q1];  // cyclic indexing: sign included
+      }
+    const Fp det = V[0][0] * cof[0][0] + V[0][1] * cof[0][1] + V[0][2] * cof[0][2];
+    const Fp det_inv = det.inv();
+    for (int p = 0; p < 3; p++)
+      for (int j = 0; j < 3; j++) K.h_solve[p][j] = cof[j][p] * det_inv;  // inverse = adjugate^T / det
   }
   // selectors -> fixed columns
   int n_sel_cols = 0;
