@@ -296,6 +296,22 @@ def main():
     e2e_val = jobs * n / (e2e_ms * 1e-3)
     assert all(p == proof for p in proofs_e2e), "host-input and device-input proofs differ"
 
+    # ---- the other two calls of the reference's sequence, for the record (one context, rank 0) -----
+    verify_ms = mock_ms = None
+    if rank == 0 and not split:
+        assert ctx.verify_proof(proof), ctx.last_error()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            ok = ctx.verify_proof(proof)
+        verify_ms = (time.perf_counter() - t0) / 5 * 1e3
+        assert ok
+        assert ctx.mock_verify(inputs, n) is None
+        t0 = time.perf_counter()
+        for _ in range(5):
+            ctx.mock_verify(inputs, n)
+        mock_ms = (time.perf_counter() - t0) / 5 * 1e3
+    barrier()
+
     if rank == 0:
         hbm_peak, hbm_kind = load_peaks()
         int_peak = ctx.bench_int_pipe(1, 20000)  # mad.wide.u32 instructions/s = 32x32->64 MAC/s
@@ -366,6 +382,7 @@ def main():
                             "device (XorShift jump-ahead), challenges/commitments move as <1 KB "
                             "transcript round trips inside the call"},
             "gpu_launches": int(launches), "roofline": roofline, "kernels": others,
+            "verify_proof_ms": verify_ms, "mock_verify_ms": mock_ms,
         }
         if not args.no_cpu_baseline:
             op, cin, cseed = cpu_oracle_setup()
