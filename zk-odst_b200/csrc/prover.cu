@@ -25,8 +25,13 @@ struct ProofWorkspace {
   uint8_t* inputs = nullptr;
   uint64_t* digests = nullptr;
   Fp* advice_values = nullptr;  // [12][n]
-  Fp* advice_polys = nullptr;   // [12][n]
-  Fp* advice_cosets = nullptr;  // [12][en]
+  // The 19 witness polynomials live in two slot arrays (coefficients, coset values) so that a multi-GPU
+  // group can all-gather them in place: slots 0..11 advice, 12 permuted input, 13 permuted table,
+  // 14..17 permutation products, 18 lookup product (padded to a multiple of the group size).
+  Fp* polys_all = nullptr;      // [slots][n]
+  Fp* cosets_all = nullptr;     // [slots][en]
+  Fp* advice_polys = nullptr;   // = polys_all   ([12][n])
+  Fp* advice_cosets = nullptr;  // = cosets_all  ([12][en])
   Fp *cin = nullptr, *ctab = nullptr, *pin = nullptr, *ptab = nullptr;  // lookup, n each
   Fp *pin_poly = nullptr, *ptab_poly = nullptr, *zl_poly = nullptr;
   Fp *pin_coset = nullptr, *ptab_coset = nullptr, *zl_coset = nullptr;
@@ -55,6 +60,11 @@ struct ProofWorkspace {
   std::vector<void*> all;
 };
 
+constexpr int SLOT_PIN = 12, SLOT_PTAB = 13, SLOT_Z0 = 14, SLOT_ZL = 18, NUM_WITNESS_POLYS = 19;
+// slots per rank when the transforms are sharded by column over `world` ranks
+static inline uint64_t witness_slots_per_rank(int world) { return (NUM_WITNESS_POLYS + world - 1) / world; }
+static inline uint64_t witness_slots_padded(int world) { return witness_slots_per_rank(world) * world; }
+
 void free_workspace(void* p) {
   ProofWorkspace* W = (ProofWorkspace*)p;
   for (void* q : W->all) cudaFree(q);
@@ -82,15 +92,22 @@ int32_t get_workspace(zk_ctx* ctx, DeviceKeys& K, ProofWorkspace** out) {
     A(inputs, K.n_compressions * 213 + 16);
     A(digests, K.n_compressions * 8 + 8);
     A(advice_values, 12 * n);
-    A(advice_polys, 12 * n);
-    A(advice_cosets, 12 * en);
-    A(cin, n); A(ctab, n); A(pin, n); A(ptab, n);
-    A(pin_poly, n); A(ptab_poly, n); A(zl_poly, n);
-    A(pin_coset, en); A(ptab_coset, en); A(zl_coset, en);
+    const uint64_t slots = witness_slots_padded(ctx->dist_world);
+    A(polys_all, slots * n);
+    A(cosets_all, slots * en);
+    W->advice_polys = W->polys_all;
+    W->advice_cosets = W->cosets_all;
+    W->pin_poly = W->polys_all + SLOT_PIN * n;
+    W->ptab_poly = W->polys_all + SLOT_PTAB * n;
+    W->zl_poly = W->polys_all + SLOT_ZL * n;
+    W->pin_coset = W->cosets_all + SLOT_PIN * en;
+    W->ptab_coset = W->cosets_all + SLOT_PTAB * en;
+    W->zl_coset = W->cosets_all + SLOT_ZL * en;
     for (int s = 0; s < NUM_SETS; s++) {
-      A(z_poly[s], n);
-      A(z_coset[s], en);
+      W->z_poly[s] = W->polys_all + (SLOT_Z0 + s) * n;
+      W->z_coset[s] = W->cosets_all + (SLOT_Z0 + s) * en;
     }
+    A(cin, n); A(ctab, n); A(pin, n); A(ptab, n);
     for (int s = 0; s <= NUM_SETS; s++) A(z_vals[s], n);
     A(tmp_a, n); A(tmp_b, n); A(tmp_c, n);
     A(h, en); A(h_coeffs, en);
@@ -424,9 +441,6 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
     if ((rc = commit_batch(ctx, cols, P.fb_gl, n, advice_blinds, 12, cms))) return rc;
     for (int c = 0; c < 12; c++) tr.write_point(cms[c]);
   }
-  for (int c = 0; c < 12; c++)
-    if ((rc = ntt_run(ctx, adv(c), (uint32_t)n, adv_poly(c), k, inv))) return rc;
-
   const Fp theta = tr.squeeze_challenge();
 
   phase.mark("advice commit + iNTT");
@@ -492,8 +506,6 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
     if ((rc = commit_batch(ctx, cols, P.fb_gl, n, blinds, 2, cms))) return rc;
     tr.write_point(cms[0]);
     tr.write_point(cms[1]);
-    if ((rc = ntt_run(ctx, W->pin, (uint32_t)n, W->pin_poly, k, inv))) return rc;
-    if ((rc = ntt_run(ctx, W->ptab, (uint32_t)n, W->ptab_poly, k, inv))) return rc;
   }
 
   const Fp beta = tr.squeeze_challenge();
@@ -561,9 +573,6 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
     blinds[NUM_SETS] = zl_blind;
     if ((rc = commit_batch(ctx, cols, P.fb_gl, n, blinds, NUM_SETS + 1, cms))) return rc;
     for (int s = 0; s <= NUM_SETS; s++) tr.write_point(cms[s]);
-    for (int s = 0; s < NUM_SETS; s++)
-      if ((rc = ntt_run(ctx, W->z_vals[s], (uint32_t)n, W->z_poly[s], k, inv))) return rc;
-    if ((rc = ntt_run(ctx, z, (uint32_t)n, W->zl_poly, k, inv))) return rc;
   }
   phase.mark("lookup product");
   // ---- vanishing argument: random polynomial ----------------------------------------------------------------
@@ -579,13 +588,28 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
   phase.mark("random poly commit");
   // ---- quotient (K5 + K6) ---------------------------------------------------------------------------------------
   {
-    for (int c = 0; c < 12; c++)
-      if ((rc = coeff_to_extended(ctx, K, adv_poly(c), adv_coset(c)))) return rc;
-    for (int s = 0; s < NUM_SETS; s++)
-      if ((rc = coeff_to_extended(ctx, K, W->z_poly[s], W->z_coset[s]))) return rc;
-    if ((rc = coeff_to_extended(ctx, K, W->zl_poly, W->zl_coset))) return rc;
-    if ((rc = coeff_to_extended(ctx, K, W->pin_poly, W->pin_coset))) return rc;
-    if ((rc = coeff_to_extended(ctx, K, W->ptab_poly, W->ptab_coset))) return rc;
+    // The 19 witness columns go to coefficients and to the three cosets here, after the last of them is
+    // committed (neither form is needed earlier).  Transforms shard by column: in a
+    // group every rank transforms its own block of slots and the two slot arrays are all-gathered in
+    // place; the column values themselves are already replicated.
+    const int world = ctx->dist_world;
+    const uint64_t spr = witness_slots_per_rank(world);
+    const uint64_t slot_lo = spr * (uint64_t)ctx->dist_rank;
+    const uint64_t slot_hi = std::min<uint64_t>(slot_lo + spr, NUM_WITNESS_POLYS);
+    for (uint64_t slot = slot_lo; slot < slot_hi; slot++) {
+      const Fp* vals = slot < 12          ? adv((int)slot)
+                       : slot == SLOT_PIN  ? W->pin
+                       : slot == SLOT_PTAB ? W->ptab
+                                           : W->z_vals[slot - SLOT_Z0];
+      Fp* poly = W->polys_all + slot * n;
+      if ((rc = ntt_run(ctx, vals, (uint32_t)n, poly, k, inv))) return rc;
+      if ((rc = coeff_to_extended(ctx, K, poly, W->cosets_all + slot * en))) return rc;
+    }
+    if (world > 1) {
+      if ((rc = dist_allgather_device(ctx, W->polys_all + slot_lo * n, W->polys_all, spr * n * sizeof(Fp)))) return rc;
+      if ((rc = dist_allgather_device(ctx, W->cosets_all + slot_lo * en, W->cosets_all, spr * en * sizeof(Fp))))
+        return rc;
+    }
     NttTables* TNq = nullptr;
     if ((rc = ntt_tables(ctx, k, &TNq))) return rc;
     QuotientArgs qa;
@@ -617,7 +641,15 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
     for (int e = NUM_GATE_POLYS - 2; e >= 0; e--) qa.ypow[e] = qa.ypow[e + 1] * y;
     qa.k.pow2[0] = Fp::one();
     for (int e = 1; e < 127; e++) qa.k.pow2[e] = qa.k.pow2[e - 1].dbl();
-    if ((rc = quotient_run(ctx, qa, n))) return rc;
+    // rows shard too: every rank now holds all coset columns, evaluates its own range of the 3n rows and
+    // the ranges of h are all-gathered in place
+    if (world > 1 && en % (uint64_t)world == 0) {
+      const uint64_t rows = en / (uint64_t)world, row_lo = rows * (uint64_t)ctx->dist_rank;
+      if ((rc = quotient_run(ctx, qa, n, row_lo, row_lo + rows))) return rc;
+      if ((rc = dist_allgather_device(ctx, W->h + row_lo, W->h, rows * sizeof(Fp)))) return rc;
+    } else {
+      if ((rc = quotient_run(ctx, qa, n, 0, en))) return rc;
+    }
     // back to coefficients.  On coset j, h(c_j w^i) = sum_p (c_j^n)^p h_p(c_j w^i): the size-n inverse
     // transform of the coset's values, unscaled by c_j^-i, is e_j = sum_p gamma_j^p h_p coefficient-wise,
     // and the 3 x 3 Vandermonde system gives the three pieces h_p (K.h_solve = V^-1).

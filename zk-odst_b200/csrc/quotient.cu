@@ -37,9 +37,9 @@ constexpr int Q_MINB = 4;
 // regrouped by expression — gates that share a polynomial (a1/a2, c1/c2, d1/d2) share its evaluation —
 // and every cell and selector is fetched where it is used, which keeps the live set small.  The order
 // of evaluation does not matter: field arithmetic is exact, the value equals fold_gates (gates.cuh).
-__global__ void __launch_bounds__(128, Q_MINB) quotient_gates_kernel(const __grid_constant__ QuotientArgs qa, uint64_t n, uint64_t mask) {
-  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i >= NUM_COSETS * n) return;
+__global__ void __launch_bounds__(128, Q_MINB) quotient_gates_kernel(const __grid_constant__ QuotientArgs qa, uint64_t n, uint64_t mask, uint64_t lo, uint64_t hi) {
+  const uint64_t i = lo + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= hi) return;
   const uint64_t row = i & mask, base = i - row;  // coset-major: i = coset * n + row
   const uint64_t ip = base + ((row - 1) & mask), in = base + ((row + 1) & mask);  // rotations stay in the coset
   // advice by a-number: a0..a9 -> halo2 columns 7,8,9,1,2,0,3,4,5,6
@@ -115,9 +115,9 @@ __global__ void __launch_bounds__(128, Q_MINB) quotient_gates_kernel(const __gri
 }
 
 // part 2: the permutation argument (columns in enable_equality order: a1,a2 | a3,a4 | a5,a6 | a7,a8)
-__global__ void __launch_bounds__(128, Q_MINB) quotient_perm_kernel(const __grid_constant__ QuotientArgs qa, uint64_t n, uint64_t mask) {
-  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i >= NUM_COSETS * n) return;
+__global__ void __launch_bounds__(128, Q_MINB) quotient_perm_kernel(const __grid_constant__ QuotientArgs qa, uint64_t n, uint64_t mask, uint64_t lo, uint64_t hi) {
+  const uint64_t i = lo + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= hi) return;
   const uint64_t row = i & mask, base = i - row;  // coset-major: i = coset * n + row
   const uint64_t in = base + ((row + 1) & mask);
   const Fp one = Fp::one();
@@ -153,9 +153,9 @@ __global__ void __launch_bounds__(128, Q_MINB) quotient_perm_kernel(const __grid
 }
 
 // part 3: the lookup argument, then the division by X^n - 1
-__global__ void __launch_bounds__(128, Q_MINB) quotient_lookup_kernel(const __grid_constant__ QuotientArgs qa, uint64_t n, uint64_t mask) {
-  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i >= NUM_COSETS * n) return;
+__global__ void __launch_bounds__(128, Q_MINB) quotient_lookup_kernel(const __grid_constant__ QuotientArgs qa, uint64_t n, uint64_t mask, uint64_t lo, uint64_t hi) {
+  const uint64_t i = lo + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= hi) return;
   const uint64_t row = i & mask, base = i - row;  // coset-major: i = coset * n + row
   const uint64_t ip = base + ((row - 1) & mask), in = base + ((row + 1) & mask);
   const Fp one = Fp::one();
@@ -175,12 +175,14 @@ __global__ void __launch_bounds__(128, Q_MINB) quotient_lookup_kernel(const __gr
 
 }  // namespace
 
-int32_t quotient_run(zk_ctx* ctx, const QuotientArgs& args, uint64_t n) {
+int32_t quotient_run(zk_ctx* ctx, const QuotientArgs& args, uint64_t n, uint64_t lo, uint64_t hi) {
+  if (lo > hi || hi > NUM_COSETS * n) return set_error(ctx, ZK_E_INVALID, "quotient row range");
+  if (lo == hi) return ZK_OK;
   KernelTimer timer(ctx, KC_QUOTIENT);
-  const unsigned grid = (unsigned)((NUM_COSETS * n + 127) / 128);
-  quotient_gates_kernel<<<grid, 128, 0, ctx->stream>>>(args, n, n - 1);
-  quotient_perm_kernel<<<grid, 128, 0, ctx->stream>>>(args, n, n - 1);
-  quotient_lookup_kernel<<<grid, 128, 0, ctx->stream>>>(args, n, n - 1);
+  const unsigned grid = (unsigned)((hi - lo + 127) / 128);
+  quotient_gates_kernel<<<grid, 128, 0, ctx->stream>>>(args, n, n - 1, lo, hi);
+  quotient_perm_kernel<<<grid, 128, 0, ctx->stream>>>(args, n, n - 1, lo, hi);
+  quotient_lookup_kernel<<<grid, 128, 0, ctx->stream>>>(args, n, n - 1, lo, hi);
   ctx->launches += 3;
   ZK_CUDA(ctx, cudaGetLastError());
   return ZK_OK;

@@ -23,7 +23,9 @@ struct QuotientArgs {
   Fp ypow[NUM_GATE_POLYS];  // ypow[k] = y^(NUM_GATE_POLYS - 1 - k)
 };
 
-// evaluates h on the NUM_COSETS cosets (coset-major arrays of NUM_COSETS * n elements)
-int32_t quotient_run(zk_ctx* ctx, const QuotientArgs& args, uint64_t n);
+// evaluates h on rows [lo, hi) of the NUM_COSETS cosets (coset-major arrays of NUM_COSETS * n elements);
+// a row reads its own and its rotated neighbours' column values and writes only h[row], so disjoint row
+// ranges may run on different GPUs that hold the same columns
+int32_t quotient_run(zk_ctx* ctx, const QuotientArgs& args, uint64_t n, uint64_t lo, uint64_t hi);
 
 }  // namespace zkodst

@@ -7,7 +7,7 @@
 // rows; each cell's descriptor (blake2f_layout.h) selects a bit-piece of a trace word and
 // whether the cell carries its dense value, spread form (table16/util.rs:61-75 `spread_bits`)
 // or range tag (spread_table.rs:213-222 `get_tag`); the value is converted to a
-// Montgomery-form pallas::Base (table16.rs:93-98) and written with 128-bit stores to the
+// Montgomery-form pallas::Base (table16.rs:93-98) and written with one 256-bit store per cell to the
 // column-major advice buffer, consecutive threads writing consecutive rows of a column.
 //
 // Roofline: HBM store-bound.  Algorithmic bytes per compression = R * 12 * 32 written
@@ -53,11 +53,16 @@ __device__ __forceinline__ uint32_t spread16(uint32_t x) {
   return x;
 }
 
-// integer < 2^64 -> Montgomery-form Fp, as two 16-byte halves
-__device__ __forceinline__ void to_montgomery(uint64_t v, uint4& lo, uint4& hi) {
+// one advice cell (4 x u64 limbs) with a single 256-bit store: a warp covers 1024 contiguous bytes of
+// a column per instruction (STG.E.256, sm_100)
+__device__ __forceinline__ void store_cell(uint64_t* p, uint64_t r0, uint64_t r1, uint64_t r2, uint64_t r3) {
+  asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(r0), "l"(r1), "l"(r2), "l"(r3) : "memory");
+}
+
+// integer < 2^64 -> Montgomery-form Fp, stored at p
+__device__ __forceinline__ void store_montgomery(uint64_t* p, uint64_t v) {
   if (v == 0) {
-    lo = make_uint4(0, 0, 0, 0);
-    hi = make_uint4(0, 0, 0, 0);
+    store_cell(p, 0, 0, 0, 0);
     return;
   }
   // prod = (C1:C0) * v, 192 bits
@@ -74,8 +79,7 @@ __device__ __forceinline__ void to_montgomery(uint64_t v, uint4& lo, uint4& hi) 
   uint64_t r2 = 0 - q2 - b1;
   uint64_t b2 = (q2 != 0) | b1;
   uint64_t r3 = P3 - b2;
-  lo = make_uint4((uint32_t)r0, (uint32_t)(r0 >> 32), (uint32_t)r1, (uint32_t)(r1 >> 32));
-  hi = make_uint4((uint32_t)r2, (uint32_t)(r2 >> 32), (uint32_t)r3, (uint32_t)(r3 >> 32));
+  store_cell(p, r0, r1, r2, r3);
 }
 
 __device__ __forceinline__ uint64_t eval_cell(uint32_t d, const uint64_t* __restrict__ trace) {
@@ -122,13 +126,12 @@ __device__ __forceinline__ void mix_g(uint64_t& a, uint64_t& b, uint64_t& c, uin
 
 // Grid: n_compressions * slices blocks.  Block (comp, slice) rebuilds the compression's trace
 // (cheap, and it keeps every block independent) and emits rows
-// [slice * rows_per_slice, (slice + 1) * rows_per_slice) of that region.  Lane pairs share a
-// row: lane 2m writes the low 16 bytes of a cell, lane 2m+1 the high 16 bytes, so every
-// 128-bit store instruction covers 512 contiguous bytes of one column.
+// [slice * rows_per_slice, (slice + 1) * rows_per_slice) of that region, one thread per row: a cell
+// is one 256-bit store, so every store instruction of a warp covers 1024 contiguous bytes of a column.
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 blake2f_witness_kernel(const uint8_t* __restrict__ inputs, uint32_t rounds, uint32_t R,
-                       const uint32_t* __restrict__ desc, uint4* __restrict__ advice, uint64_t n,
+                       const uint32_t* __restrict__ desc, uint64_t* __restrict__ advice, uint64_t n,
                        uint64_t* __restrict__ digests, uint64_t n_compressions, uint32_t slices,
                        uint32_t rows_per_slice, int* __restrict__ status) {
   extern __shared__ uint64_t trace[];  // trace_words
@@ -208,23 +211,15 @@ blake2f_witness_kernel(const uint8_t* __restrict__ inputs, uint32_t rounds, uint
     const uint64_t base = comp * (uint64_t)R;
     const uint32_t row_begin = slice * rows_per_slice;
     const uint32_t row_end = min(R, row_begin + rows_per_slice);
-    const uint32_t half = threadIdx.x & 1;
-    for (uint32_t row = row_begin + (threadIdx.x >> 1); row < row_end; row += THREADS / 2) {
+    for (uint32_t row = row_begin + threadIdx.x; row < row_end; row += THREADS) {
 #pragma unroll
       for (int c = 0; c < NUM_USED_COLUMNS; c++) {
-        uint32_t d = __ldg(desc + (size_t)c * R + row);
-        uint4 lo, hi;
-        if (d == 0) {
-          lo = make_uint4(0, 0, 0, 0);
-          hi = lo;
-        } else {
-          to_montgomery(eval_cell(d, trace), lo, hi);
-        }
-        advice[((uint64_t)c * n + base + row) * 2 + half] = half ? hi : lo;
+        const uint32_t d = __ldg(desc + (size_t)c * R + row);
+        store_montgomery(advice + ((uint64_t)c * n + base + row) * 4, d == 0 ? 0 : eval_cell(d, trace));
       }
 #pragma unroll
       for (int c = NUM_USED_COLUMNS; c < NUM_ADVICE_COLUMNS; c++)
-        advice[((uint64_t)c * n + base + row) * 2 + half] = make_uint4(0, 0, 0, 0);
+        store_cell(advice + ((uint64_t)c * n + base + row) * 4, 0, 0, 0, 0);
     }
     __syncthreads();
   }
@@ -247,6 +242,7 @@ int32_t launch_witness(zk_ctx* ctx, int32_t k, uint32_t rounds, const uint8_t* d
                        uint64_t n_compressions, void* d_advice, uint64_t* d_digests) {
   if (k < 17 || k > 28) return set_error(ctx, ZK_E_INVALID, "k out of range [17, 28]");
   if (!d_advice || (!d_inputs && n_compressions)) return set_error(ctx, ZK_E_INVALID, "null buffer");
+  if ((uintptr_t)d_advice & 31) return set_error(ctx, ZK_E_INVALID, "advice buffer must be 32-byte aligned");
   DeviceRegionLayout* L = nullptr;
   int32_t rc = get_layout(ctx, rounds, &L);
   if (rc) return rc;
@@ -261,20 +257,29 @@ int32_t launch_witness(zk_ctx* ctx, int32_t k, uint32_t rounds, const uint8_t* d
     ZK_CUDA(ctx, cudaFuncSetAttribute(blake2f_witness_kernel<THREADS>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (n_compressions) {
-    // aim for >= 8 resident blocks per SM; a slice is never smaller than 256 rows
-    uint64_t want = (uint64_t)ctx->sm_count * 8;
-    uint32_t slices = (uint32_t)((want + n_compressions - 1) / n_compressions);
-    uint32_t max_slices = (uint32_t)((R + 255) / 256);
-    if (slices > max_slices) slices = max_slices;
-    if (slices < 1) slices = 1;
-    uint32_t rows_per_slice = (uint32_t)((R + slices - 1) / slices);
-    rows_per_slice = (rows_per_slice + 127) / 128 * 128;  // whole passes of the thread block
-    slices = (uint32_t)((R + rows_per_slice - 1) / rows_per_slice);
-    uint64_t total = n_compressions * slices;
-    unsigned grid = (unsigned)(total < (1ull << 22) ? total : (1ull << 22));
+    // One balanced wave: the work items are (compression, slice) pairs walked by a grid of at most
+    // `cap` resident blocks.  Among the slice counts that keep a slice >= 256 rows, take the one that
+    // fills the last round of the grid best (fewer slices on near-ties: every item recomputes the trace).
+    int per_sm = 0;
+    ZK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, blake2f_witness_kernel<THREADS>, THREADS, smem));
+    const uint64_t cap = (uint64_t)ctx->sm_count * (uint64_t)(per_sm > 0 ? per_sm : 1);
+    const uint32_t max_slices = (uint32_t)((R + 255) / 256);
+    uint32_t slices = 1;
+    double best = -1.0;
+    for (uint32_t s = 1; s <= max_slices; s++) {
+      const uint64_t items = n_compressions * s, rounds_of_grid = (items + cap - 1) / cap;
+      const double fill = (double)items / (double)(rounds_of_grid * cap) - 0.004 * s;
+      if (fill > best) {
+        best = fill;
+        slices = s;
+      }
+    }
+    const uint32_t rows_per_slice = (uint32_t)((R + slices - 1) / slices);
+    const uint64_t total = n_compressions * slices;
+    const unsigned grid = (unsigned)(total < cap ? total : cap);
     KernelTimer timer(ctx, KC_WITNESS);
     blake2f_witness_kernel<THREADS><<<grid, THREADS, smem, ctx->stream>>>(
-        d_inputs, rounds, (uint32_t)R, L->d_desc, (uint4*)d_advice, n, d_digests, n_compressions,
+        d_inputs, rounds, (uint32_t)R, L->d_desc, (uint64_t*)d_advice, n, d_digests, n_compressions,
         slices, rows_per_slice, ctx->d_status);
     ctx->launches++;
   }
