@@ -326,7 +326,9 @@ def main():
         fold = 5 if (k > 13 and (not split or 32 % world == 0)) else k
         ipa_terms = fold + (k - fold) / float(1 << fold)
         full_terms = 13 + ipa_terms
-        mac_per_proof = nrows * (full_terms * MAC_FULL + 12 * MAC_SMALL)
+        # (MSM-split group: the timed launches are rank 0's, which process 1 / world of every MSM's terms)
+        share = world if split else 1
+        mac_per_proof = nrows * (full_terms * MAC_FULL + 12 * MAC_SMALL) / share
         acc_ms, acc_launches = per.get("msm_accumulate", (0.0, 0.0))
         msm_ms, _ = per.get("msm", (0.0, 0.0))
         achieved = mac_per_proof / (acc_ms * 1e-3) / 1e12 if acc_ms else None
@@ -343,13 +345,17 @@ def main():
             "launches_per_proof": acc_launches, "avg_launch_ms": acc_ms / acc_launches if acc_launches else None,
             "algorithmic_mac_per_proof": mac_per_proof,
             "accounting": "SURVEY.md 8d per-term figures (23936 MAC full-width, 2992 MAC advice) x the "
-                          "terms the launches process: %.2f n full-width + 12 n advice" % full_terms,
+                          "terms the launches process: %.2f n full-width + 12 n advice%s"
+                          % (full_terms, " (rank 0's 1/%d share of each MSM)" % world if split else ""),
         }
         ntt_ms, ntt_launches = per.get("ntt", (0.0, 0.0))
         # 19 inverse transforms to coefficients, 19 columns x 3 coset transforms, 3 inverse transforms of
         # h's coset values: all of size n (the quotient lives on three cosets of the n-th roots)
-        ext = 3 * nrows
-        n_transforms = 19 + 19 * 3 + 3
+        # (MSM-split group: rank 0 transforms ceil(19 / world) of the columns and evaluates 1 / world of the
+        # quotient rows; the 3 transforms of h stay replicated)
+        ext = 3 * nrows // share
+        own_cols = -(-19 // share)
+        n_transforms = own_cols + own_cols * 3 + 3
         ntt_bytes = n_transforms * 64 * nrows
         ntt_mac = n_transforms * (nrows // 2) * k * MAC_PER_FP_MUL
         wit_ms, _ = per.get("witness", (0.0, 0.0))

@@ -59,37 +59,69 @@ __device__ __forceinline__ void store_cell(uint64_t* p, uint64_t r0, uint64_t r1
   asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(r0), "l"(r1), "l"(r2), "l"(r3) : "memory");
 }
 
-// integer < 2^64 -> Montgomery-form Fp, stored at p
+// integer < 2^64 -> Montgomery-form Fp, stored at p:  v R mod p = p - 4t v  (0 < v < 2^64, see above).
+// The 64 x 128-bit product runs as eight 32 x 32 -> 64 multiplies summed in two carry chains (even- and
+// odd-aligned partial products), the subtraction from p as one borrow chain.
 __device__ __forceinline__ void store_montgomery(uint64_t* p, uint64_t v) {
   if (v == 0) {
     store_cell(p, 0, 0, 0, 0);
     return;
   }
-  // prod = (C1:C0) * v, 192 bits
-  uint64_t m0 = C0 * v, h0 = __umul64hi(C0, v);
-  uint64_t m1 = C1 * v, h1 = __umul64hi(C1, v);
-  uint64_t q0 = m0;
-  uint64_t q1 = h0 + m1;
-  uint64_t q2 = h1 + (q1 < m1 ? 1 : 0);
-  // r = p - prod
-  uint64_t r0 = P0 - q0;
-  uint64_t b0 = P0 < q0;
-  uint64_t r1 = P1 - q1 - b0;
-  uint64_t b1 = (P1 < q1) | ((P1 == q1) & b0);
-  uint64_t r2 = 0 - q2 - b1;
-  uint64_t b2 = (q2 != 0) | b1;
-  uint64_t r3 = P3 - b2;
+  constexpr uint32_t c0 = (uint32_t)C0, c1 = (uint32_t)(C0 >> 32), c2 = (uint32_t)C1, c3 = (uint32_t)(C1 >> 32);
+  const uint32_t v0 = (uint32_t)v, v1 = (uint32_t)(v >> 32);
+  uint64_t r0, r1, r2, r3;
+  asm("{\n\t"
+      ".reg .u64 a0, a1, b0, b1, d0, d1, e0, e1, x1, x2, y0, y1, y2, m1, m2, q0, q1, q2;\n\t"
+      ".reg .u32 y0l, y0h, y1l, y1h, y2l, y2h, z;\n\t"
+      "mul.wide.u32 a0, %4, %6;\n\t"   // v0 c0: limbs 0,1
+      "mul.wide.u32 a1, %4, %8;\n\t"   // v0 c2: limbs 2,3
+      "mul.wide.u32 b0, %4, %7;\n\t"   // v0 c1: limbs 1,2
+      "mul.wide.u32 b1, %4, %9;\n\t"   // v0 c3: limbs 3,4
+      "mul.wide.u32 d0, %5, %6;\n\t"   // v1 c0: limbs 1,2
+      "mul.wide.u32 d1, %5, %8;\n\t"   // v1 c2: limbs 3,4
+      "mul.wide.u32 e0, %5, %7;\n\t"   // v1 c1: limbs 2,3
+      "mul.wide.u32 e1, %5, %9;\n\t"   // v1 c3: limbs 4,5
+      "add.cc.u64 x1, a1, e0;\n\t"     // even-aligned words: a0 | a1 + e0 | e1 + carry
+      "addc.u64 x2, e1, 0;\n\t"
+      "add.cc.u64 y0, b0, d0;\n\t"     // odd-aligned words (limbs 1,2 | 3,4 | 5)
+      "addc.cc.u64 y1, b1, d1;\n\t"
+      "addc.u64 y2, 0, 0;\n\t"
+      "mov.b64 {y0l, y0h}, y0;\n\t"
+      "mov.b64 {y1l, y1h}, y1;\n\t"
+      "mov.b64 {y2l, y2h}, y2;\n\t"
+      "mov.u32 z, 0;\n\t"
+      "mov.b64 q0, {z, y0l};\n\t"      // the odd chain shifted up by one limb
+      "mov.b64 m1, {y0h, y1l};\n\t"
+      "mov.b64 m2, {y1h, y2l};\n\t"
+      "add.cc.u64 q0, q0, a0;\n\t"     // q = 4t v  (< 2^192)
+      "addc.cc.u64 q1, m1, x1;\n\t"
+      "addc.u64 q2, m2, x2;\n\t"
+      "sub.cc.u64 %0, %10, q0;\n\t"    // p - q
+      "subc.cc.u64 %1, %11, q1;\n\t"
+      "subc.cc.u64 %2, 0, q2;\n\t"
+      "subc.u64 %3, %12, 0;\n\t"
+      "}"
+      : "=l"(r0), "=l"(r1), "=l"(r2), "=l"(r3)
+      : "r"(v0), "r"(v1), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(P0), "l"(P1), "l"(P3));
   store_cell(p, r0, r1, r2, r3);
 }
 
+// piece = rotr64(trace word, rot) & (2^len - 1), then dense value / spread form / range tag; straight-line
+// (the three forms are a handful of ALU operations, cheaper than diverging on the kind)
 __device__ __forceinline__ uint64_t eval_cell(uint32_t d, const uint64_t* __restrict__ trace) {
-  uint64_t w = trace[d >> 14];
-  uint32_t rot = (d >> 8) & 63, len = ((d >> 2) & 63) + 1, kind = d & 3;
-  uint64_t x = rotr64(w, rot);
-  if (len < 64) x &= (1ull << len) - 1;
-  if (kind == CK_DENSE) return x;
-  if (kind == CK_SPREAD) return spread16((uint32_t)x);
-  return x < 256 ? 0 : (x < 32768 ? 1 : 2);  // CK_TAG
+  const uint64_t w = trace[d >> 14];
+  const uint32_t rot = (d >> 8) & 63, drop = 63 - ((d >> 2) & 63), kind = d & 3;  // drop = 64 - len
+  uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
+  if (rot & 32) {
+    const uint32_t t = lo;
+    lo = hi;
+    hi = t;
+  }
+  const uint32_t xl = __funnelshift_r(lo, hi, rot), xh = __funnelshift_r(hi, lo, rot);  // shift amount mod 32
+  const uint64_t x = (((uint64_t)xh << 32) | xl) & (~0ull >> drop);
+  const uint32_t x32 = (uint32_t)x;
+  const uint32_t tag = (x32 >= 256u) + (x32 >= 32768u);  // get_tag: pieces with a tag are <= 16 bits
+  return kind == CK_DENSE ? x : (kind == CK_SPREAD ? (uint64_t)spread16(x32) : (uint64_t)tag);
 }
 
 __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
@@ -141,6 +173,15 @@ blake2f_witness_kernel(const uint8_t* __restrict__ inputs, uint32_t rounds, uint
   for (uint64_t blk = blockIdx.x; blk < total; blk += gridDim.x) {
     const uint64_t comp = blk / slices;
     const uint32_t slice = (uint32_t)(blk % slices);
+    // this item's rows; the first pass's cell descriptors are requested now so that their latency
+    // overlaps the mixing schedule below
+    const uint32_t row_begin = slice * rows_per_slice;
+    const uint32_t row_end = min(R, row_begin + rows_per_slice);
+    uint32_t dnext[NUM_USED_COLUMNS];
+    if (row_begin + threadIdx.x < row_end) {
+#pragma unroll
+      for (int c = 0; c < NUM_USED_COLUMNS; c++) dnext[c] = __ldg(desc + (size_t)c * R + row_begin + threadIdx.x);
+    }
     // ---- load and parse the 213-byte EIP-152 record ---------------------------------------
     for (int i = threadIdx.x; i < 213; i += THREADS) rec[i] = inputs[comp * 213 + i];
     __syncthreads();
@@ -209,14 +250,17 @@ blake2f_witness_kernel(const uint8_t* __restrict__ inputs, uint32_t rounds, uint
 
     // ---- phase 2: emit this slice's cells ---------------------------------------------------
     const uint64_t base = comp * (uint64_t)R;
-    const uint32_t row_begin = slice * rows_per_slice;
-    const uint32_t row_end = min(R, row_begin + rows_per_slice);
     for (uint32_t row = row_begin + threadIdx.x; row < row_end; row += THREADS) {
+      uint32_t dcur[NUM_USED_COLUMNS];
 #pragma unroll
-      for (int c = 0; c < NUM_USED_COLUMNS; c++) {
-        const uint32_t d = __ldg(desc + (size_t)c * R + row);
-        store_montgomery(advice + ((uint64_t)c * n + base + row) * 4, d == 0 ? 0 : eval_cell(d, trace));
+      for (int c = 0; c < NUM_USED_COLUMNS; c++) dcur[c] = dnext[c];
+      if (row + THREADS < row_end) {  // next pass's descriptors travel while this pass computes
+#pragma unroll
+        for (int c = 0; c < NUM_USED_COLUMNS; c++) dnext[c] = __ldg(desc + (size_t)c * R + row + THREADS);
       }
+#pragma unroll
+      for (int c = 0; c < NUM_USED_COLUMNS; c++)
+        store_montgomery(advice + ((uint64_t)c * n + base + row) * 4, dcur[c] == 0 ? 0 : eval_cell(dcur[c], trace));
 #pragma unroll
       for (int c = NUM_USED_COLUMNS; c < NUM_ADVICE_COLUMNS; c++)
         store_cell(advice + ((uint64_t)c * n + base + row) * 4, 0, 0, 0, 0);
