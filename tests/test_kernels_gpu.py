@@ -89,7 +89,9 @@ def test_msm_linearity(ctx, oracle, urs):
     assert np.array_equal(out_sum, out_ab)
 
 
-@pytest.mark.parametrize("log_n", [0, 1, 3, 8, 9, 13, 16, 17])
+# every round plan of the pass scheduler: single passes of 1..10 stages (rounds 3/2/1), two passes
+# (11 = 6 + 5 ... 20 = 10 + 10) and the column-grouped later passes
+@pytest.mark.parametrize("log_n", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 16, 17, 19, 20])
 @pytest.mark.parametrize("inverse", [False, True])
 def test_ntt_matches_oracle(ctx, oracle, log_n, inverse):
     n = 1 << log_n
@@ -103,7 +105,7 @@ def test_ntt_matches_oracle(ctx, oracle, log_n, inverse):
 @pytest.mark.parametrize("log_n", [21, 22, 24, 25])
 def test_ntt_roundtrip_large(ctx, oracle, log_n):
     """Full-size property: iNTT(NTT(x)) == x at the extended-domain sizes of configs 3 and 4
-    (2^21 .. 2^25; 22 and 24 split into 8-stage passes, the others into 7- and 6-stage ones)."""
+    (2^21 .. 2^25: three passes of 7 to 9 stages over 1024-element tiles)."""
     import torch
     n = 1 << log_n
     data = oracle_lib.random_fields(oracle, SEED, 1 << 12)

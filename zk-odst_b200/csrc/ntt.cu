@@ -4,12 +4,17 @@
 // {lagrange_to_coeff, coeff_to_extended, extended_to_coeff}` inside `create_proof`
 // (blake2f-circuit/benches/blake2f.rs:125).  Natural order in, natural order out.
 //
-// Decimation-in-time radix-2 butterflies, executed as shared-memory passes of up to 8 stages:
-// a pass loads a tile of 2^S elements x W adjacent columns (W * 32 B contiguous per row), runs
-// S stages out of shared memory and stores the tile back, so a 2^21-point transform touches
-// HBM 3 times instead of 21.  The first pass fuses the bit-reversal gather, zero padding and
-// an optional per-element input scaling (coset evaluation: c^i from a table); the last pass fuses the
-// 1/N scaling.  Several transforms of one size run as one batch of launches (blockIdx.y).  Twiddles come from a per-domain table of N/2 powers.
+// Decimation-in-time butterflies, executed as shared-memory passes of up to 10 stages over tiles of 1024
+// elements: a tile is G independent groups x 2^S transform indices x W adjacent columns (W * 32 B
+// contiguous per row), so a 2^19-point transform touches HBM twice instead of 19 times.  Inside a pass
+// the stages run in rounds: a thread takes 2^Q elements into registers, runs Q stages (Q = 2: four
+// butterflies, three twiddles) and puts them back, so shared memory and the barrier are visited once per
+// Q stages.  The tile is padded by one element in eight, which spreads every round's stride over
+// the banks.  The first pass fuses the bit-reversal gather, zero padding and an optional per-element
+// input scaling (coset evaluation: c^i from a table); the last pass fuses the 1/N scaling.  Several
+// transforms of one size run as one batch of launches (blockIdx.y, blockIdx.z), which also fills the
+// grid: one 2^19-point transform is only 512 tiles.  Twiddles come from a per-domain
+// table of N/2 powers; stage 0's twiddle is 1 and its multiplication is skipped.
 //
 // Roofline: algorithmic bytes 64*N per transform; work (N/2) log2 N Fp multiplications
 // (~20 MAC/B at N = 2^19): integer-pipe bound; both fractions are reported.
@@ -27,37 +32,100 @@ __global__ void powers_kernel(Fp base, Fp* out, uint32_t n) {
 
 __device__ __forceinline__ uint32_t bitrev(uint32_t v, int bits) { return __brev(v) >> (32 - bits); }
 
+constexpr int NTT_TILE_LOG = 10;     // elements per tile (log2)
+constexpr int NTT_THREADS = 128;     // 8 elements per thread
+constexpr int NTT_MAX_ROUNDS = 5;
+// Stages per round and resident blocks per SM.  Measured on B200 inside the prover (k = 19, NTT ms per
+// proof): 3 stages / 3 blocks (168 registers) 7.71, 3 / 4 (128 registers, spills) 7.22, 2 / 6 (80 registers)
+// 6.87, 2 / 8 (64 registers, spills) 7.07 — the butterflies are bound by the quarter-rate IMAD.WIDE.X
+// chains, so what the wider rounds save in shared-memory trips they lose in resident warps.
+constexpr int NTT_ROUND_STAGES = 2;
+constexpr int NTT_MIN_BLOCKS = 6;
+
 struct NttPassArgs {
   const Fp* in;
   Fp* out;
   const Fp* tw;      // omega^i, i < N/2
   const Fp* scale_in;  // first pass: optional per-element multiplier
   size_t in_stride, out_stride, scale_stride;  // per transform of the batch (blockIdx.y)
+  size_t in_stride2, out_stride2;              // second batch level (blockIdx.z)
   int log_n;         // L
   int s0;            // stages already done
   int S;             // stages in this pass
   int logW;          // log2 of adjacent columns per tile (0 for the first pass)
+  int logG;          // log2 of independent high-index groups per tile
+  int nrounds;       // the S stages as rounds of q[i] in {1, 2, 3} stages
+  int q[NTT_MAX_ROUNDS];
   uint32_t n_in;     // first pass: input length (zero padded above)
   int first, last;
   int scale_out;     // last pass: multiply by `scale` (1/N of the inverse transform)
   Fp scale;
 };
 
-__global__ void __launch_bounds__(256, 5) ntt_pass_kernel(NttPassArgs a) {
+// slot of tile element e: one element of padding after every eight
+__device__ __forceinline__ uint32_t ntt_slot(uint32_t e) { return e + (e >> 3); }
+
+// One round: Q consecutive stages, starting at stage r of the pass, on 2^Q elements held in registers.
+// Tile element e = (g << (S + logW)) | (t << logW) | l; a unit is the 2^Q elements whose t differ only in
+// bits [r, r + Q).  The butterfly of stage r + q on the pair (m, m | 2^q) uses the twiddle of global index
+// j = (((m mod 2^q) << r | t mod 2^r) << s0) | lo, scaled to the domain: omega^(j * N / 2^(s0 + r + q + 1)).
+template <int Q>
+__device__ __forceinline__ void ntt_round(Fp* __restrict__ sm, const NttPassArgs& a, int r, uint32_t lo0,
+                                          uint32_t tile_elems) {
+  const int logW = a.logW;
+  const uint32_t W = 1u << logW;
+  const uint32_t units = tile_elems >> Q;
+  const uint32_t mstride = 1u << (r + logW);
+  const bool unit_twiddle = a.s0 + r == 0;  // stage 0 of the transform: omega^0
+  for (uint32_t u = threadIdx.x; u < units; u += NTT_THREADS) {
+    const uint32_t l = u & (W - 1), ub = u >> logW;
+    const uint32_t tlo = ub & ((1u << r) - 1), up = ub >> r;
+    const uint32_t ebase = ((((up << (r + Q)) | tlo)) << logW) | l;
+    const uint32_t lo = lo0 + l;
+    Fp x[1 << Q];
+#pragma unroll
+    for (int m = 0; m < (1 << Q); m++) x[m] = sm[ntt_slot(ebase + m * mstride)];
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+      const int shift = a.log_n - (a.s0 + r + q) - 1;
+#pragma unroll
+      for (int mlow = 0; mlow < (1 << q); mlow++) {
+        const uint32_t j = ((((uint32_t)mlow << r) | tlo) << a.s0) | lo;
+        const Fp w = a.tw[(size_t)j << shift];
+#pragma unroll
+        for (int mh = 0; mh < (1 << (Q - q - 1)); mh++) {
+          const int i0 = (mh << (q + 1)) | mlow, i1 = i0 | (1 << q);
+          const Fp y = (q == 0 && unit_twiddle) ? x[i1] : x[i1] * w;
+          x[i1] = x[i0] - y;
+          x[i0] = x[i0] + y;
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < (1 << Q); m++) sm[ntt_slot(ebase + m * mstride)] = x[m];
+  }
+}
+
+template <int MAXQ, int MINB>
+__global__ void __launch_bounds__(NTT_THREADS, MINB) ntt_pass_kernel(const __grid_constant__ NttPassArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Fp* sm = reinterpret_cast<Fp*>(smem_raw);
-  const int L = a.log_n, S = a.S, logW = a.logW, W = 1 << logW;
-  const uint32_t tile_elems = 1u << (S + logW);
-  // tile id -> (hi, lo0): global index = hi << (s0 + S) | t << s0 | lo,  lo in [lo0, lo0 + W)
-  const uint32_t lo_groups = (1u << a.s0) >> logW;  // number of W-wide lo groups (>= 1)
+  const int L = a.log_n, S = a.S, logW = a.logW, logG = a.logG;
+  const uint32_t W = 1u << logW;
+  const uint32_t tile_elems = 1u << (S + logW + logG);
+  // tile id -> (hi0, lo0): global index = (hi0 + g) << (s0 + S) | t << s0 | (lo0 + l)
+  const uint32_t lo_tiles = (1u << a.s0) >> logW;
   const uint32_t tile = blockIdx.x;
-  const uint32_t hi = tile / lo_groups, lo0 = (tile % lo_groups) << logW;
-  const Fp* const in = a.in + (a.first ? blockIdx.y * a.in_stride : blockIdx.y * a.out_stride);
-  Fp* const out = a.out + blockIdx.y * a.out_stride;
+  const uint32_t hi0 = (tile / lo_tiles) << logG, lo0 = (tile % lo_tiles) << logW;
+  Fp* const out = a.out + blockIdx.y * a.out_stride + blockIdx.z * a.out_stride2;
+  const Fp* const in = a.first ? a.in + blockIdx.y * a.in_stride + blockIdx.z * a.in_stride2 : out;
+  auto global_index = [&](uint32_t e) {
+    const uint32_t l = e & (W - 1), t = (e >> logW) & ((1u << S) - 1), g = e >> (logW + S);
+    return ((hi0 + g) << (a.s0 + S)) | (t << a.s0) | (lo0 + l);
+  };
   // ---- load
-  for (uint32_t e = threadIdx.x; e < tile_elems; e += blockDim.x) {
-    uint32_t t = e >> logW, l = e & (W - 1);
-    uint32_t idx = (hi << (a.s0 + S)) | (t << a.s0) | (lo0 + l);
+  for (uint32_t e = threadIdx.x; e < tile_elems; e += NTT_THREADS) {
+    const uint32_t idx = global_index(e);
     Fp v;
     if (a.first) {
       uint32_t src = bitrev(idx, L);
@@ -70,37 +138,24 @@ __global__ void __launch_bounds__(256, 5) ntt_pass_kernel(NttPassArgs a) {
     } else {
       v = in[idx];
     }
-    sm[e] = v;
+    sm[ntt_slot(e)] = v;
   }
   __syncthreads();
-  // ---- stages: one butterfly per thread (blockDim = tile_elems / 2); the twiddle of the next stage is
-  // requested before the barrier so that its latency overlaps the wait
-  {
-    const uint32_t b = threadIdx.x;
-    const uint32_t l = b & (W - 1), tb = b >> logW;  // tb in [0, 2^(S-1))
-    auto twiddle_index = [&](int r) {
-      const uint32_t tlo = tb & ((1u << r) - 1);
-      const uint32_t j = (tlo << a.s0) | (lo0 + l);  // index within the half
-      return (size_t)j << (L - (a.s0 + r + 1));
-    };
-    Fp w = a.tw[twiddle_index(0)];
-    for (int r = 0; r < S; r++) {
-      const uint32_t tlo = tb & ((1u << r) - 1), thi = tb >> r;
-      const uint32_t t0 = (thi << (r + 1)) | tlo, t1 = t0 | (1u << r);
-      const Fp x = sm[(t0 << logW) | l], y = sm[(t1 << logW) | l] * w;
-      sm[(t0 << logW) | l] = x + y;
-      sm[(t1 << logW) | l] = x - y;
-      if (r + 1 < S) w = a.tw[twiddle_index(r + 1)];
-      __syncthreads();
-    }
+  // ---- stages
+  int r = 0;
+  for (int i = 0; i < a.nrounds; i++) {
+    const int q = a.q[i];
+    if (MAXQ >= 3 && q == 3) ntt_round<MAXQ >= 3 ? 3 : 1>(sm, a, r, lo0, tile_elems);
+    else if (MAXQ >= 2 && q == 2) ntt_round<MAXQ >= 2 ? 2 : 1>(sm, a, r, lo0, tile_elems);
+    else ntt_round<1>(sm, a, r, lo0, tile_elems);
+    r += q;
+    __syncthreads();
   }
   // ---- store
-  for (uint32_t e = threadIdx.x; e < tile_elems; e += blockDim.x) {
-    uint32_t t = e >> logW, l = e & (W - 1);
-    uint32_t idx = (hi << (a.s0 + S)) | (t << a.s0) | (lo0 + l);
-    Fp v = sm[e];
+  for (uint32_t e = threadIdx.x; e < tile_elems; e += NTT_THREADS) {
+    Fp v = sm[ntt_slot(e)];
     if (a.last && a.scale_out) v = v * a.scale;
-    out[idx] = v;
+    out[global_index(e)] = v;
   }
 }
 
@@ -138,7 +193,7 @@ int32_t ntt_run(zk_ctx* ctx, const Fp* in, uint32_t n_in, Fp* out, int log_n, co
   if (rc) return rc;
   const uint32_t N = 1u << log_n;
   const Fp* src = in;
-  if (in == out && opt.batch > 1) return set_error(ctx, ZK_E_INVALID, "ntt: batched transforms need distinct buffers");
+  if (in == out && (opt.batch > 1 || opt.batch2 > 1)) return set_error(ctx, ZK_E_INVALID, "ntt: batched transforms need distinct buffers");
   if (in == out) {  // bit-reversal gather cannot run in place
     rc = ensure_buf(ctx, ctx->ntt_tmp, (size_t)n_in * sizeof(Fp));
     if (rc) return rc;
@@ -151,17 +206,16 @@ int32_t ntt_run(zk_ctx* ctx, const Fp* in, uint32_t n_in, Fp* out, int log_n, co
     ZK_CUDA(ctx, cudaMemcpyAsync(out, src, sizeof(Fp), cudaMemcpyDeviceToDevice, ctx->stream));
     return ZK_OK;
   }
-  const int MAXS = 8;
+  const int passes = (log_n + NTT_TILE_LOG - 1) / NTT_TILE_LOG;
   int s0 = 0;
-  while (s0 < log_n) {
+  for (int pass = 0; pass < passes; pass++) {
     NttPassArgs a;
     memset(&a, 0, sizeof a);
-    int S = log_n - s0 < MAXS ? log_n - s0 : MAXS;
-    // balance the remaining passes so the last one is not tiny
-    int remaining = log_n - s0, passes = (remaining + MAXS - 1) / MAXS;
-    S = (remaining + passes - 1) / passes;
-    int logW = s0 == 0 ? 0 : (s0 < 2 ? s0 : 2);
-    if (S + logW > 9) logW = 9 - S;  // one butterfly per thread, at most 256 threads
+    // stages balanced over the passes, the longer ones first
+    const int S = log_n / passes + (pass < log_n % passes ? 1 : 0);
+    const int tile_log = log_n < NTT_TILE_LOG ? log_n : NTT_TILE_LOG;
+    const int logW = s0 < tile_log - S ? s0 : tile_log - S;
+    const int logG = tile_log - S - logW;  // <= log_n - s0 - S: the first pass has all the high bits, later ones logG = 0
     a.in = s0 == 0 ? src : out;
     a.out = out;
     a.tw = opt.inverse ? T->tw_inv : T->tw_fwd;
@@ -169,6 +223,12 @@ int32_t ntt_run(zk_ctx* ctx, const Fp* in, uint32_t n_in, Fp* out, int log_n, co
     a.s0 = s0;
     a.S = S;
     a.logW = logW;
+    a.logG = logG;
+    for (int left = S; left > 0;) {  // rounds of NTT_ROUND_STAGES stages
+      const int q = left >= NTT_ROUND_STAGES ? NTT_ROUND_STAGES : left;
+      a.q[a.nrounds++] = q;
+      left -= q;
+    }
     a.n_in = n_in;
     a.first = s0 == 0;
     a.last = s0 + S == log_n;
@@ -176,12 +236,15 @@ int32_t ntt_run(zk_ctx* ctx, const Fp* in, uint32_t n_in, Fp* out, int log_n, co
     a.in_stride = opt.in_stride;
     a.out_stride = opt.out_stride;
     a.scale_stride = opt.scale_stride;
+    a.in_stride2 = opt.in_stride2;
+    a.out_stride2 = opt.out_stride2;
     a.scale_out = opt.inverse;
     a.scale = T->n_inv;
-    uint32_t tile_elems = 1u << (S + logW);
-    uint32_t tiles = N / tile_elems;
-    size_t smem = (size_t)tile_elems * sizeof(Fp);
-    ntt_pass_kernel<<<dim3(tiles, (unsigned)opt.batch), tile_elems / 2, smem, ctx->stream>>>(a);
+    const uint32_t tile_elems = 1u << tile_log;
+    const uint32_t tiles = N / tile_elems;
+    const size_t smem = (size_t)(tile_elems + (tile_elems >> 3) + 1) * sizeof(Fp);
+    const dim3 grid(tiles, (unsigned)opt.batch, (unsigned)opt.batch2);
+    ntt_pass_kernel<NTT_ROUND_STAGES, NTT_MIN_BLOCKS><<<grid, NTT_THREADS, smem, ctx->stream>>>(a);
     ctx->launches++;
     s0 += S;
   }

@@ -24,10 +24,12 @@ struct ProofWorkspace {
   uint64_t n = 0, en = 0;
   uint8_t* inputs = nullptr;
   uint64_t* digests = nullptr;
-  Fp* advice_values = nullptr;  // [12][n]
-  // The 19 witness polynomials live in two slot arrays (coefficients, coset values) so that a multi-GPU
-  // group can all-gather them in place: slots 0..11 advice, 12 permuted input, 13 permuted table,
-  // 14..17 permutation products, 18 lookup product (padded to a multiple of the group size).
+  // The 19 witness columns live in three slot arrays (values, coefficients, coset values) so that their
+  // transforms run as batches and a multi-GPU group can all-gather the results in place: slots 0..11
+  // advice, 12 permuted input, 13 permuted table, 14..17 permutation products, 18 lookup product
+  // (coefficient and coset arrays padded to a multiple of the group size).
+  Fp* values_all = nullptr;     // [19][n]
+  Fp* advice_values = nullptr;  // = values_all ([12][n])
   Fp* polys_all = nullptr;      // [slots][n]
   Fp* cosets_all = nullptr;     // [slots][en]
   Fp* advice_polys = nullptr;   // = polys_all   ([12][n])
@@ -91,7 +93,11 @@ int32_t get_workspace(zk_ctx* ctx, DeviceKeys& K, ProofWorkspace** out) {
 #define A(p, cnt) if ((rc = dalloc(ctx, W, &W->p, (cnt)))) return rc
     A(inputs, K.n_compressions * 213 + 16);
     A(digests, K.n_compressions * 8 + 8);
-    A(advice_values, 12 * n);
+    A(values_all, NUM_WITNESS_POLYS * n);
+    W->advice_values = W->values_all;
+    W->pin = W->values_all + SLOT_PIN * n;
+    W->ptab = W->values_all + SLOT_PTAB * n;
+    for (int s = 0; s <= NUM_SETS; s++) W->z_vals[s] = W->values_all + (SLOT_Z0 + s) * n;
     const uint64_t slots = witness_slots_padded(ctx->dist_world);
     A(polys_all, slots * n);
     A(cosets_all, slots * en);
@@ -107,8 +113,7 @@ int32_t get_workspace(zk_ctx* ctx, DeviceKeys& K, ProofWorkspace** out) {
       W->z_poly[s] = W->polys_all + (SLOT_Z0 + s) * n;
       W->z_coset[s] = W->cosets_all + (SLOT_Z0 + s) * en;
     }
-    A(cin, n); A(ctab, n); A(pin, n); A(ptab, n);
-    for (int s = 0; s <= NUM_SETS; s++) A(z_vals[s], n);
+    A(cin, n); A(ctab, n);
     A(tmp_a, n); A(tmp_b, n); A(tmp_c, n);
     A(h, en); A(h_coeffs, en);
     A(random_poly, n); A(s_poly, n); A(q_prime, n); A(p_poly, n); A(b_vec, n); A(h_poly, n);
@@ -596,14 +601,21 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
     const uint64_t spr = witness_slots_per_rank(world);
     const uint64_t slot_lo = spr * (uint64_t)ctx->dist_rank;
     const uint64_t slot_hi = std::min<uint64_t>(slot_lo + spr, NUM_WITNESS_POLYS);
-    for (uint64_t slot = slot_lo; slot < slot_hi; slot++) {
-      const Fp* vals = slot < 12          ? adv((int)slot)
-                       : slot == SLOT_PIN  ? W->pin
-                       : slot == SLOT_PTAB ? W->ptab
-                                           : W->z_vals[slot - SLOT_Z0];
-      Fp* poly = W->polys_all + slot * n;
-      if ((rc = ntt_run(ctx, vals, (uint32_t)n, poly, k, inv))) return rc;
-      if ((rc = coeff_to_extended(ctx, K, poly, W->cosets_all + slot * en))) return rc;
+    if (slot_hi > slot_lo) {  // one batch of inverse transforms, then one of columns x cosets
+      NttOptions o = inv;
+      o.batch = (int)(slot_hi - slot_lo);
+      o.in_stride = o.out_stride = n;
+      if ((rc = ntt_run(ctx, W->values_all + slot_lo * n, (uint32_t)n, W->polys_all + slot_lo * n, k, o))) return rc;
+      NttOptions c;
+      c.batch = NUM_COSETS;
+      c.in_stride = 0;
+      c.out_stride = n;
+      c.scale_in = K.coset_scale;
+      c.scale_stride = n;
+      c.batch2 = o.batch;
+      c.in_stride2 = n;
+      c.out_stride2 = en;
+      if ((rc = ntt_run(ctx, W->polys_all + slot_lo * n, (uint32_t)n, W->cosets_all + slot_lo * en, k, c))) return rc;
     }
     if (world > 1) {
       if ((rc = dist_allgather_device(ctx, W->polys_all + slot_lo * n, W->polys_all, spr * n * sizeof(Fp)))) return rc;

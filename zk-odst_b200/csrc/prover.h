@@ -11,6 +11,10 @@ struct NttOptions {
   // transform b reads in + b * in_stride (0: all read the same vector), writes out + b * out_stride.
   int batch = 1;
   size_t in_stride = 0, out_stride = 0;
+  // Second batch level (blockIdx.z), e.g. columns x cosets: transform (b, c) reads
+  // in + b * in_stride + c * in_stride2 and writes out + b * out_stride + c * out_stride2.
+  int batch2 = 1;
+  size_t in_stride2 = 0, out_stride2 = 0;
   // Optional per-element input scaling: input element i of transform b is multiplied by
   // scale_in[b * scale_stride + i] while it is loaded (coset evaluation: scale_in[i] = c^i).
   const Fp* scale_in = nullptr;
