@@ -121,7 +121,8 @@ int32_t zk_blake2f_witness_batch(zk_ctx* ctx, int32_t k, uint32_t rounds,
                                  const uint8_t* inputs, uint64_t n_compressions,
                                  void* advice_out, uint64_t* digests_out);
 /* Device-buffer form: all three pointers are device memory on the context's device; runs
- * asynchronously on the context's stream. */
+ * asynchronously on the context's stream.  d_advice must be 32-byte aligned (cells are written with
+ * 256-bit stores; any cudaMalloc pointer is): ZK_E_INVALID otherwise. */
 int32_t zk_blake2f_witness_batch_device(zk_ctx* ctx, int32_t k, uint32_t rounds,
                                         const uint8_t* d_inputs, uint64_t n_compressions,
                                         void* d_advice, uint64_t* d_digests);
@@ -209,6 +210,13 @@ int32_t zk_dist_info(const zk_ctx* ctx, int32_t* rank, int32_t* world);
 /* The contiguous range [lo, hi) of the n base points that `rank` of `world` tabulates and sums
  * (host-only helper; the partition the MSM split uses). */
 int32_t zk_dist_range(uint64_t n_points, int32_t rank, int32_t world, uint64_t* lo, uint64_t* hi);
+/* How a group shards the transforms of the witness columns (SURVEY.md 8e "NTT only across columns"):
+ * the ZK_NUM_WITNESS_COLUMNS columns (12 advice, permuted input, permuted table, 4 permutation products,
+ * lookup product) are cut into blocks of *per_rank = ceil(columns / world) slots; `rank` transforms
+ * slots [lo, hi) (empty for the last ranks when world does not divide the count) and the slot arrays,
+ * padded to per_rank * world slots, are all-gathered in place.  Host-only helper. */
+#define ZK_NUM_WITNESS_COLUMNS 19
+int32_t zk_dist_column_block(int32_t rank, int32_t world, uint32_t* lo, uint32_t* hi, uint32_t* per_rank);
 
 #ifdef __cplusplus
 }

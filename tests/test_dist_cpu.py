@@ -74,3 +74,56 @@ def test_ranges_partition_the_points():
                 assert lo == prev and hi >= lo
                 prev = hi
             assert prev == n
+
+
+def test_column_blocks_cover_the_witness_columns():
+    """zk_dist_column_block: every one of the 19 witness columns is transformed by exactly one rank and
+    rank r's block starts at slot r * per_rank of the padded array (the in-place all-gather layout)."""
+    import zk_odst_b200 as zk
+    for world in (1, 2, 3, 4, 5, 8, 19, 24):
+        owner = [None] * 19
+        for r in range(world):
+            lo, hi, per = zk.dist_column_block(r, world)
+            assert per == -(-19 // world) and hi - lo <= per
+            assert lo == min(r * per, 19)
+            for s in range(lo, hi):
+                assert owner[s] is None
+                owner[s] = r
+        assert all(o is not None for o in owner), world
+
+
+def _column_worker(rank, world, port, out_path):
+    """The exchange prover.cu performs with ncclAllGather, over gloo: every rank fills only its own block
+    of the padded slot array, the blocks are all-gathered in place, every rank ends with all columns."""
+    import torch
+    import torch.distributed as dist
+    import zk_odst_b200 as zk
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    n = 64
+    lo, hi, per = zk.dist_column_block(rank, world)
+    slots = torch.full((per * world, n), -1, dtype=torch.int64)
+    for s in range(lo, hi):  # "transform" of column s: anything that depends on (s, row) only
+        slots[s] = torch.arange(n, dtype=torch.int64) * 1000 + s
+    mine = slots[rank * per:(rank + 1) * per].clone()
+    dist.all_gather(list(slots.view(world, per, n).unbind(0)), mine)
+    want = torch.arange(n, dtype=torch.int64)[None, :] * 1000 + torch.arange(19, dtype=torch.int64)[:, None]
+    ok = torch.equal(slots[:19], want)
+    # quotient rows: rank r evaluates rows [r * rows, (r + 1) * rows) of the 3n-row domain
+    en = 3 * n
+    rows = en // world
+    h = torch.full((en,), -1, dtype=torch.int64)
+    h[rank * rows:(rank + 1) * rows] = torch.arange(rank * rows, (rank + 1) * rows) * 7
+    dist.all_gather(list(h.view(world, rows).unbind(0)), h[rank * rows:(rank + 1) * rows].clone())
+    ok = ok and torch.equal(h, torch.arange(en) * 7)
+    with open(out_path + ".%d" % rank, "w") as f:
+        f.write("ok" if ok else "mismatch")
+    dist.destroy_process_group()
+
+
+def test_column_sharded_transforms_world2(tmp_path):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    out = str(tmp_path / "cols")
+    mp.spawn(_column_worker, args=(2, port, out), nprocs=2, join=True)
+    for r in range(2):
+        assert open(out + ".%d" % r).read() == "ok"

@@ -65,6 +65,30 @@ def test_rejections(ctx, zk):
     assert e.value.code == -5
 
 
+@pytest.mark.parametrize("n", [1, 3, 9, 26])
+def test_slice_plans_bit_exact(ctx, oracle, zk, n):
+    """The (compression, slice) work items are sized from the batch: every slice count the planner can
+    pick at k = 17 (n = 1 -> 20 slices ... n = 26 -> many items per block) must emit the same cells."""
+    inputs = zk.synthetic_inputs(n, stream=n)
+    adv, dig = gpu_witness(ctx, 17, 12, inputs, n)
+    ref, _, rdig = oracle.witness(17, 12, inputs, n)
+    assert np.array_equal(dig, rdig)
+    assert np.array_equal(adv, ref)
+
+
+def test_device_buffer_alignment(ctx, zk):
+    """Cells are written with 256-bit stores: a device advice buffer that is not 32-byte aligned is
+    rejected (ZK_E_INVALID), not written with misaligned stores."""
+    import torch
+    d_in = torch.frombuffer(bytearray(zk.synthetic_inputs(1)), dtype=torch.uint8).cuda()
+    buf = torch.empty(12 * (1 << 17) * 32 + 64, dtype=torch.uint8, device="cuda")
+    with pytest.raises(zk.ZkError) as e:
+        ctx.witness_batch_device(17, 12, d_in, 1, buf.data_ptr() + 16)
+    assert e.value.code == -1
+    ctx.witness_batch_device(17, 12, d_in, 1, buf.data_ptr() + 32)
+    ctx.synchronize()
+
+
 def test_full_size_properties(ctx, oracle, zk):
     """Config 3 (64 compressions, k = 19): digests equal the oracle's F on every record and the
     device-resident path equals the host path; the oracle's per-cell check runs on a sample."""

@@ -17,5 +17,6 @@ from .binding import (  # noqa: F401
     blake2f_compress,
     blake2b_records,
     dist_range,
+    dist_column_block,
 )
 from .inputs import eip152_record, synthetic_inputs, XorShiftRng, REFERENCE_SEED  # noqa: F401

@@ -68,6 +68,8 @@ def load_library():
             "zk_dist_init": (i32, [vp, c.c_char_p, i32, i32]),
             "zk_dist_info": (i32, [vp, c.POINTER(i32), c.POINTER(i32)]),
             "zk_dist_range": (i32, [u64, i32, i32, c.POINTER(u64), c.POINTER(u64)]),
+            "zk_dist_column_block": (i32, [i32, i32, c.POINTER(c.c_uint32), c.POINTER(c.c_uint32),
+                                           c.POINTER(c.c_uint32)]),
         }
         for name, (res, args) in sigs.items():
             fn = getattr(lib, name)
@@ -124,6 +126,16 @@ def dist_range(n_points, rank, world):
     if rc:
         raise ZkError(rc)
     return lo.value, hi.value
+
+
+def dist_column_block(rank, world):
+    """(lo, hi, per_rank): the witness-column slots `rank` of `world` transforms (zk_dist_column_block)."""
+    lib = load_library()
+    lo, hi, per = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
+    rc = lib.zk_dist_column_block(rank, world, ctypes.byref(lo), ctypes.byref(hi), ctypes.byref(per))
+    if rc:
+        raise ZkError(rc)
+    return lo.value, hi.value, per.value
 
 
 def rows_per_compression(rounds):

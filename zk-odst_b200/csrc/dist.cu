@@ -59,6 +59,15 @@ void dist_range(uint64_t n, int rank, int world, uint64_t* lo, uint64_t* hi) {
   *hi = n * (uint64_t)(rank + 1) / (uint64_t)world;
 }
 
+// block of witness-column slots transformed by `rank`: [lo, hi) of `count`, per_rank slots per block
+void dist_column_block(uint32_t count, int rank, int world, uint32_t* lo, uint32_t* hi, uint32_t* per_rank) {
+  const uint32_t per = (count + (uint32_t)world - 1) / (uint32_t)world;
+  const uint32_t first = per * (uint32_t)rank;
+  *per_rank = per;
+  *lo = first < count ? first : count;
+  *hi = first + per < count ? first + per : count;
+}
+
 // results[m] <- sum over ranks of their results[m]; identical on every rank afterwards
 int32_t dist_sum_points(zk_ctx* ctx, XYZZ* results, int nb) {
   if (ctx->dist_world <= 1) return ZK_OK;
@@ -141,5 +150,11 @@ extern "C" int32_t zk_dist_info(const zk_ctx* ctx, int32_t* rank, int32_t* world
 extern "C" int32_t zk_dist_range(uint64_t n_points, int32_t rank, int32_t world, uint64_t* lo, uint64_t* hi) {
   if (!lo || !hi || world < 1 || rank < 0 || rank >= world) return ZK_E_INVALID;
   dist_range(n_points, rank, world, lo, hi);
+  return ZK_OK;
+}
+
+extern "C" int32_t zk_dist_column_block(int32_t rank, int32_t world, uint32_t* lo, uint32_t* hi, uint32_t* per_rank) {
+  if (!lo || !hi || !per_rank || world < 1 || rank < 0 || rank >= world) return ZK_E_INVALID;
+  dist_column_block(ZK_NUM_WITNESS_COLUMNS, rank, world, lo, hi, per_rank);
   return ZK_OK;
 }

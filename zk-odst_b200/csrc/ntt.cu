@@ -37,7 +37,7 @@ constexpr int NTT_THREADS = 128;     // 8 elements per thread
 constexpr int NTT_MAX_ROUNDS = 5;
 // Stages per round and resident blocks per SM.  Measured on B200 inside the prover (k = 19, NTT ms per
 // proof): 3 stages / 3 blocks (168 registers) 7.71, 3 / 4 (128 registers, spills) 7.22, 2 / 6 (80 registers)
-// 6.87, 2 / 8 (64 registers, spills) 7.07 — the butterflies are bound by the quarter-rate IMAD.WIDE.X
+// 6.87, 2 / 8 (64 registers, spills) 7.07 — the butterflies are bound by the half-rate IMAD.WIDE.X
 // chains, so what the wider rounds save in shared-memory trips they lose in resident warps.
 constexpr int NTT_ROUND_STAGES = 2;
 constexpr int NTT_MIN_BLOCKS = 6;

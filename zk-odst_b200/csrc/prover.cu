@@ -62,10 +62,13 @@ struct ProofWorkspace {
   std::vector<void*> all;
 };
 
-constexpr int SLOT_PIN = 12, SLOT_PTAB = 13, SLOT_Z0 = 14, SLOT_ZL = 18, NUM_WITNESS_POLYS = 19;
-// slots per rank when the transforms are sharded by column over `world` ranks
-static inline uint64_t witness_slots_per_rank(int world) { return (NUM_WITNESS_POLYS + world - 1) / world; }
-static inline uint64_t witness_slots_padded(int world) { return witness_slots_per_rank(world) * world; }
+constexpr int SLOT_PIN = 12, SLOT_PTAB = 13, SLOT_Z0 = 14, SLOT_ZL = 18, NUM_WITNESS_POLYS = ZK_NUM_WITNESS_COLUMNS;
+// slots of the coefficient / coset arrays when the transforms are sharded by column over `world` ranks
+static inline uint64_t witness_slots_padded(int world) {
+  uint32_t lo, hi, per;
+  dist_column_block(NUM_WITNESS_POLYS, 0, world, &lo, &hi, &per);
+  return (uint64_t)per * world;
+}
 
 void free_workspace(void* p) {
   ProofWorkspace* W = (ProofWorkspace*)p;
@@ -598,9 +601,10 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
     // group every rank transforms its own block of slots and the two slot arrays are all-gathered in
     // place; the column values themselves are already replicated.
     const int world = ctx->dist_world;
-    const uint64_t spr = witness_slots_per_rank(world);
-    const uint64_t slot_lo = spr * (uint64_t)ctx->dist_rank;
-    const uint64_t slot_hi = std::min<uint64_t>(slot_lo + spr, NUM_WITNESS_POLYS);
+    uint32_t blk_lo, blk_hi, blk_per;
+    dist_column_block(NUM_WITNESS_POLYS, ctx->dist_rank, world, &blk_lo, &blk_hi, &blk_per);
+    const uint64_t spr = blk_per, slot_lo = blk_lo, slot_hi = blk_hi;
+    const uint64_t send_slot = spr * (uint64_t)ctx->dist_rank;  // this rank's block of the padded arrays
     if (slot_hi > slot_lo) {  // one batch of inverse transforms, then one of columns x cosets
       NttOptions o = inv;
       o.batch = (int)(slot_hi - slot_lo);
@@ -618,8 +622,8 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
       if ((rc = ntt_run(ctx, W->polys_all + slot_lo * n, (uint32_t)n, W->cosets_all + slot_lo * en, k, c))) return rc;
     }
     if (world > 1) {
-      if ((rc = dist_allgather_device(ctx, W->polys_all + slot_lo * n, W->polys_all, spr * n * sizeof(Fp)))) return rc;
-      if ((rc = dist_allgather_device(ctx, W->cosets_all + slot_lo * en, W->cosets_all, spr * en * sizeof(Fp))))
+      if ((rc = dist_allgather_device(ctx, W->polys_all + send_slot * n, W->polys_all, spr * n * sizeof(Fp)))) return rc;
+      if ((rc = dist_allgather_device(ctx, W->cosets_all + send_slot * en, W->cosets_all, spr * en * sizeof(Fp))))
         return rc;
     }
     NttTables* TNq = nullptr;

@@ -111,6 +111,7 @@ struct KernelTimer {  // CUDA-event bracket on the context's stream, only when t
 // dist.cu
 struct XYZZ;
 void dist_range(uint64_t n, int rank, int world, uint64_t* lo, uint64_t* hi);
+void dist_column_block(uint32_t count, int rank, int world, uint32_t* lo, uint32_t* hi, uint32_t* per_rank);
 int32_t dist_sum_points(zk_ctx* ctx, XYZZ* results, int nb);
 // recv[r * bytes .. (r + 1) * bytes) <- rank r's send buffer (device pointers), on the context's stream
 int32_t dist_allgather_device(zk_ctx* ctx, const void* send, void* recv, size_t bytes);
