@@ -97,10 +97,12 @@ __device__ __forceinline__ uint32_t aggregated_add(uint32_t* counters, uint32_t 
   return base;
 }
 
-// entries_tmp[((job * nwin + w) * stride) + t] = bucket + 1 | sign << 31   (0 = no entry)
+// entries_tmp[((job * nwin + w) * stride) + t] = bucket + 1 | sign << 31   (0 = no entry);
+// ranks_tmp[same index] = the entry's position inside its bucket: the value the histogram increment returned,
+// so the scatter needs no second round of atomics
 __global__ void fixed_digits_kernel(DevJobs jobs, uint64_t count, uint64_t lo, const Fp* __restrict__ extra, int c,
                                     int nwin, uint64_t stride, uint32_t B, uint32_t* __restrict__ entries_tmp,
-                                    uint32_t* __restrict__ counts) {
+                                    uint32_t* __restrict__ ranks_tmp, uint32_t* __restrict__ counts) {
   const int job = blockIdx.y;
   uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   const uint64_t total = count + jobs.n_extra[job];
@@ -121,6 +123,7 @@ __global__ void fixed_digits_kernel(DevJobs jobs, uint64_t count, uint64_t lo, c
   }
   uint32_t* my_counts = counts + (size_t)job * B;
   uint32_t* my_tmp = entries_tmp + (size_t)job * nwin * stride + t;
+  uint32_t* my_rank = ranks_tmp + (size_t)job * nwin * stride + t;
   uint32_t carry = 0;
   for (int w = 0; w < nwin; w++) {
     uint32_t e = 0;
@@ -139,7 +142,8 @@ __global__ void fixed_digits_kernel(DevJobs jobs, uint64_t count, uint64_t lo, c
       }
     }
     my_tmp[(size_t)w * stride] = e;
-    aggregated_add(my_counts, (e & 0x7fffffffu) - 1, e != 0);
+    const uint32_t rank = aggregated_add(my_counts, (e & 0x7fffffffu) - 1, e != 0);
+    if (e) my_rank[(size_t)w * stride] = rank;
   }
 }
 
@@ -222,23 +226,24 @@ __global__ void fscan_add_kernel(uint32_t* __restrict__ out, const uint32_t* __r
 }
 
 // scatter: sorted[pos] = table entry index (w * npoints + point) | sign << 31
-__global__ void fixed_scatter_kernel(DevJobs jobs, const uint32_t* __restrict__ entries_tmp, uint64_t count,
+__global__ void fixed_scatter_kernel(DevJobs jobs, const uint32_t* __restrict__ entries_tmp,
+                                     const uint32_t* __restrict__ ranks_tmp, uint64_t count,
                                      const uint32_t* __restrict__ extra_index, int nwin, uint64_t stride,
                                      uint64_t npoints, uint32_t B, const uint32_t* __restrict__ offsets,
-                                     uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
+                                     uint32_t* __restrict__ sorted) {
   const int job = blockIdx.y;
   uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   const uint64_t total = count + jobs.n_extra[job];
   if (t >= total) return;
   const uint32_t point = t < count ? (uint32_t)t : extra_index[job * 4 + (t - count)];  // local indices
   const uint32_t* my_tmp = entries_tmp + (size_t)job * nwin * stride + t;
-  uint32_t* my_cursor = cursor + (size_t)job * B;
+  const uint32_t* my_rank = ranks_tmp + (size_t)job * nwin * stride + t;
   const uint32_t* my_offsets = offsets + (size_t)job * B;
   for (int w = 0; w < nwin; w++) {
     const uint32_t e = my_tmp[(size_t)w * stride];
-    const uint32_t bucket = (e & 0x7fffffffu) - 1;
-    const uint32_t rank = aggregated_add(my_cursor, bucket, e != 0);
-    if (e) sorted[my_offsets[bucket] + rank] = (uint32_t)((uint64_t)w * npoints + point) | (e & 0x80000000u);
+    if (e)
+      sorted[my_offsets[(e & 0x7fffffffu) - 1] + my_rank[(size_t)w * stride]] =
+          (uint32_t)((uint64_t)w * npoints + point) | (e & 0x80000000u);
   }
 }
 
@@ -507,8 +512,8 @@ int32_t msm_fixed_batch(zk_ctx* ctx, const FixedBase& fb, const MsmJob* jobs, in
     off += (bytes + 255) / 256 * 256;
     return o;
   };
-  const size_t o_tmp = take(max_entries * 4), o_counts = take((size_t)NB * 4), o_offsets = take((size_t)(NB + 1) * 4),
-               o_cursor = take((size_t)NB * 4), o_tiles = take((size_t)ntiles * 4 + 16), o_sorted = take(max_entries * 4 + 16),
+  const size_t o_tmp = take(max_entries * 4), o_ranks = take(max_entries * 4), o_counts = take((size_t)NB * 4), o_offsets = take((size_t)(NB + 1) * 4),
+               o_tiles = take((size_t)ntiles * 4 + 16), o_sorted = take(max_entries * 4 + 16),
                o_plan = take(sizeof(Plan)), o_heads = take((size_t)max_chunks * sizeof(XYZZ)),
                o_hitems = take((size_t)max_items * sizeof(HeavyItem)),
                o_hb = take((size_t)max_hbuckets * sizeof(HeavyBucket)),
@@ -520,7 +525,7 @@ int32_t msm_fixed_batch(zk_ctx* ctx, const FixedBase& fb, const MsmJob* jobs, in
   if (rc) return rc;
   char* ws = (char*)ctx->msm_ws.ptr;
   uint32_t *tmp = (uint32_t*)(ws + o_tmp), *counts = (uint32_t*)(ws + o_counts), *offsets = (uint32_t*)(ws + o_offsets),
-           *cursor = (uint32_t*)(ws + o_cursor), *tiles = (uint32_t*)(ws + o_tiles), *sorted = (uint32_t*)(ws + o_sorted),
+           *ranks = (uint32_t*)(ws + o_ranks), *tiles = (uint32_t*)(ws + o_tiles), *sorted = (uint32_t*)(ws + o_sorted),
            *eidx = (uint32_t*)(ws + o_eidx);
   Plan* plan = (Plan*)(ws + o_plan);
   HeavyItem* hitems = (HeavyItem*)(ws + o_hitems);
@@ -557,16 +562,15 @@ int32_t msm_fixed_batch(zk_ctx* ctx, const FixedBase& fb, const MsmJob* jobs, in
     ZK_CUDA(ctx, cudaMemcpyAsync(eidx, h_eidx, sizeof(h_eidx), cudaMemcpyHostToDevice, st));
   }
   ZK_CUDA(ctx, cudaMemsetAsync(counts, 0, (size_t)NB * 4, st));
-  ZK_CUDA(ctx, cudaMemsetAsync(cursor, 0, (size_t)NB * 4, st));
   {
     KernelTimer timer(ctx, KC_MSM);
     const int T = 256;
     const dim3 gt((unsigned)((stride + T - 1) / T), (unsigned)nb);
-    fixed_digits_kernel<<<gt, T, 0, st>>>(dj, count, fb.lo, d_extra, c, nwin, stride, B, tmp, counts);
+    fixed_digits_kernel<<<gt, T, 0, st>>>(dj, count, fb.lo, d_extra, c, nwin, stride, B, tmp, ranks, counts);
     fscan_tiles_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(counts, offsets, tiles, NB);
     fscan_sums_kernel<<<1, 1024, 0, st>>>(tiles, ntiles);
     fscan_add_kernel<<<(NB + T - 1) / T, T, 0, st>>>(offsets, tiles, counts, NB, resident, plan);
-    fixed_scatter_kernel<<<gt, T, 0, st>>>(dj, tmp, count, eidx, nwin, stride, fb.npoints, B, offsets, cursor, sorted);
+    fixed_scatter_kernel<<<gt, T, 0, st>>>(dj, tmp, ranks, count, eidx, nwin, stride, fb.npoints, B, offsets, sorted);
     {
       KernelTimer acc_timer(ctx, KC_MSM_ACC);
       fixed_accumulate_kernel<<<acc_grid, ACC_THREADS, 0, st>>>(fb.table, sorted, offsets, NB, plan, heads, buckets);

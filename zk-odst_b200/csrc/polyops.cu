@@ -4,113 +4,173 @@
 namespace zkodst {
 
 // ---- affine recurrence scan ----------------------------------------------------------------------
-__global__ void affine_up_kernel(const Fp* __restrict__ m, Fp m_const, const Fp* __restrict__ a, uint64_t n,
-                                 AffinePair* __restrict__ agg, uint64_t nchunks) {
-  uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (c >= nchunks) return;
-  uint64_t lo = c * SCAN_CH, hi = lo + SCAN_CH < n ? lo + SCAN_CH : n;
-  Fp M = Fp::one(), A = Fp::zero();
+// Three launches whatever n: every block composes its tile of SCAN_T x SCAN_E elements into one affine
+// map (thread-serial over SCAN_E elements, shuffle scan inside the warp, one more across the warps); one
+// block scans the per-tile maps and applies them to `init`; every block then rebuilds its threads'
+// exclusive prefixes the same way, starts from its tile's carry and writes the outputs.
+namespace {
+constexpr int SCAN_T = 256, SCAN_E = 8, SCAN_TILE = SCAN_T * SCAN_E;
+
+__device__ __forceinline__ Fp shfl_up_fp(const Fp& v, int d) {
+  Fp r;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const uint32_t lo = __shfl_up_sync(0xffffffffu, (uint32_t)v.l[i], d);
+    const uint32_t hi = __shfl_up_sync(0xffffffffu, (uint32_t)(v.l[i] >> 32), d);
+    r.l[i] = ((uint64_t)hi << 32) | lo;
+  }
+  return r;
+}
+// (M, A) <- first (M1, A1) then (M, A):  y -> (y M1 + A1) M + A
+template <bool HAS_A>
+__device__ __forceinline__ void compose_before(Fp& M, Fp& A, const Fp& M1, const Fp& A1) {
+  if (HAS_A) A = A1 * M + A;
+  M = M1 * M;
+}
+// the thread's own elements as one map
+template <bool HAS_A>
+__device__ __forceinline__ void thread_map(const Fp* __restrict__ m, const Fp& m_const, const Fp* __restrict__ a,
+                                           uint64_t lo, uint64_t hi, Fp& M, Fp& A) {
+  M = Fp::one();
+  A = Fp::zero();
   for (uint64_t i = lo; i < hi; i++) {
-    Fp mi = m ? m[i] : m_const;
+    const Fp mi = m ? m[i] : m_const;
+    if (HAS_A) A = A * mi + a[i];
     M = M * mi;
-    if (a) A = A * mi + a[i];
   }
-  agg[c] = AffinePair{M, A};
 }
-__global__ void affine_up_pairs_kernel(const AffinePair* __restrict__ in, uint64_t n,
-                                       AffinePair* __restrict__ agg, uint64_t nchunks) {
-  uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (c >= nchunks) return;
-  uint64_t lo = c * SCAN_CH, hi = lo + SCAN_CH < n ? lo + SCAN_CH : n;
-  Fp M = Fp::one(), A = Fp::zero();
+// Inclusive scan of the threads' maps over the block, in thread order; afterwards (M, A) of thread t is the
+// composition of threads 0..t.  `excl` additionally returns the composition of threads 0..t-1.
+template <bool HAS_A>
+__device__ __forceinline__ void block_scan_maps(Fp& M, Fp& A, Fp* exclM, Fp* exclA) {
+  __shared__ Fp wM[SCAN_T / 32], wA[SCAN_T / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const Fp pM = shfl_up_fp(M, d);
+    Fp pA;
+    if (HAS_A) pA = shfl_up_fp(A, d);
+    if (lane >= d) compose_before<HAS_A>(M, A, pM, pA);
+  }
+  if (lane == 31) {
+    wM[warp] = M;
+    if (HAS_A) wA[warp] = A;
+  }
+  __syncthreads();
+  if (warp == 0) {  // inclusive scan of the SCAN_T / 32 warp totals
+    Fp tM = lane < SCAN_T / 32 ? wM[lane] : Fp::one(), tA = Fp::zero();
+    if (HAS_A && lane < SCAN_T / 32) tA = wA[lane];
+#pragma unroll
+    for (int d = 1; d < SCAN_T / 32; d <<= 1) {
+      const Fp pM = shfl_up_fp(tM, d);
+      Fp pA;
+      if (HAS_A) pA = shfl_up_fp(tA, d);
+      if (lane >= d) compose_before<HAS_A>(tM, tA, pM, pA);
+    }
+    if (lane < SCAN_T / 32) {
+      wM[lane] = tM;
+      if (HAS_A) wA[lane] = tA;
+    }
+  }
+  __syncthreads();
+  if (warp > 0) compose_before<HAS_A>(M, A, wM[warp - 1], HAS_A ? wA[warp - 1] : Fp::zero());
+  if (exclM) {  // exclusive = inclusive of the previous thread
+    Fp eM = shfl_up_fp(M, 1), eA = Fp::zero();
+    if (HAS_A) eA = shfl_up_fp(A, 1);
+    if (lane == 0) {
+      eM = warp > 0 ? wM[warp - 1] : Fp::one();
+      eA = (HAS_A && warp > 0) ? wA[warp - 1] : Fp::zero();
+    }
+    *exclM = eM;
+    *exclA = eA;
+  }
+}
+
+template <bool HAS_A>
+__global__ void __launch_bounds__(SCAN_T) affine_tile_up_kernel(const Fp* __restrict__ m, Fp m_const,
+                                                               const Fp* __restrict__ a, uint64_t n,
+                                                               AffinePair* __restrict__ agg) {
+  const uint64_t lo = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_E;
+  const uint64_t hi = lo + SCAN_E < n ? lo + SCAN_E : n;
+  Fp M, A;
+  thread_map<HAS_A>(m, m_const, a, lo < n ? lo : n, hi, M, A);
+  block_scan_maps<HAS_A>(M, A, nullptr, nullptr);
+  if (threadIdx.x == SCAN_T - 1) agg[blockIdx.x] = AffinePair{M, A};
+}
+
+// one block: carry[b] = init pushed through tiles 0..b-1
+template <bool HAS_A>
+__global__ void __launch_bounds__(SCAN_T) affine_tile_carry_kernel(const AffinePair* __restrict__ agg, uint64_t ntiles,
+                                                                  const Fp* __restrict__ init,
+                                                                  Fp* __restrict__ carry) {
+  __shared__ Fp run;  // value entering the current group of SCAN_T tiles
+  if (threadIdx.x == 0) run = *init;
+  __syncthreads();
+  for (uint64_t base = 0; base < ntiles; base += SCAN_T) {
+    const uint64_t b = base + threadIdx.x;
+    Fp M = Fp::one(), A = Fp::zero();
+    if (b < ntiles) {
+      M = agg[b].m;
+      if (HAS_A) A = agg[b].a;
+    }
+    Fp eM, eA;
+    block_scan_maps<HAS_A>(M, A, &eM, &eA);
+    const Fp start = run;
+    if (b < ntiles) carry[b] = HAS_A ? start * eM + eA : start * eM;
+    __syncthreads();
+    if (threadIdx.x == SCAN_T - 1) run = HAS_A ? start * M + A : start * M;
+    __syncthreads();
+  }
+}
+
+template <bool HAS_A>
+__global__ void __launch_bounds__(SCAN_T) affine_tile_down_kernel(const Fp* __restrict__ m, Fp m_const,
+                                                                 const Fp* __restrict__ a, uint64_t n,
+                                                                 const Fp* __restrict__ carry, Fp* __restrict__ out) {
+  const uint64_t lo0 = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_E;
+  const uint64_t lo = lo0 < n ? lo0 : n, hi = lo0 + SCAN_E < n ? lo0 + SCAN_E : n;
+  Fp M, A, eM, eA;
+  thread_map<HAS_A>(m, m_const, a, lo, hi, M, A);
+  block_scan_maps<HAS_A>(M, A, &eM, &eA);
+  const Fp c = carry[blockIdx.x];
+  Fp y = HAS_A ? c * eM + eA : c * eM;
   for (uint64_t i = lo; i < hi; i++) {
-    AffinePair p = in[i];
-    M = M * p.m;
-    A = A * p.m + p.a;
-  }
-  agg[c] = AffinePair{M, A};
-}
-__global__ void affine_down_kernel(const Fp* __restrict__ m, Fp m_const, const Fp* __restrict__ a, uint64_t n,
-                                   const Fp* __restrict__ carry, Fp* __restrict__ out, uint64_t nchunks) {
-  uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (c >= nchunks) return;
-  uint64_t lo = c * SCAN_CH, hi = lo + SCAN_CH < n ? lo + SCAN_CH : n;
-  Fp y = carry[c];
-  for (uint64_t i = lo; i < hi; i++) {
-    Fp mi = m ? m[i] : m_const;
-    Fp ai = a ? a[i] : Fp::zero();
-    out[i] = y;  // exclusive; out may alias m or a (each element is read before it is written)
-    y = y * mi + ai;
+    const Fp mi = m ? m[i] : m_const;
+    Fp ai;
+    if (HAS_A) ai = a[i];
+    out[i] = y;  // exclusive; out may alias m or a (an element is read, by its own thread, before it is written)
+    y = HAS_A ? y * mi + ai : y * mi;
   }
 }
-__global__ void affine_down_pairs_kernel(const AffinePair* __restrict__ in, uint64_t n,
-                                         const Fp* __restrict__ carry, Fp* __restrict__ out, uint64_t nchunks) {
-  uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (c >= nchunks) return;
-  uint64_t lo = c * SCAN_CH, hi = lo + SCAN_CH < n ? lo + SCAN_CH : n;
-  Fp y = carry[c];
-  for (uint64_t i = lo; i < hi; i++) {
-    AffinePair p = in[i];
-    out[i] = y;
-    y = y * p.m + p.a;
+
+template <bool HAS_A>
+int32_t affine_scan_impl(zk_ctx* ctx, const Fp* m, const Fp& m_const, const Fp* a, uint64_t n, const Fp& init,
+                         Fp* out) {
+  const uint64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  int32_t rc = ensure_buf(ctx, ctx->scan_ws, ntiles * (sizeof(AffinePair) + sizeof(Fp)) + sizeof(Fp));
+  if (rc) return rc;
+  AffinePair* agg = (AffinePair*)ctx->scan_ws.ptr;
+  Fp* carry = (Fp*)(agg + ntiles);
+  Fp* d_init = carry + ntiles;
+  cudaStream_t st = ctx->stream;
+  ZK_CUDA(ctx, cudaMemcpyAsync(d_init, &init, sizeof(Fp), cudaMemcpyHostToDevice, st));
+  if (ntiles > 1) {
+    affine_tile_up_kernel<HAS_A><<<(unsigned)ntiles, SCAN_T, 0, st>>>(m, m_const, a, n, agg);
+    affine_tile_carry_kernel<HAS_A><<<1, SCAN_T, 0, st>>>(agg, ntiles, d_init, carry);
+    ctx->launches += 2;
   }
+  affine_tile_down_kernel<HAS_A><<<(unsigned)ntiles, SCAN_T, 0, st>>>(m, m_const, a, n, ntiles > 1 ? carry : d_init, out);
+  ctx->launches++;
+  ZK_CUDA(ctx, cudaGetLastError());
+  return ZK_OK;
 }
+}  // namespace
 
 int32_t affine_scan(zk_ctx* ctx, const Fp* m, const Fp& m_const, const Fp* a, uint64_t n, const Fp& init,
                     Fp* out) {
   if (n == 0) return ZK_OK;
-  // level sizes: sz[0] = n elements, sz[l] = chunks of level l-1
-  uint64_t sz[8];
-  int levels = 0;
-  sz[0] = n;
-  while (sz[levels] > 1) {
-    sz[levels + 1] = (sz[levels] + SCAN_CH - 1) / SCAN_CH;
-    levels++;
-  }
-  // workspace: pairs for levels 1..levels, carries for levels 1..levels (+1 slot for init)
-  size_t off = 0, pair_off[8], carry_off[8];
-  for (int l = 1; l <= levels; l++) {
-    pair_off[l] = off;
-    off += sz[l] * sizeof(AffinePair);
-  }
-  for (int l = 1; l <= levels; l++) {
-    carry_off[l] = off;
-    off += sz[l] * sizeof(Fp);
-  }
-  size_t init_off = off;
-  off += sizeof(Fp);
-  int32_t rc = ensure_buf(ctx, ctx->scan_ws, off);
-  if (rc) return rc;
-  char* ws = (char*)ctx->scan_ws.ptr;
-  auto pairs = [&](int l) { return (AffinePair*)(ws + pair_off[l]); };
-  auto carry = [&](int l) { return (Fp*)(ws + carry_off[l]); };
-  Fp* d_init = (Fp*)(ws + init_off);
-  cudaStream_t st = ctx->stream;
-  ZK_CUDA(ctx, cudaMemcpyAsync(d_init, &init, sizeof(Fp), cudaMemcpyHostToDevice, st));
-  const int T = 128;
-  if (levels == 0) {  // n == 1
-    affine_down_kernel<<<1, 1, 0, st>>>(m, m_const, a, n, d_init, out, 1);
-    ctx->launches++;
-    return ZK_OK;
-  }
-  affine_up_kernel<<<(unsigned)((sz[1] + T - 1) / T), T, 0, st>>>(m, m_const, a, n, pairs(1), sz[1]);
-  ctx->launches++;
-  for (int l = 2; l <= levels; l++) {
-    affine_up_pairs_kernel<<<(unsigned)((sz[l] + T - 1) / T), T, 0, st>>>(pairs(l - 1), sz[l - 1], pairs(l), sz[l]);
-    ctx->launches++;
-  }
-  // top level has one chunk: its carry is init
-  const Fp* c_in = d_init;
-  for (int l = levels; l >= 2; l--) {
-    affine_down_pairs_kernel<<<(unsigned)((sz[l] + T - 1) / T), T, 0, st>>>(pairs(l - 1), sz[l - 1], c_in,
-                                                                          carry(l - 1), sz[l]);
-    ctx->launches++;
-    c_in = carry(l - 1);
-  }
-  affine_down_kernel<<<(unsigned)((sz[1] + T - 1) / T), T, 0, st>>>(m, m_const, a, n, c_in, out, sz[1]);
-  ctx->launches++;
-  ZK_CUDA(ctx, cudaGetLastError());
-  return ZK_OK;
+  return a ? affine_scan_impl<true>(ctx, m, m_const, a, n, init, out)
+           : affine_scan_impl<false>(ctx, m, m_const, nullptr, n, init, out);
 }
 
 // ---- batched inversion ---------------------------------------------------------------------------

@@ -30,22 +30,10 @@ inline void launch_map(zk_ctx* ctx, uint64_t n, F f, int threads = 256) {
 // y_0 = init;  y_{i+1} = y_i * m_i + a_i      (i = 0 .. n-1), output y_0 .. y_{n-1}  (exclusive)
 // With a == nullptr the recurrence is the running product used by the permutation and lookup
 // grand products; with a constant multiplier it is Horner / synthetic division.
-// Three levels of chunked scans (chunk = 32): up-sweep aggregates (M, A), then down-sweep.
+// Tile-wise scan in three launches (polyops.cu).
 struct AffinePair {
   Fp m, a;
 };
-constexpr int SCAN_CH = 32;
-
-// aggregates of chunk c: composition of its elements
-__global__ void affine_up_kernel(const Fp* __restrict__ m, Fp m_const, const Fp* __restrict__ a, uint64_t n,
-                                 AffinePair* __restrict__ agg, uint64_t nchunks);
-__global__ void affine_up_pairs_kernel(const AffinePair* __restrict__ in, uint64_t n,
-                                       AffinePair* __restrict__ agg, uint64_t nchunks);
-// down-sweep: chunk c starts from carry[c] and writes exclusive outputs
-__global__ void affine_down_kernel(const Fp* __restrict__ m, Fp m_const, const Fp* __restrict__ a, uint64_t n,
-                                   const Fp* __restrict__ carry, Fp* __restrict__ out, uint64_t nchunks);
-__global__ void affine_down_pairs_kernel(const AffinePair* __restrict__ in, uint64_t n,
-                                         const Fp* __restrict__ carry, Fp* __restrict__ out, uint64_t nchunks);
 
 // Host driver.  m may be nullptr (use m_const); a may be nullptr (zero).  out may alias m or a.
 int32_t affine_scan(zk_ctx* ctx, const Fp* m, const Fp& m_const, const Fp* a, uint64_t n, const Fp& init,
