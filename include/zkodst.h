@@ -217,6 +217,13 @@ int32_t zk_dist_range(uint64_t n_points, int32_t rank, int32_t world, uint64_t* 
  * padded to per_rank * world slots, are all-gathered in place.  Host-only helper. */
 #define ZK_NUM_WITNESS_COLUMNS 19
 int32_t zk_dist_column_block(int32_t rank, int32_t world, uint32_t* lo, uint32_t* hi, uint32_t* per_rank);
+/* How a group shards the quotient: `rank` evaluates rows [*row_lo, *row_hi) of the coset-major 3n-row
+ * domain (3n / world rows; ZK_E_INVALID when world does not divide 3n) and, because a row reads its
+ * rotations -1, +1, -6 inside its own coset, needs the rows listed in `segments` (pairs start, length;
+ * sorted, disjoint) of every column — the rows the other ranks send it.  *n_segments: in = capacity in
+ * pairs, out = pairs needed (ZK_E_BUFFER if short).  Host-only helper. */
+int32_t zk_dist_quotient_rows(uint64_t n, int32_t rank, int32_t world, uint64_t* row_lo, uint64_t* row_hi,
+                              uint64_t* segments, uint32_t* n_segments);
 
 #ifdef __cplusplus
 }

@@ -55,5 +55,7 @@ extern "C" {
     pub fn zk_dist_info(ctx: *const zk_ctx, rank: *mut i32, world: *mut i32) -> i32;
     pub fn zk_dist_range(n_points: u64, rank: i32, world: i32, lo: *mut u64, hi: *mut u64) -> i32;
     pub fn zk_dist_column_block(rank: i32, world: i32, lo: *mut u32, hi: *mut u32, per_rank: *mut u32) -> i32;
+    pub fn zk_dist_quotient_rows(n: u64, rank: i32, world: i32, row_lo: *mut u64, row_hi: *mut u64,
+        segments: *mut u64, n_segments: *mut u32) -> i32;
 }
 pub const ZK_DIST_ID_BYTES: usize = 128;

@@ -127,3 +127,32 @@ def test_column_sharded_transforms_world2(tmp_path):
     mp.spawn(_column_worker, args=(2, port, out), nprocs=2, join=True)
     for r in range(2):
         assert open(out + ".%d" % r).read() == "ok"
+
+
+def test_quotient_row_segments_cover_the_rotations():
+    """zk_dist_quotient_rows: the segments a rank receives are exactly the rows its share of the quotient
+    reads — every row of its range and the rotations -1, +1, -6 inside the row's own coset — and the
+    ranks' ranges tile the 3n-row domain."""
+    import zk_odst_b200 as zk
+    for n in (16, 64, 1 << 10):
+        for world in (1, 2, 3, 4, 6, 8):
+            if (3 * n) % world:
+                continue
+            prev = 0
+            for r in range(world):
+                (lo, hi), segs = zk.dist_quotient_rows(n, r, world)
+                assert lo == prev and hi - lo == 3 * n // world
+                prev = hi
+                need = set()
+                for i in range(lo, hi):
+                    c, row = divmod(i, n)
+                    for rot in (0, -1, 1, -6):
+                        need.add(c * n + (row + rot) % n)
+                got = set()
+                last_end = -1
+                for start, length in segs:
+                    assert length > 0 and start > last_end  # sorted, disjoint, not even adjacent
+                    last_end = start + length
+                    got.update(range(start, start + length))
+                assert got == need, (n, world, r)
+            assert prev == 3 * n

@@ -18,5 +18,6 @@ from .binding import (  # noqa: F401
     blake2b_records,
     dist_range,
     dist_column_block,
+    dist_quotient_rows,
 )
 from .inputs import eip152_record, synthetic_inputs, XorShiftRng, REFERENCE_SEED  # noqa: F401

@@ -68,6 +68,8 @@ def load_library():
             "zk_dist_init": (i32, [vp, c.c_char_p, i32, i32]),
             "zk_dist_info": (i32, [vp, c.POINTER(i32), c.POINTER(i32)]),
             "zk_dist_range": (i32, [u64, i32, i32, c.POINTER(u64), c.POINTER(u64)]),
+            "zk_dist_quotient_rows": (i32, [u64, i32, i32, c.POINTER(u64), c.POINTER(u64), c.POINTER(u64),
+                                            c.POINTER(c.c_uint32)]),
             "zk_dist_column_block": (i32, [i32, i32, c.POINTER(c.c_uint32), c.POINTER(c.c_uint32),
                                            c.POINTER(c.c_uint32)]),
         }
@@ -136,6 +138,18 @@ def dist_column_block(rank, world):
     if rc:
         raise ZkError(rc)
     return lo.value, hi.value, per.value
+
+
+def dist_quotient_rows(n, rank, world):
+    """((row_lo, row_hi), [(start, length), ...]): the quotient rows `rank` evaluates and the row segments
+    of every coset column it reads (zk_dist_quotient_rows)."""
+    lib = load_library()
+    lo, hi, cnt = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint32(16)
+    segs = (ctypes.c_uint64 * 32)()
+    rc = lib.zk_dist_quotient_rows(n, rank, world, ctypes.byref(lo), ctypes.byref(hi), segs, ctypes.byref(cnt))
+    if rc:
+        raise ZkError(rc)
+    return (lo.value, hi.value), [(segs[2 * i], segs[2 * i + 1]) for i in range(cnt.value)]
 
 
 def rows_per_compression(rounds):

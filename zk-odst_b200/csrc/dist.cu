@@ -9,7 +9,9 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <algorithm>
 #include <cstring>
+#include <utility>
 #include <vector>
 
 #include "ec.cuh"
@@ -23,6 +25,10 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   bool ok = false;
@@ -39,9 +45,14 @@ NcclApi& nccl() {
     a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(a.lib, "ncclGetUniqueId");
     a.CommInitRank = (decltype(a.CommInitRank))dlsym(a.lib, "ncclCommInitRank");
     a.AllGather = (decltype(a.AllGather))dlsym(a.lib, "ncclAllGather");
+    a.Send = (decltype(a.Send))dlsym(a.lib, "ncclSend");
+    a.Recv = (decltype(a.Recv))dlsym(a.lib, "ncclRecv");
+    a.GroupStart = (decltype(a.GroupStart))dlsym(a.lib, "ncclGroupStart");
+    a.GroupEnd = (decltype(a.GroupEnd))dlsym(a.lib, "ncclGroupEnd");
     a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.lib, "ncclCommDestroy");
     a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.lib, "ncclGetErrorString");
-    a.ok = a.GetUniqueId && a.CommInitRank && a.AllGather && a.CommDestroy && a.GetErrorString;
+    a.ok = a.GetUniqueId && a.CommInitRank && a.AllGather && a.Send && a.Recv && a.GroupStart && a.GroupEnd &&
+           a.CommDestroy && a.GetErrorString;
     return a;
   }();
   return api;
@@ -66,6 +77,95 @@ void dist_column_block(uint32_t count, int rank, int world, uint32_t* lo, uint32
   *per_rank = per;
   *lo = first < count ? first : count;
   *hi = first + per < count ? first + per : count;
+}
+
+// Rows of the coset-major quotient domain (NUM_COSETS cosets of n rows) that evaluating rows [lo, hi) reads:
+// a row reads itself and its rotations -1, +1 and -(blinding + 1) = -6 inside its own coset (quotient.cu),
+// so per coset the local range [a, b) needs [a - 6, b + 1) modulo n.  Sorted, merged (start, length) pairs.
+void dist_quotient_segments(uint64_t n, uint64_t lo, uint64_t hi, std::vector<std::pair<uint64_t, uint64_t>>& out) {
+  constexpr int64_t BACK = 6, FWD = 1;
+  std::vector<std::pair<uint64_t, uint64_t>> iv;  // [start, end) absolute
+  const int64_t N = (int64_t)n;
+  // local interval [s, e) of coset c (s may be negative, e may exceed n), wrapped into the coset
+  auto add = [&](uint64_t c0, int64_t s_, int64_t e_) {
+    if (e_ - s_ >= N) {
+      iv.push_back({c0, c0 + n});
+      return;
+    }
+    if (e_ <= 0) {
+      s_ += N;
+      e_ += N;
+    } else if (s_ >= N) {
+      s_ -= N;
+      e_ -= N;
+    }
+    if (s_ < 0) {
+      iv.push_back({c0 + (uint64_t)(N + s_), c0 + n});
+      s_ = 0;
+    }
+    if (e_ > N) {
+      iv.push_back({c0, c0 + (uint64_t)(e_ - N)});
+      e_ = N;
+    }
+    if (s_ < e_) iv.push_back({c0 + (uint64_t)s_, c0 + (uint64_t)e_});
+  };
+  for (uint64_t c = 0; c * n < hi; c++) {
+    const uint64_t c0 = c * n, c1 = c0 + n;
+    if (c1 <= lo) continue;
+    const int64_t a = (int64_t)((lo > c0 ? lo : c0) - c0), b = (int64_t)((hi < c1 ? hi : c1) - c0);
+    if (a >= b) continue;
+    add(c0, a - 1, b + FWD);     // the rows themselves and their rotations -1, +1
+    add(c0, a - BACK, b - BACK);  // rotation -(blinding + 1)
+  }
+  std::sort(iv.begin(), iv.end());
+  out.clear();
+  for (auto& v : iv) {
+    if (!out.empty() && v.first <= out.back().first + out.back().second) {
+      const uint64_t end = v.second > out.back().first + out.back().second ? v.second : out.back().first + out.back().second;
+      out.back().second = end - out.back().first;
+    } else {
+      out.push_back({v.first, v.second - v.first});
+    }
+  }
+}
+
+// Column-sharded coset arrays -> row-sharded quotient input.  `slots` holds nslots arrays of `en` rows each
+// (en = NUM_COSETS * n); this rank has filled the whole arrays of its own column block and evaluates the
+// quotient on rows [rank * en / world, (rank + 1) * en / world).  Every rank sends each peer the row segments
+// that peer reads, of the columns it owns, and receives its own segments of the peers' columns in place:
+// en / world rows (plus a 7-row halo per coset) of every column arrive, instead of every column in full.
+int32_t dist_exchange_quotient_rows(zk_ctx* ctx, char* slots, size_t elem_bytes, uint64_t n, uint64_t en,
+                                    uint32_t nslots) {
+  const int world = ctx->dist_world, me = ctx->dist_rank;
+  if (world <= 1) return ZK_OK;
+  const uint64_t rows = en / (uint64_t)world;
+  std::vector<std::vector<std::pair<uint64_t, uint64_t>>> segs(world);
+  for (int q = 0; q < world; q++) dist_quotient_segments(n, rows * q, rows * (q + 1), segs[q]);
+  ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+  ncclResult_t r = nccl().GroupStart();
+  if (r != ncclSuccess) return nccl_error(ctx, r, "ncclGroupStart");
+  for (int q = 0; q < world && r == ncclSuccess; q++) {
+    if (q == me) continue;
+    uint32_t lo, hi, per;
+    dist_column_block(nslots, me, world, &lo, &hi, &per);
+    for (uint32_t s = lo; s < hi && r == ncclSuccess; s++)
+      for (auto& g : segs[q]) {
+        r = nccl().Send(slots + ((size_t)s * en + g.first) * elem_bytes, g.second * elem_bytes, ncclUint8, q, comm,
+                        ctx->stream);
+        if (r != ncclSuccess) break;
+      }
+    dist_column_block(nslots, q, world, &lo, &hi, &per);
+    for (uint32_t s = lo; s < hi && r == ncclSuccess; s++)
+      for (auto& g : segs[me]) {
+        r = nccl().Recv(slots + ((size_t)s * en + g.first) * elem_bytes, g.second * elem_bytes, ncclUint8, q, comm,
+                        ctx->stream);
+        if (r != ncclSuccess) break;
+      }
+  }
+  const ncclResult_t e = nccl().GroupEnd();
+  if (r != ncclSuccess) return nccl_error(ctx, r, "ncclSend/ncclRecv");
+  if (e != ncclSuccess) return nccl_error(ctx, e, "ncclGroupEnd");
+  return ZK_OK;
 }
 
 // results[m] <- sum over ranks of their results[m]; identical on every rank afterwards
@@ -156,5 +256,25 @@ extern "C" int32_t zk_dist_range(uint64_t n_points, int32_t rank, int32_t world,
 extern "C" int32_t zk_dist_column_block(int32_t rank, int32_t world, uint32_t* lo, uint32_t* hi, uint32_t* per_rank) {
   if (!lo || !hi || !per_rank || world < 1 || rank < 0 || rank >= world) return ZK_E_INVALID;
   dist_column_block(ZK_NUM_WITNESS_COLUMNS, rank, world, lo, hi, per_rank);
+  return ZK_OK;
+}
+
+extern "C" int32_t zk_dist_quotient_rows(uint64_t n, int32_t rank, int32_t world, uint64_t* row_lo, uint64_t* row_hi,
+                                         uint64_t* segments, uint32_t* n_segments) {
+  if (!row_lo || !row_hi || !n_segments || world < 1 || rank < 0 || rank >= world || n == 0) return ZK_E_INVALID;
+  const uint64_t en = 3 * n;  // NUM_COSETS cosets of the n-th roots (prover_state.h)
+  if (en % (uint64_t)world) return ZK_E_INVALID;
+  const uint64_t rows = en / (uint64_t)world;
+  *row_lo = rows * (uint64_t)rank;
+  *row_hi = *row_lo + rows;
+  std::vector<std::pair<uint64_t, uint64_t>> segs;
+  dist_quotient_segments(n, *row_lo, *row_hi, segs);
+  const uint32_t cap = *n_segments;
+  *n_segments = (uint32_t)segs.size();
+  if (!segments || cap < segs.size()) return ZK_E_BUFFER;
+  for (size_t i = 0; i < segs.size(); i++) {
+    segments[2 * i] = segs[i].first;
+    segments[2 * i + 1] = segs[i].second;
+  }
   return ZK_OK;
 }

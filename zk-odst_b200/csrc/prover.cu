@@ -621,10 +621,19 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
       c.out_stride2 = en;
       if ((rc = ntt_run(ctx, W->polys_all + slot_lo * n, (uint32_t)n, W->cosets_all + slot_lo * en, k, c))) return rc;
     }
+    // coefficients: every rank needs every column in full (evaluations, multiopen) -> in-place all-gather.
+    // coset values: every rank needs only the rows of its share of the quotient -> row segments exchanged
+    // point to point (world x less traffic than gathering the columns in full)
+    const bool shard_rows = world > 1 && en % (uint64_t)world == 0;
     if (world > 1) {
       if ((rc = dist_allgather_device(ctx, W->polys_all + send_slot * n, W->polys_all, spr * n * sizeof(Fp)))) return rc;
-      if ((rc = dist_allgather_device(ctx, W->cosets_all + send_slot * en, W->cosets_all, spr * en * sizeof(Fp))))
+      if (shard_rows) {
+        if ((rc = dist_exchange_quotient_rows(ctx, (char*)W->cosets_all, sizeof(Fp), n, en, NUM_WITNESS_POLYS)))
+          return rc;
+      } else if ((rc = dist_allgather_device(ctx, W->cosets_all + send_slot * en, W->cosets_all,
+                                             spr * en * sizeof(Fp)))) {
         return rc;
+      }
     }
     NttTables* TNq = nullptr;
     if ((rc = ntt_tables(ctx, k, &TNq))) return rc;
@@ -659,7 +668,7 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
     for (int e = 1; e < 127; e++) qa.k.pow2[e] = qa.k.pow2[e - 1].dbl();
     // rows shard too: every rank now holds all coset columns, evaluates its own range of the 3n rows and
     // the ranges of h are all-gathered in place
-    if (world > 1 && en % (uint64_t)world == 0) {
+    if (shard_rows) {
       const uint64_t rows = en / (uint64_t)world, row_lo = rows * (uint64_t)ctx->dist_rank;
       if ((rc = quotient_run(ctx, qa, n, row_lo, row_lo + rows))) return rc;
       if ((rc = dist_allgather_device(ctx, W->h + row_lo, W->h, rows * sizeof(Fp)))) return rc;

@@ -115,6 +115,9 @@ void dist_column_block(uint32_t count, int rank, int world, uint32_t* lo, uint32
 int32_t dist_sum_points(zk_ctx* ctx, XYZZ* results, int nb);
 // recv[r * bytes .. (r + 1) * bytes) <- rank r's send buffer (device pointers), on the context's stream
 int32_t dist_allgather_device(zk_ctx* ctx, const void* send, void* recv, size_t bytes);
+// column-sharded slot arrays -> the row segments each rank's share of the quotient reads (dist.cu)
+int32_t dist_exchange_quotient_rows(zk_ctx* ctx, char* slots, size_t elem_bytes, uint64_t n, uint64_t en,
+                                    uint32_t nslots);
 void dist_free(zk_ctx* ctx);
 
 // witness.cu
