@@ -191,6 +191,25 @@ int32_t dist_sum_points(zk_ctx* ctx, XYZZ* results, int nb) {
   return ZK_OK;
 }
 
+// host_out[i] <- sum over ranks of their d_vals[i] (device, `count` field elements); identical on every rank
+int32_t dist_sum_fields(zk_ctx* ctx, const Fp* d_vals, int count, Fp* host_out) {
+  const int world = ctx->dist_world;
+  const size_t bytes = (size_t)count * sizeof(Fp);
+  int32_t rc = ensure_buf(ctx, ctx->dist_buf, bytes * world);
+  if (rc) return rc;
+  ncclResult_t r = nccl().AllGather(d_vals, ctx->dist_buf.ptr, bytes, ncclUint8, (ncclComm_t)ctx->nccl_comm, ctx->stream);
+  if (r != ncclSuccess) return nccl_error(ctx, r, "ncclAllGather");
+  std::vector<Fp> all((size_t)count * world);
+  ZK_CUDA(ctx, cudaMemcpyAsync(all.data(), ctx->dist_buf.ptr, bytes * world, cudaMemcpyDeviceToHost, ctx->stream));
+  ZK_CUDA(ctx, zk_stream_sync(ctx));
+  for (int i = 0; i < count; i++) {
+    Fp acc = all[i];
+    for (int q = 1; q < world; q++) acc = acc + all[(size_t)q * count + i];
+    host_out[i] = acc;
+  }
+  return ZK_OK;
+}
+
 int32_t dist_allgather_device(zk_ctx* ctx, const void* send, void* recv, size_t bytes) {
   ncclResult_t r = nccl().AllGather(send, recv, bytes, ncclUint8, (ncclComm_t)ctx->nccl_comm, ctx->stream);
   if (r != ncclSuccess) return nccl_error(ctx, r, "ncclAllGather");

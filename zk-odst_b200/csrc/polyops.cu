@@ -216,11 +216,12 @@ struct EvalJobs {
   EvalJob j[48];
 };
 __global__ void __launch_bounds__(EV_THREADS)
-poly_eval_kernel(EvalJobs jobs, uint64_t n, Fp* __restrict__ partials, uint32_t nblocks) {
+poly_eval_kernel(EvalJobs jobs, uint64_t n, Fp* __restrict__ partials, uint32_t nblocks, uint32_t first_block) {
   __shared__ Fp sh[EV_THREADS];
   const EvalJob& job = jobs.j[blockIdx.y];
   const Fp x = job.point;
-  uint64_t lo = (uint64_t)blockIdx.x * EV_BLOCK + (uint64_t)threadIdx.x * EV_PER;
+  const uint32_t blk = first_block + blockIdx.x;  // coefficients [blk * EV_BLOCK, (blk + 1) * EV_BLOCK)
+  uint64_t lo = (uint64_t)blk * EV_BLOCK + (uint64_t)threadIdx.x * EV_PER;
   Fp acc = Fp::zero();
   if (lo < n) {
     uint64_t hi = lo + EV_PER < n ? lo + EV_PER : n;
@@ -230,7 +231,7 @@ poly_eval_kernel(EvalJobs jobs, uint64_t n, Fp* __restrict__ partials, uint32_t 
   }
   Fp total = block_sum(acc, sh);
   if (threadIdx.x == 0)
-    partials[(size_t)blockIdx.y * nblocks + blockIdx.x] = total * x.pow_u64((uint64_t)blockIdx.x * EV_BLOCK);
+    partials[(size_t)blockIdx.y * nblocks + blockIdx.x] = total * x.pow_u64((uint64_t)blk * EV_BLOCK);
 }
 __global__ void __launch_bounds__(EV_THREADS)
 sum_partials_kernel(const Fp* __restrict__ partials, uint32_t nblocks, Fp* __restrict__ results) {
@@ -262,9 +263,16 @@ int32_t batch_invert(zk_ctx* ctx, Fp* data, uint64_t n) {
   return ZK_OK;
 }
 
+// In a multi-GPU group the polynomials are replicated, so the sum splits by coefficient range: every rank
+// evaluates its own contiguous range of EV_BLOCK-coefficient blocks for all jobs and the per-rank partial
+// values are exchanged (dist_sum_fields): balanced whatever the number of jobs.
 int32_t poly_eval_batch(zk_ctx* ctx, const EvalJob* jobs, int njobs, uint64_t n, Fp* results_host) {
   cudaStream_t st = ctx->stream;
-  uint32_t nblocks = (uint32_t)((n + EV_BLOCK - 1) / EV_BLOCK);
+  const uint32_t all_blocks = (uint32_t)((n + EV_BLOCK - 1) / EV_BLOCK);
+  uint64_t b_lo = 0, b_hi = all_blocks;
+  const bool split = ctx->dist_world > 1 && all_blocks >= 4u * (uint32_t)ctx->dist_world;
+  if (split) dist_range(all_blocks, ctx->dist_rank, ctx->dist_world, &b_lo, &b_hi);
+  const uint32_t nblocks = (uint32_t)(b_hi - b_lo);
   for (int base = 0; base < njobs; base += 48) {
     int cnt = njobs - base < 48 ? njobs - base : 48;
     int32_t rc = ensure_buf(ctx, ctx->eval_ws, ((size_t)cnt * nblocks + 64) * sizeof(Fp));
@@ -273,12 +281,16 @@ int32_t poly_eval_batch(zk_ctx* ctx, const EvalJob* jobs, int njobs, uint64_t n,
     Fp* results = partials + (size_t)cnt * nblocks;
     EvalJobs ej;
     for (int i = 0; i < cnt; i++) ej.j[i] = jobs[base + i];
-    poly_eval_kernel<<<dim3(nblocks, cnt), EV_THREADS, 0, st>>>(ej, n, partials, nblocks);
+    poly_eval_kernel<<<dim3(nblocks, cnt), EV_THREADS, 0, st>>>(ej, n, partials, nblocks, (uint32_t)b_lo);
     sum_partials_kernel<<<cnt, EV_THREADS, 0, st>>>(partials, nblocks, results);
     ctx->launches += 2;
     ZK_CUDA(ctx, cudaGetLastError());
-    ZK_CUDA(ctx, cudaMemcpyAsync(results_host + base, results, (size_t)cnt * sizeof(Fp), cudaMemcpyDeviceToHost, st));
-    ZK_CUDA(ctx, zk_stream_sync(ctx));
+    if (split) {
+      if ((rc = dist_sum_fields(ctx, results, cnt, results_host + base))) return rc;
+    } else {
+      ZK_CUDA(ctx, cudaMemcpyAsync(results_host + base, results, (size_t)cnt * sizeof(Fp), cudaMemcpyDeviceToHost, st));
+      ZK_CUDA(ctx, zk_stream_sync(ctx));
+    }
   }
   return ZK_OK;
 }

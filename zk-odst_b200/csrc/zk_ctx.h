@@ -118,6 +118,8 @@ int32_t dist_allgather_device(zk_ctx* ctx, const void* send, void* recv, size_t 
 // column-sharded slot arrays -> the row segments each rank's share of the quotient reads (dist.cu)
 int32_t dist_exchange_quotient_rows(zk_ctx* ctx, char* slots, size_t elem_bytes, uint64_t n, uint64_t en,
                                     uint32_t nslots);
+// host_out[i] <- sum over ranks of d_vals[i] (one small all-gather, summed on the host)
+int32_t dist_sum_fields(zk_ctx* ctx, const Fp* d_vals, int count, Fp* host_out);
 void dist_free(zk_ctx* ctx);
 
 // witness.cu
