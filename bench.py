@@ -113,7 +113,8 @@ def cpu_sample_text(dt):
 
 def workload_config(k, n, split=False, world=1):
     what = ("configs[3] shape: ONE proof of %d compressions, every MSM split by point range over %d "
-            "GPUs (NCCL all-gather of partial points), the rest replicated" % (n, world)) if split else (
+            "GPUs (NCCL all-gather of partial points), the witness transforms sharded by column, the "
+            "quotient by row, evaluations by coefficient range; the rest replicated" % (n, world)) if split else (
             "configs[2]: %d twelve-round BLAKE2f compressions in one circuit, "
             "full create_proof (Pasta/IPA)" % n)
     return {"workload": what,
@@ -170,7 +171,8 @@ def main():
                          "when ranks x streams would oversubscribe the cores")
     ap.add_argument("--msm-split", action="store_true",
                     help="configs[3]: ONE proof stream, every MSM split by point range across the "
-                         "ranks (NCCL all-gather of partial points); strong scaling")
+                         "ranks (NCCL all-gather of partial points), transforms by column, quotient by row; "
+                         "strong scaling")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

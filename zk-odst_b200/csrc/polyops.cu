@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(128) batch_invert_kernel(Fp* __restrict__ data
 }
 
 // ---- evaluation ----------------------------------------------------------------------------------
-constexpr int EV_THREADS = 256, EV_PER = 16, EV_BLOCK = EV_THREADS * EV_PER;
+constexpr int EV_THREADS = 256, EV_PER = 64, EV_BLOCK = EV_THREADS * EV_PER;  // 64: the two power computations per thread amortise over more coefficients (2.4 -> 1.3 products per coefficient)
 
 __device__ __forceinline__ Fp block_sum(Fp v, Fp* sh) {
   sh[threadIdx.x] = v;
@@ -226,8 +226,8 @@ poly_eval_kernel(EvalJobs jobs, uint64_t n, Fp* __restrict__ partials, uint32_t 
   if (lo < n) {
     uint64_t hi = lo + EV_PER < n ? lo + EV_PER : n;
     for (uint64_t i = hi; i-- > lo;) acc = acc * x + job.poly[i];
-    Fp x16 = x.pow_u64(EV_PER);
-    acc = acc * x16.pow_u64(threadIdx.x);
+    Fp xper = x.pow_u64(EV_PER);
+    acc = acc * xper.pow_u64(threadIdx.x);
   }
   Fp total = block_sum(acc, sh);
   if (threadIdx.x == 0)
