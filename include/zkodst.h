@@ -199,7 +199,9 @@ int32_t zk_mock_verify(zk_ctx* ctx, const uint8_t* inputs, uint64_t n_compressio
  * (`Params::commit`, `commit_lagrange`, the IPA rounds) covers only this rank's contiguous range
  * of the base points; the per-rank partial points are all-gathered over NCCL and summed, so all
  * ranks obtain the same commitment and — fed the same records and seed — the same proof bytes as
- * a single GPU.  Everything that is not an MSM runs replicated.
+ * a single GPU.  A group also shards the transforms of the witness columns by column
+ * (zk_dist_column_block), the quotient by row (zk_dist_quotient_rows) and the polynomial evaluations by
+ * coefficient range; the remaining steps run replicated.
  *   rank 0: zk_dist_unique_id(id); share id with the other ranks by any means
  *   all:    zk_ctx_create; zk_dist_init(ctx, id, rank, world); params; keygen; create_proof */
 #define ZK_DIST_ID_BYTES 128
