@@ -159,7 +159,7 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -233,13 +233,15 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def run_streams(per_stream, src, on_device):
-        """Every context proves `per_stream` batches on its own CUDA stream, from its own host thread
-        (create_proof returns after the proof bytes reached the host).  Returns the last proofs."""
+    def run_streams(total, src, on_device):
+        """`total` proofs shared by the S contexts (the first total % S take one more), each context on its
+        own CUDA stream from its own host thread (create_proof returns after the proof bytes reached the
+        host).  Returns the last proof of every context that proved one."""
         out = [None] * S
+        counts = [total // S + (1 if i < total % S else 0) for i in range(S)]
 
         def work(i):
-            for _ in range(per_stream):
+            for _ in range(counts[i]):
                 out[i] = ctxs[i].create_proof(src, n, seed, on_device=on_device)
         if S == 1:
             work(0)
@@ -249,24 +251,24 @@ def main():
                 t.start()
             for t in ts:
                 t.join()
-        return out
+        return [p for p in out if p is not None]
 
-    def timed(per_stream, src, on_device):
+    def timed(total, src, on_device):
         """Device time (CUDA events around the region; every stream is idle at both ends) per proof."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record(ev_stream)
-        proofs = run_streams(per_stream, src, on_device)
+        proofs = run_streams(total, src, on_device)
         e1.record(ev_stream)
         torch.cuda.synchronize()
         dt_host = time.perf_counter() - t0
         dt = e0.elapsed_time(e1) * 1e-3
         assert abs(dt - dt_host) < 0.05 * dt_host + 0.01, (dt, dt_host)
-        return dt / (per_stream * S), proofs
+        return dt / total, proofs
 
     # ---- warm-up, then one context alone with per-kernel-class CUDA-event timing ------------------
-    run_streams(args.warmup, d_in, True)
+    run_streams(args.warmup * S, d_in, True)   # W warm-up proofs on every context
     barrier()
     single_steps = max(3, min(args.steps, 5))
     ctx.enable_timing(True)
@@ -279,21 +281,21 @@ def main():
     ctx.enable_timing(False)
 
     # ---- value: inputs resident in HBM, S concurrent proof streams ------------------------------------
-    per_stream = (args.steps + S - 1) // S
+    # exactly --steps proofs are timed, shared by the S contexts
+    steps_done = max(1, args.steps)
     launches0 = sum(c.launch_count() for c in ctxs)
     with ClockSampler(local_rank) as clocks:
-        sec_per_proof, proofs = timed(per_stream, d_in, True)
+        sec_per_proof, proofs = timed(steps_done, d_in, True)
     launches = sum(c.launch_count() for c in ctxs) - launches0
     assert all(p == proof for p in proofs), "streams disagree on the proof bytes"
-    steps_done = per_stream * S
     ms_per_step = max_over_ranks(sec_per_proof * 1e3)
     jobs = 1 if split else world  # split: all ranks work on the same proof
     value = jobs * n / (ms_per_step * 1e-3)
 
     # ---- e2e: host (pinned) records in, proof bytes out, through the C-ABI call ---------------------
-    run_streams(1, h_in, False)
-    e2e_per_stream = max(2, min(per_stream, 5))
-    e2e_sec, proofs_e2e = timed(e2e_per_stream, h_in, False)
+    run_streams(S, h_in, False)
+    e2e_steps = max(2 * S, min(steps_done, 5 * S))
+    e2e_sec, proofs_e2e = timed(e2e_steps, h_in, False)
     e2e_ms = max_over_ranks(e2e_sec * 1e3)
     e2e_val = jobs * n / (e2e_ms * 1e-3)
     assert all(p == proof for p in proofs_e2e), "host-input and device-input proofs differ"
