@@ -90,8 +90,8 @@ def test_msm_linearity(ctx, oracle, urs):
 
 
 # every round plan of the pass scheduler: single passes of 1..10 stages (rounds 3/2/1), two passes
-# (11 = 6 + 5 ... 20 = 10 + 10) and the column-grouped later passes
-@pytest.mark.parametrize("log_n", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 16, 17, 19, 20])
+# (11 = 6 + 5 ... 20 = 10 + 10), three passes (21 = 7 + 7 + 7, 23 = 8 + 8 + 7) and the column-grouped later passes
+@pytest.mark.parametrize("log_n", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 16, 17, 19, 20, 21, 23])
 @pytest.mark.parametrize("inverse", [False, True])
 def test_ntt_matches_oracle(ctx, oracle, log_n, inverse):
     n = 1 << log_n

@@ -76,6 +76,31 @@ def test_slice_plans_bit_exact(ctx, oracle, zk, n):
     assert np.array_equal(adv, ref)
 
 
+def test_more_items_than_resident_blocks(ctx, zk):
+    """700 compressions at k = 22: more (compression, slice) items than one wave of resident blocks, so
+    blocks walk several items.  The region of compression j must equal what the single-wave path (checked
+    against the oracle above) writes when the batch is cut in two, and the digests must equal F."""
+    import torch
+    n, k, half = 700, 22, 350
+    R = zk.rows_per_compression(12)
+    inputs = zk.synthetic_inputs(n, stream=5)
+    d_in = torch.frombuffer(bytearray(inputs), dtype=torch.uint8).cuda()
+    big = torch.empty((12, 1 << k, 4), dtype=torch.int64, device="cuda")
+    dig = torch.empty((n, 8), dtype=torch.int64, device="cuda")
+    ctx.witness_batch_device(k, 12, d_in, n, big, dig)
+    ctx.synchronize()
+    part = torch.empty_like(big)
+    for lo in (0, half):
+        ctx.witness_batch_device(k, 12, d_in[lo * 213:], half, part, None)
+        ctx.synchronize()
+        assert torch.equal(big[:, lo * R:(lo + half) * R], part[:, :half * R]), lo
+    assert not big[:, n * R:].any()
+    got = dig.cpu().numpy().view(np.uint64)
+    for j in (0, 1, 349, 350, 591, 592, 593, 699):
+        want = np.frombuffer(zk.blake2f_compress(inputs[213 * j:213 * (j + 1)]), dtype=np.uint64)
+        assert np.array_equal(got[j], want), j
+
+
 def test_device_buffer_alignment(ctx, zk):
     """Cells are written with 256-bit stores: a device advice buffer that is not 32-byte aligned is
     rejected (ZK_E_INVALID), not written with misaligned stores."""
