@@ -11,7 +11,9 @@
 //! `keygen_vk`, `MockProver` and `verify_proof` keep working on the same circuit.
 //!
 //! NOTE: this crate is shipped as source; the build image has no Rust toolchain, so it has not
-//! been compiled.  INTEGRATION.md walks through the steps a maintainer follows.
+//! been compiled.  INTEGRATION.md walks through the steps a maintainer follows.  The same surface
+//! exists in C++ (include/zkodst.hpp), which IS compiled and run by the test suite
+//! (tests/cpp/facade_test.cpp); `gadget` below follows it line for line.
 use std::ffi::CStr;
 use std::ptr;
 
@@ -157,5 +159,199 @@ impl GpuProver {
 impl Drop for GpuProver {
     fn drop(&mut self) {
         unsafe { sys::zk_ctx_destroy(self.ctx) }
+    }
+}
+
+// ---- the chip / gadget surface ----------------------------------------------------------------------------
+// Same shape as include/zkodst.hpp (which is compiled and tested in this repository): `synthesize` runs
+// against a recording layouter — every `compress` lays out one region, i.e. one EIP-152 record — and the
+// cells of all regions are assigned on the device in one call.
+pub mod gadget {
+    use super::{sys, Blake2fWitness, Error};
+
+    /// The size of a message block, in 64-bit words (blake2f-circuit/src/blake2f.rs:34).
+    pub const BLOCK_SIZE: usize = 16;
+    /// The size of a digest, in 64-bit words (src/blake2f.rs:36).
+    pub const DIGEST_SIZE: usize = 8;
+    /// table16.rs:47-56
+    pub const IV: [u64; 8] = [
+        0x6a09e667f3bcc908, 0xbb67ae8584caa73b, 0x3c6ef372fe94f82b, 0xa54ff53a5f1d36f1,
+        0x510e527fade682d1, 0x9b05688c2b3e6c1f, 0x1f83d9abfb41bd6b, 0x5be0cd19137e2179,
+    ];
+
+    /// table16.rs:59-61 with 64-bit words; `None` = `Value::unknown()` (key generation).
+    #[derive(Clone, Copy, Debug)]
+    pub struct BlockWord(pub Option<u64>);
+    impl Default for BlockWord {
+        fn default() -> Self {
+            BlockWord(Some(0)) // the zero word `finalize` pads with
+        }
+    }
+
+    /// table16/compression.rs:286-525 `State`, as values, plus what BLAKE2b's F needs besides the chaining
+    /// value: the byte counter of the block about to be compressed, the final flag, the round count.
+    #[derive(Clone, Debug)]
+    pub struct State {
+        pub h: [Option<u64>; 8],
+        pub t: u64,
+        pub last: bool,
+        pub rounds: u32,
+    }
+
+    /// Records the regions a circuit lays out: 213 bytes per compression, in layout order.
+    pub struct Layouter {
+        pub witnesses_known: bool,
+        pub table_loaded: bool,
+        pub rounds: u32,
+        pub regions: u64,
+        pub records: Vec<u8>,
+    }
+    impl Layouter {
+        pub fn new(witnesses_known: bool) -> Self {
+            Layouter { witnesses_known, table_loaded: false, rounds: 0, regions: 0, records: Vec::new() }
+        }
+    }
+
+    /// blake2f-circuit/src/blake2f.rs:40-72
+    pub trait Blake2fInstructions {
+        fn initialization_vector(&self, layouter: &mut Layouter) -> Result<State, Error>;
+        fn initialization(&self, layouter: &mut Layouter, init_state: &State) -> Result<State, Error>;
+        fn compress(&self, layouter: &mut Layouter, initialized_state: &State,
+                    input: [BlockWord; BLOCK_SIZE]) -> Result<State, Error>;
+        fn digest(&self, layouter: &mut Layouter, state: &State) -> Result<[BlockWord; DIGEST_SIZE], Error>;
+    }
+
+    #[derive(Clone, Debug, Default)]
+    pub struct Table16Config;
+
+    /// blake2f-circuit/src/blake2f/table16.rs:250-384
+    #[derive(Clone, Debug)]
+    pub struct Table16Chip {
+        config: Table16Config,
+    }
+    impl Table16Chip {
+        /// The column / gate / lookup plan is fixed (docs/CIRCUIT.md) and lives in the library.
+        pub fn configure() -> Table16Config {
+            Table16Config
+        }
+        pub fn construct(config: Table16Config) -> Self {
+            Table16Chip { config }
+        }
+        pub fn load(_config: Table16Config, layouter: &mut Layouter) -> Result<(), Error> {
+            layouter.table_loaded = true;
+            Ok(())
+        }
+        pub fn config(&self) -> &Table16Config {
+            &self.config
+        }
+    }
+
+    fn synthesis_error(message: &str) -> Error {
+        Error { code: sys::ZK_E_INPUT, message: message.into() }
+    }
+
+    impl Blake2fInstructions for Table16Chip {
+        fn initialization_vector(&self, _layouter: &mut Layouter) -> Result<State, Error> {
+            let mut h = [None; 8];
+            for i in 0..8 {
+                h[i] = Some(IV[i]);
+            }
+            h[0] = Some(IV[0] ^ 0x0101_0040); // BLAKE2b-512, unkeyed
+            Ok(State { h, t: 0, last: false, rounds: 12 })
+        }
+        fn initialization(&self, _layouter: &mut Layouter, init_state: &State) -> Result<State, Error> {
+            Ok(init_state.clone())
+        }
+        fn compress(&self, layouter: &mut Layouter, st: &State, input: [BlockWord; BLOCK_SIZE]) -> Result<State, Error> {
+            if !layouter.table_loaded {
+                return Err(Error { code: sys::ZK_E_STATE, message: "compress before load".into() });
+            }
+            if layouter.regions > 0 && layouter.rounds != st.rounds {
+                return Err(synthesis_error("regions of one circuit must share the round count"));
+            }
+            layouter.rounds = st.rounds;
+            layouter.regions += 1;
+            let mut out = st.clone();
+            if !layouter.witnesses_known {
+                out.h = [None; 8];
+                return Ok(out);
+            }
+            let mut w = Blake2fWitness { rounds: st.rounds, h: [0; 8], m: [0; 16], t: [st.t, 0], f: st.last };
+            for i in 0..8 {
+                w.h[i] = st.h[i].ok_or_else(|| synthesis_error("unknown chaining value in a proving run"))?;
+            }
+            for i in 0..BLOCK_SIZE {
+                w.m[i] = input[i].0.ok_or_else(|| synthesis_error("unknown block word in a proving run"))?;
+            }
+            let record = w.to_eip152();
+            layouter.records.extend_from_slice(&record);
+            let mut hout = [0u8; 64];
+            let rc = unsafe { sys::zk_blake2f_compress(record.as_ptr(), hout.as_mut_ptr()) };
+            if rc != sys::ZK_OK {
+                return Err(Error { code: rc, message: "zk_blake2f_compress".into() });
+            }
+            for i in 0..8 {
+                let mut b = [0u8; 8];
+                b.copy_from_slice(&hout[8 * i..8 * i + 8]);
+                out.h[i] = Some(u64::from_le_bytes(b));
+            }
+            Ok(out)
+        }
+        fn digest(&self, _layouter: &mut Layouter, state: &State) -> Result<[BlockWord; DIGEST_SIZE], Error> {
+            let mut out = [BlockWord(None); DIGEST_SIZE];
+            for i in 0..DIGEST_SIZE {
+                out[i] = BlockWord(state.h[i]);
+            }
+            Ok(out)
+        }
+    }
+
+    /// blake2f-circuit/src/blake2f.rs:80-181, at a granularity of one 64-bit word.  BLAKE2b flags its last
+    /// block, so a full block is compressed only once more data (or `finalize`) arrives.
+    pub struct Blake2f<CS: Blake2fInstructions> {
+        chip: CS,
+        state: State,
+        cur_block: Vec<BlockWord>,
+        bytes_done: u64,
+    }
+    impl<CS: Blake2fInstructions> Blake2f<CS> {
+        pub fn new(chip: CS, layouter: &mut Layouter) -> Result<Self, Error> {
+            let state = chip.initialization_vector(layouter)?;
+            Ok(Blake2f { chip, state, cur_block: Vec::with_capacity(BLOCK_SIZE), bytes_done: 0 })
+        }
+        fn flush(&mut self, layouter: &mut Layouter, last: bool, block_bytes: u64) -> Result<(), Error> {
+            let mut st = self.chip.initialization(layouter, &self.state)?;
+            st.t = self.bytes_done + block_bytes;
+            st.last = last;
+            let mut block = [BlockWord::default(); BLOCK_SIZE];
+            block[..self.cur_block.len()].copy_from_slice(&self.cur_block);
+            self.state = self.chip.compress(layouter, &st, block)?;
+            self.bytes_done += block_bytes;
+            self.cur_block.clear();
+            Ok(())
+        }
+        pub fn update(&mut self, layouter: &mut Layouter, data: &[BlockWord]) -> Result<(), Error> {
+            for w in data {
+                if self.cur_block.len() == BLOCK_SIZE {
+                    self.flush(layouter, false, 128)?;
+                }
+                self.cur_block.push(*w);
+            }
+            Ok(())
+        }
+        /// `unused_bytes_of_last_word` (< 8) trims the byte counter when the message does not end on a word boundary.
+        pub fn finalize(mut self, layouter: &mut Layouter, unused_bytes_of_last_word: u64)
+                        -> Result<[BlockWord; DIGEST_SIZE], Error> {
+            let words = self.cur_block.len() as u64;
+            let bytes = words * 8 - if words > 0 { unused_bytes_of_last_word } else { 0 };
+            self.flush(layouter, true, bytes)?;
+            self.chip.digest(layouter, &self.state)
+        }
+        pub fn digest(chip: CS, layouter: &mut Layouter, data: &[BlockWord], unused_bytes_of_last_word: u64)
+                      -> Result<[BlockWord; DIGEST_SIZE], Error> {
+            let mut hasher = Self::new(chip, layouter)?;
+            hasher.update(layouter, data)?;
+            hasher.finalize(layouter, unused_bytes_of_last_word)
+        }
     }
 }
