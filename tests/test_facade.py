@@ -28,6 +28,9 @@ def test_facade_builds_and_fails_loudly_without_a_device(tmp_path):
     CUDA device the first call throws zkodst::Error (Backend, ZK_E_CUDA): there is no CPU fallback."""
     import torch
     exe = build(tmp_path)
+    # the gadget, the recording layouter and the circuit's lay-out are host code: they run everywhere
+    res = subprocess.run([exe, "--host-only"], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0 and "facade host part ok" in res.stdout, res.stdout + res.stderr
     if torch.cuda.is_available():
         pytest.skip("a device is present: test_facade_runs covers the run")
     res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
