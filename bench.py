@@ -2,15 +2,18 @@
 """bench.py — headline benchmark of the BLAKE2f proving path on B200.
 
   python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun)
-  python bench.py --impl reference ...                      (CPU arm: the oracle restatement)
+  python bench.py --impl reference ...                      (CPU arm: the oracle restatement, same config)
 
 A "step" is one complete proof (witness -> commitments -> quotient -> multiopen -> IPA) of one
 batch of synthetic EIP-152 records: BASELINE.json configs[2], 64 twelve-round compressions in
 one circuit (k = 19).  With N GPUs every rank proves its own independent batch (configs[4]:
-independent proof streams, weak scaling, no data-path collective).
+independent proof streams, weak scaling, no data-path collective); the same run then also proves ONE
+configs[3]-shape circuit sharded over all N ranks (`strong_split`) and checks that a sharded proof has
+the single-GPU bytes (`split_parity`).
 Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for the definitions.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -29,6 +32,13 @@ UNIT = "compressions/s"
 # a <= 32-bit advice term = 2 windows.
 MAC_FULL, MAC_SMALL = 16 * 11 * 136, 2 * 11 * 136
 MAC_PER_FP_MUL = 136
+ROWS_PER_COMPRESSION = 292 + 392 * ROUNDS
+# dram__bytes_read.sum + dram__bytes_write.sum of one full-width accumulation launch (k = 19), from the
+# `ncu --set full` capture named here (not measured in the run: DRAM counters need the profiler)
+TRAFFIC_CAPTURE = {"bytes": None, "source": None}
+_tc = os.path.join(ROOT, "profiles", "accumulate_traffic.json")
+if os.path.exists(_tc):
+    TRAFFIC_CAPTURE = json.load(open(_tc))
 
 
 def load_peaks():
@@ -84,31 +94,35 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.samples)}
 
 
-# ---- CPU arm: the oracle (halo2-0.3.0-equivalent restatement), all host threads ------------------
+# ---- CPU arm: the oracle (halo2-0.3.0-equivalent restatement) ------------------------------------------
+# The reference itself is Rust and does not compile (SURVEY.md §2.3; no cargo in the image), so this arm is the
+# repo's C++ port of its algorithm: kind "port".  Phase labels follow benchmarking/src/constants.rs:1-3.
 CPU_SAMPLE_K, CPU_SAMPLE_N = 17, 26   # bounded sample: the largest batch that fits the default k
 
 
-def cpu_oracle_setup():
+def oracle_modules():
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
     import zk_odst_b200 as zk
-    oracle = oracle_lib.load()
-    op = oracle_lib.OracleProver(oracle, k=CPU_SAMPLE_K, seed=zk.REFERENCE_SEED)
-    op.keygen(ROUNDS, CPU_SAMPLE_N)
-    return op, zk.synthetic_inputs(CPU_SAMPLE_N), zk.REFERENCE_SEED
+    return oracle_lib, zk
 
 
-def cpu_prove_once(op, inputs, seed):
+def cpu_timed_setup(oracle_lib, oracle, k, n_compressions, seed):
+    """[Setup generation]: Params + keygen_vk + keygen_pk of the oracle; returns (prover, seconds)."""
     t0 = time.perf_counter()
-    proof = op.create_proof(inputs, CPU_SAMPLE_N, seed)
+    op = oracle_lib.OracleProver(oracle, k=k, seed=seed)
+    t1 = time.perf_counter()
+    op.keygen(ROUNDS, n_compressions)
+    t2 = time.perf_counter()
+    return op, {"params_s": t1 - t0, "keygen_s": t2 - t1}
+
+
+def cpu_prove(op, inputs, n, seed):
+    t0 = time.perf_counter()
+    proof = op.create_proof(inputs, n, seed)
     dt = time.perf_counter() - t0
-    return CPU_SAMPLE_N / dt, dt, proof
-
-
-def cpu_sample_text(dt):
-    return ("one proof of %d compressions at k=%d (create_proof only; params/keygen excluded), "
-            "%.1f s, C++ oracle restating halo2_proofs 0.3.0, std::thread x %d" %
-            (CPU_SAMPLE_N, CPU_SAMPLE_K, dt, os.cpu_count() or 1))
+    synth_ms, rest_ms = op.last_proof_ms()
+    return proof, dt, synth_ms * 1e-3
 
 
 def workload_config(k, n, split=False, world=1):
@@ -119,7 +133,8 @@ def workload_config(k, n, split=False, world=1):
             "full create_proof (Pasta/IPA)" % n)
     return {"workload": what,
             "k": k, "rounds": ROUNDS, "compressions_per_proof": n,
-            "rows_per_compression": 292 + 392 * ROUNDS,
+            "rows_per_compression": ROWS_PER_COMPRESSION,
+            "rows_used_frac": round(n * ROWS_PER_COMPRESSION / float(1 << k), 3),
             "params": "substitute URS (zk_params_generate_substitute, reference seed)",
             "l2": "per proof the prover streams > 2 GB of column/coset data (advice cosets alone "
                   "12 x 3 x 2^k x 32 B = %d MB), far above the 126 MB L2; no explicit flush" %
@@ -127,33 +142,173 @@ def workload_config(k, n, split=False, world=1):
 
 
 def run_reference(args, rank):
+    """The reference arm: the CPU restatement proves configs[2] itself (k = 19, 64 compressions) with every
+    host thread; then, at --gpus 1, the single-thread figure (the pinned reference has rayon off:
+    blake2f-circuit/Cargo.toml:15) on the bounded k = 17 sample."""
     if rank != 0:
         return
-    op, inputs, seed = cpu_oracle_setup()
-    budget_s = 150.0
-    steps, t_used, last_dt = 0, 0.0, 0.0
+    oracle_lib, zk = oracle_modules()
+    oracle = oracle_lib.load()
+    cores = oracle_lib.set_threads(oracle, 0)
+    t_run = time.perf_counter()
+    n = args.compressions
+    k = 17
+    while n * ROWS_PER_COMPRESSION > (1 << k) - 6:
+        k += 1
+    seed = zk.REFERENCE_SEED
+    inputs = zk.synthetic_inputs(n)
+    op, setup = cpu_timed_setup(oracle_lib, oracle, k, n, seed)
+    prove_budget_s = 150.0
+    steps, t_used, synth_s, proof = 0, 0.0, 0.0, None
     t_start = time.perf_counter()
     while steps < max(1, args.steps):
-        _, dt, _ = cpu_prove_once(op, inputs, seed)
+        proof, dt, sy = cpu_prove(op, inputs, n, seed)
         steps += 1
         t_used += dt
-        last_dt = dt
-        if time.perf_counter() - t_start + dt > budget_s:
+        synth_s += sy
+        if time.perf_counter() - t_start + dt > prove_budget_s:
             break
     dt = t_used / steps
-    val = CPU_SAMPLE_N / dt
-    cfg = workload_config(CPU_SAMPLE_K, CPU_SAMPLE_N)
-    cfg["workload"] += " — CPU arm runs the bounded sample below (k=17 is the smallest circuit)"
+    t0 = time.perf_counter()
+    rc, msg = op.verify(proof)
+    verify_s = time.perf_counter() - t0
+    assert rc == 0, "oracle rejected its own proof: " + msg
+    op.close()
+    val = n / dt
+    phases = {"[Setup generation]": setup["params_s"] + setup["keygen_s"], "[Proof generation]": dt,
+              "[Proof verification]": verify_s, "witness synthesis (inside proof generation)": synth_s / steps,
+              "params_s": setup["params_s"], "keygen_s": setup["keygen_s"], "unit": "s"}
+    one_thread = None
+    elapsed = time.perf_counter() - t_run
+    if args.gpus == 1 and not args.no_one_thread and elapsed < 170.0:
+        oracle_lib.set_threads(oracle, 0)
+        op1, _ = cpu_timed_setup(oracle_lib, oracle, CPU_SAMPLE_K, CPU_SAMPLE_N, seed)
+        oracle_lib.set_threads(oracle, 1)
+        _, dt1, sy1 = cpu_prove(op1, zk.synthetic_inputs(CPU_SAMPLE_N), CPU_SAMPLE_N, seed)
+        oracle_lib.set_threads(oracle, 0)
+        op1.close()
+        one_thread = {"value": CPU_SAMPLE_N / dt1, "unit": UNIT, "cores": 1, "proof_generation_s": dt1,
+                      "witness_synthesis_s": sy1,
+                      "sample": "one proof of %d compressions at k=%d on ONE thread (the pinned reference is "
+                                "single-threaded: rayon off); a k=19 proof on one thread would take ~%d s" %
+                                (CPU_SAMPLE_N, CPU_SAMPLE_K, int(dt * cores * 0.8))}
+    cfg = workload_config(k, n)
+    sample = ("%d proof(s) of %d compressions at k=%d (create_proof incl. witness synthesis; setup timed "
+              "separately), %.1f s each, C++ oracle restating halo2_proofs 0.3.0, std::thread x %d" %
+              (steps, n, k, dt, cores))
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": 0, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u64 (4x64-bit Montgomery limbs)",
         "data": "synthetic", "config": cfg, "proofs_per_sec": 1.0 / dt,
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-                         "sample": cpu_sample_text(last_dt)},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "phases": phases, "one_thread": one_thread},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "proof_sha256": hashlib.sha256(proof).hexdigest(),
     }
     print(json.dumps(line))
+
+
+# ---- sharded single proof: parity and strong scaling (world > 1) ---------------------------------------
+def split_section(args, zk, torch, dist, rank, world, local_rank, barrier, max_over_ranks):
+    """(split_parity, strong_split): one k = 17 proof sharded over all ranks must have the single-GPU bytes;
+    then ONE configs[3]-shape circuit (k = 21 on 2 GPUs, k = 23 on 4 / 8) is proved by the whole group and by
+    rank 0 alone."""
+    seed = zk.REFERENCE_SEED
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid = torch.frombuffer(bytearray(zk.dist_unique_id()), dtype=torch.uint8).cuda()
+    dist.broadcast(uid, 0)
+    g = zk.Context(local_rank)
+    g.set_blocking_sync(world * 2 > (os.cpu_count() or 1))
+    g.dist_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
+
+    def digest_all_equal(blob):
+        h = torch.frombuffer(bytearray(hashlib.sha256(blob).digest()), dtype=torch.uint8).cuda()
+        hs = [torch.zeros_like(h) for _ in range(world)]
+        dist.all_gather(hs, h)
+        return all(bool(torch.equal(x, hs[0])) for x in hs)
+
+    # -- parity: k = 17, 3 compressions, every rank's bytes == rank 0's == a single GPU's
+    kp, np_ = 17, 3
+    rec = zk.synthetic_inputs(np_)
+    g.params_generate_substitute(kp, seed)
+    g.keygen(ROUNDS, np_)
+    mine = g.vk_bytes() + g.create_proof(rec, np_, seed)
+    same = digest_all_equal(mine)
+    single_equal = None
+    if rank == 0:
+        s = zk.Context(local_rank)
+        s.params_generate_substitute(kp, seed)
+        s.keygen(ROUNDS, np_)
+        single_equal = (s.vk_bytes() + s.create_proof(rec, np_, seed)) == mine
+        s.close()
+    parity = {"k": kp, "compressions": np_, "ranks_agree": same, "equals_single_gpu": single_equal,
+              "ok": bool(same and single_equal)} if rank == 0 else None
+    barrier()
+
+    # -- strong scaling of one proof
+    n = args.split_compressions or (256 if world == 2 else 1024)
+    k = zk.min_k(ROUNDS, n)
+    rec = zk.synthetic_inputs(n)
+    t0 = time.perf_counter()
+    g.params_generate_substitute(k, seed)
+    g.keygen(ROUNDS, n)
+    setup_s = time.perf_counter() - t0
+    d_in = torch.frombuffer(bytearray(rec), dtype=torch.uint8).cuda()
+    proof = g.create_proof(d_in, n, seed, on_device=True)   # warm-up (allocates the workspace)
+    g.enable_timing(True)
+    g.timing_report()
+    steps = 3
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        proof = g.create_proof(d_in, n, seed, on_device=True)
+    torch.cuda.synchronize()
+    ms_split = max_over_ranks((time.perf_counter() - t0) / steps * 1e3)
+    rep = g.timing_report()
+    g.enable_timing(False)
+    agree = digest_all_equal(proof)
+    classes = {name: ms / steps for name, (ms, cnt) in rep.items() if cnt}
+    g.close()
+    barrier()
+    ms_single, single_same = None, None
+    if rank == 0 and not args.no_split_single:
+        s = zk.Context(local_rank)
+        s.params_generate_substitute(k, seed)
+        s.keygen(ROUNDS, n)
+        p1 = s.create_proof(d_in, n, seed, on_device=True)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            p1 = s.create_proof(d_in, n, seed, on_device=True)
+        ms_single = (time.perf_counter() - t0) / steps * 1e3
+        single_same = p1 == proof
+        assert s.verify_proof(proof), s.last_error()
+        s.close()
+    barrier()
+    if rank != 0:
+        return None, None
+    nrows = 1 << k
+    per_rank_slots = -(-19 // world)
+    sharded = classes.get("msm", 0.0) + classes.get("ntt", 0.0) + classes.get("quotient", 0.0) + \
+        classes.get("collapse", 0.0) + classes.get("witness", 0.0)
+    strong = {
+        "workload": workload_config(k, n, True, world)["workload"], "k": k, "compressions_per_proof": n,
+        "ms_per_proof": ms_split, "ms_single_gpu": ms_single,
+        "speedup": ms_single / ms_split if ms_single else None,
+        "efficiency": ms_single / ms_split / world if ms_single else None,
+        "compressions_per_sec": n / (ms_split * 1e-3),
+        "ranks_agree": agree, "equals_single_gpu": single_same, "setup_s": setup_s, "steps": steps,
+        "rank0_class_ms": classes,
+        # what rank 0's timed kernel classes do not cover: grand-product scans, batch inversions, lookup
+        # permutation, evaluations, multiopen, host transcript round trips and the NCCL exchanges
+        "replicated_ms": ms_split - sharded,
+        "allgather_bytes": {"coefficient_columns_received_per_rank": per_rank_slots * world * nrows * 32,
+                            "coset_row_segments_received_per_rank": int(19 * (3 * nrows // world + 21) * 32 * (world - 1) / world),
+                            "h_rows_received_per_rank": 3 * nrows * 32,
+                            "partial_points_per_msm_batch": 128 * 16 * world},
+    }
+    return parity, strong
 
 
 def main():
@@ -162,7 +317,9 @@ def main():
     ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true",
+                    help="skip the CPU oracle legs (cpu_baseline and the parity gates that need it)")
+    ap.add_argument("--no-one-thread", action="store_true", help="reference arm: skip the single-thread figure")
     ap.add_argument("--compressions", type=int, default=N_COMPRESSIONS)
     ap.add_argument("--streams", type=int, default=4,
                     help="concurrent proof streams per GPU (one context and host thread each)")
@@ -170,9 +327,15 @@ def main():
                     help="1: host threads sleep while waiting for the device, 0: spin, -1: sleep only "
                          "when ranks x streams would oversubscribe the cores")
     ap.add_argument("--msm-split", action="store_true",
-                    help="configs[3]: ONE proof stream, every MSM split by point range across the "
+                    help="configs[3] as the headline: ONE proof stream, every MSM split by point range across the "
                          "ranks (NCCL all-gather of partial points), transforms by column, quotient by row; "
                          "strong scaling")
+    ap.add_argument("--no-split-section", action="store_true",
+                    help="N > 1: skip the split_parity / strong_split sub-records")
+    ap.add_argument("--no-split-single", action="store_true",
+                    help="strong_split: skip the single-GPU proof of the same circuit (no efficiency)")
+    ap.add_argument("--split-compressions", type=int, default=0,
+                    help="strong_split: compressions per proof (default 256 on 2 GPUs, 1024 on 4 / 8)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -302,7 +465,7 @@ def main():
 
     # ---- the other two calls of the reference's sequence, for the record (one context, rank 0) -----
     verify_ms = mock_ms = None
-    if rank == 0 and not split:
+    if rank == 0 and not split:   # (a group context's verifier MSM is a collective: not from rank 0 alone)
         assert ctx.verify_proof(proof), ctx.last_error()
         t0 = time.perf_counter()
         for _ in range(5):
@@ -316,12 +479,21 @@ def main():
         mock_ms = (time.perf_counter() - t0) / 5 * 1e3
     barrier()
 
+    # ---- the sharded single proof, visible to the driver's scaling run --------------------------------
+    split_parity = strong_split = None
+    if world > 1 and not split and not args.no_split_section:
+        for c in ctxs[1:]:
+            c.close()   # the configs[3] circuit needs the memory of the extra proof streams
+        ctxs = ctxs[:1]
+        split_parity, strong_split = split_section(args, zk, torch, dist, rank, world, local_rank, barrier,
+                                                   max_over_ranks)
+
     if rank == 0:
         hbm_peak, hbm_kind = load_peaks()
         int_peak = ctx.bench_int_pipe(1, 20000)  # mad.wide.u32 instructions/s = 32x32->64 MAC/s
         steps = single_steps
         per = {name: (ms / steps, cnt / steps) for name, (ms, cnt) in report.items() if cnt}
-        R = 292 + 392 * ROUNDS
+        R = ROWS_PER_COMPRESSION
         # dominant kernel: MSM bucket accumulation
         # terms the accumulate launches process per proof: 13 full-width commitments (2 lookup, 5 grand
         # products, random, 3 h pieces, q', s), 12 advice columns (<= 32-bit cells), and the IPA: 5 rounds
@@ -340,10 +512,8 @@ def main():
             "kernel": "fixed_accumulate_kernel (+ heavy-bucket kernels)", "bound": "int_pipe",
             "achieved": achieved, "peak": int_peak / 1e12, "unit": "TMAC/s",
             "frac": achieved / (int_peak / 1e12) if achieved else None,
-            # dram__bytes_read.sum + dram__bytes_write.sum of one full-width launch (8.39 M sorted
-            # entries, k = 19) from the ncu --set full capture profiles/r01_fixed_accumulate_ncu_full_v2.txt;
-            # algorithmic bytes of that launch: 8.39 M x (64 B point + 4 B index) = 0.57 GB
-            "traffic": 1.073e9 if k == 19 else None,
+            "traffic": TRAFFIC_CAPTURE["bytes"] if k == 19 else None,
+            "traffic_source": TRAFFIC_CAPTURE["source"],
             "peak_source": "zk_bench_int_pipe mode 1 (mad.wide.u32) measured in this run; "
                            "MEASURED_PEAKS.json has no integer peak",
             "launches_per_proof": acc_launches, "avg_launch_ms": acc_ms / acc_launches if acc_launches else None,
@@ -393,12 +563,54 @@ def main():
                             "transcript round trips inside the call"},
             "gpu_launches": int(launches), "roofline": roofline, "kernels": others,
             "verify_proof_ms": verify_ms, "mock_verify_ms": mock_ms,
+            "proof_sha256": hashlib.sha256(proof).hexdigest(),
         }
+        if split_parity is not None:
+            line["split_parity"] = split_parity
+            line["strong_split"] = strong_split
         if not args.no_cpu_baseline:
-            op, cin, cseed = cpu_oracle_setup()
-            v, cdt, _ = cpu_prove_once(op, cin, cseed)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1,
-                                    "kind": "port", "sample": cpu_sample_text(cdt)}
+            # The CPU oracle, after the timed regions: (1) the bounded k = 17 sample is the cpu_baseline AND a
+            # parity gate — the GPU proves the same records with the same seed and must produce the same bytes
+            # ("GPU proof bytes == oracle proof bytes"); (2) the bench's own k = 19 proof is
+            # checked by the ORACLE's verify_proof under the oracle's own keygen_vk of the same circuit.
+            oracle_lib, _ = oracle_modules()
+            oracle = oracle_lib.load()
+            cores = oracle_lib.set_threads(oracle, 0)
+            cin = zk.synthetic_inputs(CPU_SAMPLE_N)
+            op, csetup = cpu_timed_setup(oracle_lib, oracle, CPU_SAMPLE_K, CPU_SAMPLE_N, seed)
+            cproof, cdt, csynth = cpu_prove(op, cin, CPU_SAMPLE_N, seed)
+            t0 = time.perf_counter()
+            assert op.verify(cproof)[0] == 0
+            cverify = time.perf_counter() - t0
+            small = zk.Context(local_rank)
+            small.params_generate_substitute(CPU_SAMPLE_K, seed)
+            small.keygen(ROUNDS, CPU_SAMPLE_N)
+            gproof = small.create_proof(cin, CPU_SAMPLE_N, seed)
+            k17_equal = gproof == cproof and small.vk_bytes() == op.vk_bytes()
+            small.close()
+            op.close()
+            gate = {"k17_sample_proof_and_vk_bytes_equal_oracle": bool(k17_equal)}
+            if not split:
+                t0 = time.perf_counter()
+                big = oracle_lib.OracleProver(oracle, k=k, seed=seed)
+                big.keygen_vk(ROUNDS, n)
+                vk_equal = big.vk_bytes() == ctx.vk_bytes()
+                rc, msg = big.verify(proof)
+                big.close()
+                gate.update({"bench_proof_accepted_by_oracle_verifier": rc == 0, "bench_vk_bytes_equal_oracle": bool(vk_equal),
+                             "oracle_check_s": time.perf_counter() - t0})
+            gate["ok"] = all(v for kk, v in gate.items() if kk != "oracle_check_s")
+            line["parity_gate"] = gate
+            line["cpu_baseline"] = {
+                "value": CPU_SAMPLE_N / cdt, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": "one proof of %d compressions at k=%d (create_proof incl. witness synthesis; "
+                          "params/keygen excluded), %.1f s, C++ oracle restating halo2_proofs 0.3.0, std::thread x %d; "
+                          "the same-config (k=19) figure and the one-thread figure are the --impl reference arm's"
+                          % (CPU_SAMPLE_N, CPU_SAMPLE_K, cdt, cores),
+                "phases": {"[Setup generation]": csetup["params_s"] + csetup["keygen_s"], "[Proof generation]": cdt,
+                           "[Proof verification]": cverify, "witness synthesis (inside proof generation)": csynth,
+                           "unit": "s"}}
+            assert gate["ok"], "parity gate failed: %s" % gate
         print(json.dumps(line))
     barrier()
     if world > 1:

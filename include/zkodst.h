@@ -144,6 +144,31 @@ int32_t zk_msm_vesta(zk_ctx* ctx, const void* scalars, const void* bases, uint64
  * (scaled by 1/n).  omega_n = ROOT_OF_UNITY^(2^(32 - log_n)). */
 int32_t zk_ntt_fp(zk_ctx* ctx, void* data, int32_t log_n, int32_t inverse, int32_t on_device);
 
+/* ---- the prover's own batched forms of K2-K5, over the context's params and keys ---------------
+ * These are the pipelines create_proof drives (not the stand-alone zk_msm_vesta / zk_ntt_fp above), exported
+ * so that each can be compared with a CPU implementation on its own.
+ *
+ * zk_commit_batch replaces `Params::commit` (basis 0: bases g, coefficient form) and
+ * `Params::commit_lagrange` (basis 1: bases g_lagrange) of halo2_proofs 0.3.0 for `ncols` columns at once
+ * (create_proof commits the 12 advice columns, the 5 grand products, the 3 pieces of h this way;
+ * blake2f-circuit/benches/blake2f.rs:125): out[m] = sum_t scalars[m][t] * base_t + blinds[m] * W.
+ * scalars: ncols x 2^k Montgomery Fp, column after column (host, or device when on_device != 0);
+ * blinds: ncols Montgomery Fp (host); out_affine: ncols x 64 B (host).  index_mask != 0 restricts the sum
+ * to the terms t with ((t & index_mask) != 0) == (index_select != 0): the support of the vectors L and R of
+ * an inner-product round (`best_multiexp(&p_prime[half..], &g_prime[..half])` in poly/commitment/prover.rs).
+ *
+ * zk_ntt_fp_batch: `batch` transforms of size 2^log_n in one sequence of launches, transform b reading
+ * in + b * 2^log_n and writing out + b * 2^log_n elements (in != out); same conventions as zk_ntt_fp.
+ *
+ * zk_coeff_to_cosets replaces `EvaluationDomain::coeff_to_extended` for `ncols` polynomials of the keys'
+ * domain: the quotient lives on three cosets c_j <omega_n>, c_j = zeta * omega_4n^j (j = 0, 1, 2) of halo2's
+ * extended domain of 4n points, so out[col][j][i] = extended(col)[4 i + j]; out: ncols x 3 x 2^k elements. */
+int32_t zk_commit_batch(zk_ctx* ctx, int32_t basis, const void* scalars, uint32_t ncols, const void* blinds,
+                        uint32_t index_mask, int32_t index_select, int32_t on_device, void* out_affine);
+int32_t zk_ntt_fp_batch(zk_ctx* ctx, const void* in, void* out, int32_t log_n, uint32_t batch, int32_t inverse,
+                        int32_t on_device);
+int32_t zk_coeff_to_cosets(zk_ctx* ctx, const void* coeffs, uint32_t ncols, int32_t on_device, void* out);
+
 /* ---- params, keys, proofs ---------------------------------------------------------------
  * Replace the reference's prove sequence (blake2f-circuit/benches/blake2f.rs:83-142):
  *   Params::<EqAffine>::new / read / write  ->  zk_params_generate_substitute / _load / _write

@@ -3,6 +3,7 @@
 // C entry points over the oracle so that tests/, __graft_entry__.smoke() and bench.py's
 // cpu_baseline / --impl reference legs can drive it through ctypes.  Nothing under
 // zk-odst_b200/ may load this library.
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -266,9 +267,22 @@ int zko_describe_circuit(int k, uint32_t rounds, size_t n_compressions, char* ou
 struct OracleProver {
   Params params;
   ProvingKey pk;
-  bool has_pk = false;
+  bool has_pk = false, has_vk = false;
   ProverTrace trace;
+  double synth_ms = 0, prove_ms = 0;  // last zko_create_proof: witness synthesis, the rest of create_proof
 };
+
+// worker threads: t >= 1, or 0 for all hardware threads; returns the count now in use
+int zko_set_threads(int t) {
+  set_oracle_threads(t);
+  return oracle_threads();
+}
+// milliseconds of the last zko_create_proof: out[0] = witness synthesis (Circuit::synthesize), out[1] = the rest
+void zko_last_proof_ms(void* h, double out[2]) {
+  auto* p = (OracleProver*)h;
+  out[0] = p->synth_ms;
+  out[1] = p->prove_ms;
+}
 
 void* zko_prover_new_substitute(int k, const uint8_t seed[16]) {
   try {
@@ -317,10 +331,23 @@ int zko_keygen(void* h, uint32_t rounds, size_t n_compressions) {
   auto* p = (OracleProver*)h;
   try {
     keygen(p->params, rounds, n_compressions, p->pk);
-    p->has_pk = true;
+    p->has_pk = p->has_vk = true;
     return 0;
   } catch (std::exception& e) {
     fprintf(stderr, "zko_keygen: %s\n", e.what());
+    return -3;
+  }
+}
+// keygen_vk only: enough for zko_vk_bytes and zko_verify_proof (no proving key)
+int zko_keygen_vk(void* h, uint32_t rounds, size_t n_compressions) {
+  auto* p = (OracleProver*)h;
+  try {
+    p->has_pk = false;
+    keygen(p->params, rounds, n_compressions, p->pk, true);
+    p->has_vk = true;
+    return 0;
+  } catch (std::exception& e) {
+    fprintf(stderr, "zko_keygen_vk: %s\n", e.what());
     return -3;
   }
 }
@@ -349,10 +376,15 @@ int zko_create_proof(void* h, const uint8_t* inputs213, size_t n_compressions, c
     if (rc) return rc;
     Blake2fAssignment as;
     as.want_shape = false;
+    const auto t0 = std::chrono::steady_clock::now();
     blake2f_synthesize(as, p->params.k, rounds, in.data(), n_compressions,
                        p->pk.vk.shape.blinding_factors);
+    const auto t1 = std::chrono::steady_clock::now();
     XorShiftRng rng(seed);
     std::vector<uint8_t> proof = create_proof(p->params, p->pk, as.advice, rng, &p->trace);
+    const auto t2 = std::chrono::steady_clock::now();
+    p->synth_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    p->prove_ms = std::chrono::duration<double, std::milli>(t2 - t1).count();
     if (*proof_len < proof.size()) {
       *proof_len = proof.size();
       return -8;
@@ -367,7 +399,7 @@ int zko_create_proof(void* h, const uint8_t* inputs213, size_t n_compressions, c
 }
 int zko_verify_proof(void* h, const uint8_t* proof, size_t len, char* msg, size_t msg_len) {
   auto* p = (OracleProver*)h;
-  if (!p->has_pk) return -6;
+  if (!p->has_vk) return -6;
   std::string why;
   bool ok = verify_proof(p->params, p->pk.vk, proof, len, &why);
   set_msg(msg, msg_len, why);

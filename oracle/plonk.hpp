@@ -180,8 +180,9 @@ struct PermutationAssembly {
   }
 };
 
+// vk_only: stop after `keygen_vk` (commitments + transcript_repr), which is all `verify_proof` needs
 static inline void keygen(const Params& params, uint32_t rounds, size_t n_compressions,
-                          ProvingKey& pk) {
+                          ProvingKey& pk, bool vk_only = false) {
   VerifyingKey& vk = pk.vk;
   build_shape(vk.shape, params.k, rounds, n_compressions);
   const ConstraintSystem& cs = vk.shape.cs;
@@ -217,6 +218,7 @@ static inline void keygen(const Params& params, uint32_t rounds, size_t n_compre
   vk.permutation_commitments.clear();
   for (auto& p : pk.perm_values) vk.permutation_commitments.push_back(params.commit_lagrange(p, Fp::one()).to_affine());
   vk.transcript_repr = vk_transcript_repr(vk);
+  if (vk_only) return;
   // pk
   pk.fixed_polys.clear();
   pk.fixed_cosets.clear();

@@ -15,13 +15,19 @@
 
 namespace zko {
 
-static inline int oracle_threads() {
+// Worker threads of the oracle: ZKO_THREADS or all hardware threads; settable at run time
+// (set_oracle_threads(1) mirrors the pinned reference, whose rayon feature is off: Cargo.toml:15).
+static inline int& oracle_threads_ref() {
   static int n = [] {
     const char* e = getenv("ZKO_THREADS");
     int v = e ? atoi(e) : (int)std::thread::hardware_concurrency();
     return v < 1 ? 1 : v;
   }();
   return n;
+}
+static inline int oracle_threads() { return oracle_threads_ref(); }
+static inline void set_oracle_threads(int t) {
+  oracle_threads_ref() = t < 1 ? (int)std::max(1u, std::thread::hardware_concurrency()) : t;
 }
 
 // parallel_for over [0, n) in contiguous chunks: fn(begin, end)

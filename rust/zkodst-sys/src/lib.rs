@@ -33,6 +33,12 @@ extern "C" {
     pub fn zk_msm_vesta(ctx: *mut zk_ctx, scalars: *const c_void, bases: *const c_void, n: u64,
         on_device: i32, out_affine: *mut c_void) -> i32;
     pub fn zk_ntt_fp(ctx: *mut zk_ctx, data: *mut c_void, log_n: i32, inverse: i32, on_device: i32) -> i32;
+    pub fn zk_commit_batch(ctx: *mut zk_ctx, basis: i32, scalars: *const c_void, ncols: u32, blinds: *const c_void,
+        index_mask: u32, index_select: i32, on_device: i32, out_affine: *mut c_void) -> i32;
+    pub fn zk_ntt_fp_batch(ctx: *mut zk_ctx, input: *const c_void, out: *mut c_void, log_n: i32, batch: u32,
+        inverse: i32, on_device: i32) -> i32;
+    pub fn zk_coeff_to_cosets(ctx: *mut zk_ctx, coeffs: *const c_void, ncols: u32, on_device: i32,
+        out: *mut c_void) -> i32;
     pub fn zk_params_generate_substitute(ctx: *mut zk_ctx, k: i32, seed: *const u8) -> i32;
     pub fn zk_params_load(ctx: *mut zk_ctx, bytes: *const u8, len: u64) -> i32;
     pub fn zk_params_write(ctx: *mut zk_ctx, out: *mut u8, len: *mut u64) -> i32;

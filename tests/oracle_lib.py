@@ -149,6 +149,7 @@ def _setup_prover_api(lib):
     lib.zko_params_write.argtypes = [vp, vp, sz]
     lib.zko_params_points.argtypes = [vp, c.c_int, vp]
     lib.zko_keygen.argtypes = [vp, u32, sz]
+    lib.zko_keygen_vk.argtypes = [vp, u32, sz]
     lib.zko_vk_bytes.restype = sz
     lib.zko_vk_bytes.argtypes = [vp, vp, sz]
     lib.zko_create_proof.argtypes = [vp, c.c_char_p, sz, c.c_char_p, vp, c.POINTER(sz)]
@@ -157,6 +158,8 @@ def _setup_prover_api(lib):
     lib.zko_ntt.argtypes = [vp, c.c_int, c.c_int]
     lib.zko_coeff_to_extended.argtypes = [vp, c.c_int, c.c_int, vp]
     lib.zko_random_fields.argtypes = [c.c_char_p, sz, vp]
+    lib.zko_set_threads.argtypes = [c.c_int]
+    lib.zko_last_proof_ms.argtypes = [vp, c.POINTER(c.c_double)]
 
 
 class OracleProver:
@@ -192,6 +195,11 @@ class OracleProver:
         rc = self.o.lib.zko_keygen(self.h, rounds, n_compressions)
         assert rc == 0, rc
 
+    def keygen_vk(self, rounds, n_compressions):
+        """keygen_vk only (commitments + transcript_repr): enough for vk_bytes() and verify()."""
+        rc = self.o.lib.zko_keygen_vk(self.h, rounds, n_compressions)
+        assert rc == 0, rc
+
     def vk_bytes(self):
         need = self.o.lib.zko_vk_bytes(self.h, None, 0)
         buf = np.zeros(need, dtype=np.uint8)
@@ -204,6 +212,12 @@ class OracleProver:
         rc = self.o.lib.zko_create_proof(self.h, inputs, n, seed, buf.ctypes.data, ctypes.byref(ln))
         assert rc == 0, rc
         return buf[:ln.value].tobytes()
+
+    def last_proof_ms(self):
+        """(witness synthesis ms, rest of create_proof ms) of the last create_proof."""
+        out = (ctypes.c_double * 2)()
+        self.o.lib.zko_last_proof_ms(self.h, out)
+        return out[0], out[1]
 
     def verify(self, proof):
         msg = ctypes.create_string_buffer(256)
@@ -230,3 +244,19 @@ def ntt(oracle, data, log_n, inverse):
     d = np.ascontiguousarray(data).copy()
     oracle.lib.zko_ntt(d.ctypes.data, log_n, 1 if inverse else 0)
     return d
+
+
+def set_threads(oracle, t):
+    """Worker threads of the oracle (0 = all hardware threads); returns the count in use."""
+    _setup_prover_api(oracle.lib)
+    return oracle.lib.zko_set_threads(t)
+
+
+def coeff_to_extended(oracle, coeffs, k, cs_degree=4):
+    """halo2 `coeff_to_extended`: n coefficients -> 4n evaluations on zeta * <omega_4n>."""
+    _setup_prover_api(oracle.lib)
+    n = 1 << k
+    out = np.zeros((n << 2, 4), dtype=np.uint64)
+    c = np.ascontiguousarray(coeffs)
+    oracle.lib.zko_coeff_to_extended(c.ctypes.data, k, cs_degree, out.ctypes.data)
+    return out

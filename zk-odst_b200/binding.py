@@ -57,6 +57,9 @@ def load_library():
             "zk_create_proof_device_inputs": (i32, [vp, vp, u64, c.c_char_p, vp, c.POINTER(u64)]),
             "zk_msm_vesta": (i32, [vp, vp, vp, u64, i32, vp]),
             "zk_ntt_fp": (i32, [vp, vp, i32, i32, i32]),
+            "zk_commit_batch": (i32, [vp, i32, vp, u32, vp, u32, i32, i32, vp]),
+            "zk_ntt_fp_batch": (i32, [vp, vp, vp, i32, u32, i32, i32]),
+            "zk_coeff_to_cosets": (i32, [vp, vp, u32, i32, vp]),
             "zk_blake2f_witness_batch": (i32, [vp, i32, u32, vp, u64, vp, vp]),
             "zk_blake2f_witness_batch_device": (i32, [vp, i32, u32, vp, u64, vp, vp]),
             "zk_eip152_validate": (i32, [c.c_char_p, u64, c.POINTER(u32)]),
@@ -326,6 +329,19 @@ class Context:
     def ntt(self, data, log_n, inverse=False, on_device=False):
         self._check(self.lib.zk_ntt_fp(self.h, _ptr(data), log_n, 1 if inverse else 0,
                                        1 if on_device else 0))
+
+    def commit_batch(self, basis, scalars, ncols, blinds, out_affine, index_mask=0, index_select=0,
+                     on_device=False):
+        """Params::commit (basis 0) / commit_lagrange (basis 1) of ncols columns in one batched pipeline."""
+        self._check(self.lib.zk_commit_batch(self.h, basis, _ptr(scalars), ncols, _ptr(blinds), index_mask,
+                                             index_select, 1 if on_device else 0, _ptr(out_affine)))
+
+    def ntt_batch(self, data_in, data_out, log_n, batch, inverse=False, on_device=False):
+        self._check(self.lib.zk_ntt_fp_batch(self.h, _ptr(data_in), _ptr(data_out), log_n, batch,
+                                             1 if inverse else 0, 1 if on_device else 0))
+
+    def coeff_to_cosets(self, coeffs, ncols, out, on_device=False):
+        self._check(self.lib.zk_coeff_to_cosets(self.h, _ptr(coeffs), ncols, 1 if on_device else 0, _ptr(out)))
 
     # ---- K1 ------------------------------------------------------------------------------
     def witness_batch(self, k, rounds, inputs, n_compressions, advice_out, digests_out=None):

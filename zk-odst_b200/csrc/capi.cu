@@ -15,10 +15,12 @@ int32_t set_error(zk_ctx* ctx, int32_t code, const std::string& msg) {
 int32_t check_cuda(zk_ctx* ctx, cudaError_t e, const char* what) {
   if (e == cudaSuccess) return ZK_OK;
   std::string msg = std::string(what) + ": " + cudaGetErrorString(e);
+  if (ctx && ctx->dist_failed && !ctx->err.empty()) msg += " [" + ctx->err + "]";  // reason given by dist_stream_sync
   return set_error(ctx, e == cudaErrorMemoryAllocation ? ZK_E_NOMEM : ZK_E_CUDA, msg);
 }
 
 cudaError_t zk_stream_sync(zk_ctx* ctx) {
+  if (ctx->nccl_comm) return dist_stream_sync(ctx);
   if (!ctx->blocking_sync) return cudaStreamSynchronize(ctx->stream);
   if (!ctx->sync_event) {
     cudaError_t e = cudaEventCreateWithFlags(&ctx->sync_event, cudaEventBlockingSync | cudaEventDisableTiming);
@@ -52,10 +54,13 @@ int32_t get_layout(zk_ctx* ctx, uint32_t rounds, DeviceRegionLayout** out) {
       return set_error(ctx, ZK_E_INVALID, e.what());
     }
     size_t bytes = L.host.desc.size() * sizeof(uint32_t);
+    DevTemps tmp;
+    tmp.own(&L.d_desc);
     ZK_CUDA(ctx, cudaMalloc((void**)&L.d_desc, bytes));
     ZK_CUDA(ctx, cudaMemcpyAsync(L.d_desc, L.host.desc.data(), bytes, cudaMemcpyHostToDevice,
                                  ctx->stream));
     ZK_CUDA(ctx, zk_stream_sync(ctx));
+    tmp.release(&L.d_desc);
     it = ctx->layouts.emplace(rounds, std::move(L)).first;
   }
   *out = &it->second;
@@ -255,6 +260,9 @@ int32_t zk_blake2f_witness_batch(zk_ctx* ctx, int32_t k, uint32_t rounds, const 
   if (!ctx) return ZK_E_INVALID;
   if (k < 17 || k > 28) return set_error(ctx, ZK_E_INVALID, "k out of range [17, 28]");
   if (!inputs && n_compressions) return set_error(ctx, ZK_E_INVALID, "null inputs");
+  // the row check of launch_witness, before the records are read or any size is multiplied out
+  if (n_compressions > ((1ull << k) - 6) / region_rows(rounds))
+    return set_error(ctx, ZK_E_ROWS, "compressions do not fit in 2^k rows");
   // EIP-152 rejection cases, checked before any device work
   for (uint64_t i = 0; i < n_compressions; i++) {
     const uint8_t* r = inputs + i * ZK_BLAKE2F_INPUT_BYTES;

@@ -9,8 +9,13 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <unistd.h>
+
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
+#include <string>
 #include <utility>
 #include <vector>
 
@@ -30,6 +35,8 @@ struct NcclApi {
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;                        // optional
+  ncclResult_t (*CommGetAsyncError)(ncclComm_t, ncclResult_t*) = nullptr;  // optional
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   bool ok = false;
 };
@@ -51,6 +58,8 @@ NcclApi& nccl() {
     a.GroupEnd = (decltype(a.GroupEnd))dlsym(a.lib, "ncclGroupEnd");
     a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.lib, "ncclCommDestroy");
     a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.lib, "ncclGetErrorString");
+    a.CommAbort = (decltype(a.CommAbort))dlsym(a.lib, "ncclCommAbort");
+    a.CommGetAsyncError = (decltype(a.CommGetAsyncError))dlsym(a.lib, "ncclCommGetAsyncError");
     a.ok = a.GetUniqueId && a.CommInitRank && a.AllGather && a.Send && a.Recv && a.GroupStart && a.GroupEnd &&
            a.CommDestroy && a.GetErrorString;
     return a;
@@ -138,6 +147,7 @@ int32_t dist_exchange_quotient_rows(zk_ctx* ctx, char* slots, size_t elem_bytes,
                                     uint32_t nslots) {
   const int world = ctx->dist_world, me = ctx->dist_rank;
   if (world <= 1) return ZK_OK;
+  if (!ctx->nccl_comm) return set_error(ctx, ZK_E_STATE, "the context left its group after an error");
   const uint64_t rows = en / (uint64_t)world;
   std::vector<std::vector<std::pair<uint64_t, uint64_t>>> segs(world);
   for (int q = 0; q < world; q++) dist_quotient_segments(n, rows * q, rows * (q + 1), segs[q]);
@@ -171,6 +181,7 @@ int32_t dist_exchange_quotient_rows(zk_ctx* ctx, char* slots, size_t elem_bytes,
 // results[m] <- sum over ranks of their results[m]; identical on every rank afterwards
 int32_t dist_sum_points(zk_ctx* ctx, XYZZ* results, int nb) {
   if (ctx->dist_world <= 1) return ZK_OK;
+  if (!ctx->nccl_comm) return set_error(ctx, ZK_E_STATE, "the context left its group after an error");
   const size_t bytes = (size_t)nb * sizeof(XYZZ);
   const int world = ctx->dist_world;
   int32_t rc = ensure_buf(ctx, ctx->dist_buf, bytes * (world + 1));
@@ -194,6 +205,7 @@ int32_t dist_sum_points(zk_ctx* ctx, XYZZ* results, int nb) {
 // host_out[i] <- sum over ranks of their d_vals[i] (device, `count` field elements); identical on every rank
 int32_t dist_sum_fields(zk_ctx* ctx, const Fp* d_vals, int count, Fp* host_out) {
   const int world = ctx->dist_world;
+  if (!ctx->nccl_comm) return set_error(ctx, ZK_E_STATE, "the context left its group after an error");
   const size_t bytes = (size_t)count * sizeof(Fp);
   int32_t rc = ensure_buf(ctx, ctx->dist_buf, bytes * world);
   if (rc) return rc;
@@ -211,9 +223,54 @@ int32_t dist_sum_fields(zk_ctx* ctx, const Fp* d_vals, int count, Fp* host_out) 
 }
 
 int32_t dist_allgather_device(zk_ctx* ctx, const void* send, void* recv, size_t bytes) {
+  if (!ctx->nccl_comm) return set_error(ctx, ZK_E_STATE, "the context left its group after an error");
   ncclResult_t r = nccl().AllGather(send, recv, bytes, ncclUint8, (ncclComm_t)ctx->nccl_comm, ctx->stream);
   if (r != ncclSuccess) return nccl_error(ctx, r, "ncclAllGather");
   return ZK_OK;
+}
+
+// Leaves the group after a local failure: the communicator is aborted (outstanding collectives of this rank
+// are cancelled) so that a rank which returned early cannot sit in the group half-alive.  Its peers, blocked
+// in the collectives it skipped, leave through the timed wait below.
+void dist_abort(zk_ctx* ctx) {
+  if (!ctx->nccl_comm) return;
+  if (nccl().CommAbort) nccl().CommAbort((ncclComm_t)ctx->nccl_comm);
+  else nccl().CommDestroy((ncclComm_t)ctx->nccl_comm);
+  ctx->nccl_comm = nullptr;
+  ctx->dist_failed = true;
+}
+
+// Host wait of a context that belongs to a group: polls the stream instead of blocking in the driver, watches
+// the communicator's asynchronous error state and gives up after ZK_DIST_TIMEOUT_S seconds (default 300), so
+// a peer that failed and skipped its collectives ends this rank's call with ZK_E_CUDA instead of a deadlock.
+cudaError_t dist_stream_sync(zk_ctx* ctx) {
+  static const double limit_s = [] {
+    const char* e = getenv("ZK_DIST_TIMEOUT_S");
+    const double v = e ? atof(e) : 300.0;
+    return v > 0 ? v : 300.0;
+  }();
+  const auto t0 = std::chrono::steady_clock::now();
+  uint32_t spins = 0;
+  for (;;) {
+    const cudaError_t q = cudaStreamQuery(ctx->stream);
+    if (q != cudaErrorNotReady) return q;
+    if ((++spins & 0x3ff) == 0) {
+      ncclResult_t async = ncclSuccess;
+      if (ctx->nccl_comm && nccl().CommGetAsyncError &&
+          nccl().CommGetAsyncError((ncclComm_t)ctx->nccl_comm, &async) == ncclSuccess && async != ncclSuccess &&
+          async != ncclInProgress) {
+        dist_abort(ctx);
+        ctx->err = std::string("NCCL asynchronous error: ") + nccl().GetErrorString(async);
+        return cudaErrorUnknown;
+      }
+      if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > limit_s) {
+        dist_abort(ctx);
+        ctx->err = "group wait timed out: a peer rank did not reach the collective (ZK_DIST_TIMEOUT_S)";
+        return cudaErrorLaunchTimeout;
+      }
+      if (ctx->blocking_sync) usleep(50);
+    }
+  }
 }
 
 void dist_free(zk_ctx* ctx) {

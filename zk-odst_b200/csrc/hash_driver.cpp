@@ -4,7 +4,12 @@
 // (blake2f-circuit/src/blake2f.rs:88-181): IV -> for every 128-byte block `initialization` +
 // `compress` -> `digest`.  Here the driver turns a message into the chain of EIP-152 records that
 // the batched circuit proves — record i carries the chaining value h_i, block i, the byte counter
-// and the final flag — so `zk_create_proof` over those records proves the whole BLAKE2b-512 hash.
+// and the final flag.  What `zk_create_proof` over those records proves: every record is a correct
+// evaluation of F (its h' cells are F of its h, m, t, f cells) and, when the keys were generated with
+// record chaining (zk_blake2f_keygen_chained, docs/CIRCUIT.md "Chaining"), that record i + 1 starts from
+// record i's output.  The circuit has no instance column (the reference passes `&[&[]]`,
+// benches/blake2f.rs:125): message, counter, flag and digest are not exposed to the verifier, so the proof
+// is a statement about *some* chain of compressions, bound to this message only for whoever knows the witness.
 // The chaining values need F itself (README.md "Function Compress"); 12 rounds of it per block on
 // the host are negligible next to the proof.
 #include <cstring>

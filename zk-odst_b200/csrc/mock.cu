@@ -98,8 +98,17 @@ extern "C" int32_t zk_mock_verify(zk_ctx* ctx, const uint8_t* inputs, uint64_t n
   const DeviceKeys& K = S->keys;
   if (n_compressions != K.n_compressions) return set_error(ctx, ZK_E_INVALID, "batch size differs from keygen");
   if (!advice_override && n_compressions && !inputs) return ZK_E_INVALID;
+  // the EIP-152 rejection cases zk_create_proof applies (prover.cu): a record with f > 1 or a foreign round
+  // count would otherwise yield a self-consistent witness of a different statement
+  for (uint64_t i = 0; i < n_compressions && !advice_override; i++) {
+    const uint8_t* r = inputs + i * ZK_BLAKE2F_INPUT_BYTES;
+    const uint32_t rr = ((uint32_t)r[0] << 24) | ((uint32_t)r[1] << 16) | ((uint32_t)r[2] << 8) | r[3];
+    if (r[212] > 1) return set_error(ctx, ZK_E_INPUT, "final-block flag must be 0 or 1");
+    if (rr != K.rounds) return set_error(ctx, ZK_E_INPUT, "record rounds differ from circuit rounds");
+  }
   ZK_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
+  ZK_CUDA(ctx, cudaMemsetAsync(ctx->d_status, 0, sizeof(int), st));  // a status bit can only come from this call
   const uint64_t n = K.n, usable = n - (BLINDING + 1);
   int32_t rc = ensure_buf(ctx, ctx->scratch_advice, (size_t)NUM_ADVICE_COLUMNS * n * sizeof(Fp));
   if (rc) return rc;
@@ -147,8 +156,14 @@ extern "C" int32_t zk_mock_verify(zk_ctx* ctx, const uint8_t* inputs, uint64_t n
   }
   ZK_CUDA(ctx, cudaGetLastError());
   unsigned long long first = 0;
+  int status = 0;
   ZK_CUDA(ctx, cudaMemcpyAsync(&first, d_first, 8, cudaMemcpyDeviceToHost, st));
+  ZK_CUDA(ctx, cudaMemcpyAsync(&status, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
   ZK_CUDA(ctx, zk_stream_sync(ctx));
+  if (status) {
+    cudaMemsetAsync(ctx->d_status, 0, sizeof(int), st);
+    return set_error(ctx, ZK_E_INPUT, "EIP-152 record rejected by the witness kernel (final flag or round count)");
+  }
   if (first == ~0ull) {
     if (failure) failure[0] = failure[1] = failure[2] = 0;
     return ZK_OK;

@@ -423,6 +423,9 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
   tr.common_scalar(K.transcript_repr);
 
   PhaseTrace phase(st);
+  // a status bit may only come from this call (an earlier asynchronous zk_blake2f_witness_batch_device that was
+  // never followed by zk_ctx_synchronize must not fail this proof)
+  ZK_CUDA(ctx, cudaMemsetAsync(ctx->d_status, 0, sizeof(int), st));
   // ---- witness (K1) ---------------------------------------------------------------------------------
   if (n_compressions)
     ZK_CUDA(ctx, cudaMemcpyAsync(W->inputs, inputs, n_compressions * 213,
@@ -1011,9 +1014,16 @@ static int32_t create_proof_entry(zk_ctx* ctx, const uint8_t* inputs, bool input
   try {
     rc = create_proof_impl(ctx, inputs, inputs_on_device, n_compressions, seed, proof);
   } catch (std::exception& e) {
+    if (ctx->dist_world > 1) dist_abort(ctx);
     return set_error(ctx, ZK_E_VERIFY, e.what());
   }
-  if (rc) return rc;
+  if (rc) {
+    // a rank of a group that fails has skipped collectives its peers are waiting in: leave the group so that
+    // they end with an error (dist_stream_sync) instead of waiting for this rank forever
+    // (input / constraint failures are decided identically by every rank from the replicated records: no abort)
+    if (ctx->dist_world > 1 && (rc == ZK_E_CUDA || rc == ZK_E_NOMEM)) dist_abort(ctx);
+    return rc;
+  }
   if (!proof_out || *proof_len < proof.size()) {
     *proof_len = proof.size();
     return set_error(ctx, ZK_E_BUFFER, "proof buffer too small");

@@ -241,6 +241,8 @@ extern "C" int32_t zk_params_generate_substitute(zk_ctx* ctx, int32_t k, const u
   uint64_t* d_raw = nullptr;
   Fp *d_s = nullptr, *d_sl = nullptr;
   Affine *d_table = nullptr, *g = nullptr, *gl = nullptr;
+  DevTemps tmp;  // frees whatever was allocated on every early return
+  tmp.own(&d_raw); tmp.own(&d_s); tmp.own(&d_sl); tmp.own(&d_table); tmp.own(&g); tmp.own(&gl);
   ZK_CUDA(ctx, cudaMalloc((void**)&d_raw, raw.size() * 8));
   ZK_CUDA(ctx, cudaMalloc((void**)&d_s, n * sizeof(Fp)));
   ZK_CUDA(ctx, cudaMalloc((void**)&d_sl, n * sizeof(Fp)));
@@ -261,12 +263,8 @@ extern "C" int32_t zk_params_generate_substitute(zk_ctx* ctx, int32_t k, const u
   ctx->launches++;
   ZK_CUDA(ctx, cudaGetLastError());
   ZK_CUDA(ctx, zk_stream_sync(ctx));
-  cudaFree(d_raw);
-  cudaFree(d_s);
-  cudaFree(d_sl);
-  cudaFree(d_table);
   Affine G = vesta_generator();
-  return install_params(ctx, k, g, gl, host_scalar_mul(G, sw), host_scalar_mul(G, su));
+  return install_params(ctx, k, tmp.release(&g), tmp.release(&gl), host_scalar_mul(G, sw), host_scalar_mul(G, su));
 }
 
 extern "C" int32_t zk_params_load(zk_ctx* ctx, const uint8_t* bytes, uint64_t len) {
@@ -281,6 +279,8 @@ extern "C" int32_t zk_params_load(zk_ctx* ctx, const uint8_t* bytes, uint64_t le
   uint8_t* d_bytes = nullptr;
   Affine *g = nullptr, *gl = nullptr, *d_wu = nullptr;
   int* d_bad = nullptr;
+  DevTemps tmp;
+  tmp.own(&d_bytes); tmp.own(&g); tmp.own(&gl); tmp.own(&d_wu); tmp.own(&d_bad);
   ZK_CUDA(ctx, cudaMalloc((void**)&d_bytes, len - 4));
   ZK_CUDA(ctx, cudaMalloc((void**)&g, (n + 2) * sizeof(Affine)));
   ZK_CUDA(ctx, cudaMalloc((void**)&gl, (n + 2) * sizeof(Affine)));
@@ -300,15 +300,8 @@ extern "C" int32_t zk_params_load(zk_ctx* ctx, const uint8_t* bytes, uint64_t le
   ZK_CUDA(ctx, cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
   ZK_CUDA(ctx, cudaMemcpyAsync(wu, d_wu, sizeof wu, cudaMemcpyDeviceToHost, st));
   ZK_CUDA(ctx, zk_stream_sync(ctx));
-  cudaFree(d_bytes);
-  cudaFree(d_wu);
-  cudaFree(d_bad);
-  if (bad) {
-    cudaFree(g);
-    cudaFree(gl);
-    return set_error(ctx, ZK_E_INVALID, "params: invalid point encoding");
-  }
-  return install_params(ctx, (int)k, g, gl, wu[0], wu[1]);
+  if (bad) return set_error(ctx, ZK_E_INVALID, "params: invalid point encoding");
+  return install_params(ctx, (int)k, tmp.release(&g), tmp.release(&gl), wu[0], wu[1]);
 }
 
 extern "C" int32_t zk_params_write(zk_ctx* ctx, uint8_t* out, uint64_t* len) {
@@ -324,6 +317,8 @@ extern "C" int32_t zk_params_write(zk_ctx* ctx, uint8_t* out, uint64_t* len) {
   ZK_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   uint8_t* d_bytes = nullptr;
+  DevTemps tmp;
+  tmp.own(&d_bytes);
   ZK_CUDA(ctx, cudaMalloc((void**)&d_bytes, 64 * n));
   const unsigned T = 256;
   compress_kernel<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(S->params.g, n, d_bytes);
@@ -333,7 +328,6 @@ extern "C" int32_t zk_params_write(zk_ctx* ctx, uint8_t* out, uint64_t* len) {
   memcpy(out, &k, 4);
   ZK_CUDA(ctx, cudaMemcpyAsync(out + 4, d_bytes, 64 * n, cudaMemcpyDeviceToHost, st));
   ZK_CUDA(ctx, zk_stream_sync(ctx));
-  cudaFree(d_bytes);
   point_to_bytes(S->params.w, out + 4 + 64 * n);
   point_to_bytes(S->params.u, out + 4 + 64 * n + 32);
   return ZK_OK;
@@ -512,7 +506,7 @@ extern "C" int32_t zk_blake2f_keygen(zk_ctx* ctx, uint32_t rounds, uint64_t n_co
   if (!S->has_params) return set_error(ctx, ZK_E_STATE, "keygen before params");
   ZK_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  if (S->has_keys) free_keys(S->keys);
+  free_keys(S->keys);  // unconditionally: a keygen that failed midway leaves allocations behind has_keys == false
   S->has_keys = false;
   DeviceKeys& K = S->keys;
   const int k = S->params.k;

@@ -292,7 +292,7 @@ int32_t launch_witness(zk_ctx* ctx, int32_t k, uint32_t rounds, const uint8_t* d
   if (rc) return rc;
   const uint64_t n = 1ull << k, R = L->host.rows;
   const uint64_t usable = n - 6;  // blinding_factors 5 + 1 (docs/CIRCUIT.md)
-  if (n_compressions * R > usable)
+  if (n_compressions > usable / R)  // no 64-bit wrap for absurd batch sizes
     return set_error(ctx, ZK_E_ROWS, "compressions do not fit in 2^k rows");
   const size_t smem = (size_t)L->host.trace_words * 8;
   constexpr int THREADS = 256;

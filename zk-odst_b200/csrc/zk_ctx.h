@@ -65,6 +65,7 @@ struct zk_ctx {
   // MSM split across GPUs (dist.cu): NCCL communicator (ncclComm_t), this rank, group size
   void* nccl_comm = nullptr;
   int dist_rank = 0, dist_world = 1;
+  bool dist_failed = false;  // the context aborted its communicator after an error (dist.cu)
   zkodst::DevBuf dist_buf;
   // host waits: spin (cudaStreamSynchronize) or sleep on a blocking event (many contexts per core)
   bool blocking_sync = false;
@@ -102,6 +103,27 @@ struct KernelTimer {  // CUDA-event bracket on the context's stream, only when t
   }
 };
 
+// Device temporaries of one call: freed when the holder goes out of scope (every early return included)
+// unless released to a longer-lived owner.
+struct DevTemps {
+  std::vector<void**> slots;
+  template <class T>
+  void own(T** p) { slots.push_back((void**)p); }
+  template <class T>
+  T* release(T** p) {
+    for (auto& s : slots)
+      if (s == (void**)p) s = nullptr;
+    return *p;
+  }
+  ~DevTemps() {
+    for (auto s : slots)
+      if (s && *s) {
+        cudaFree(*s);
+        *s = nullptr;
+      }
+  }
+};
+
 #define ZK_CUDA(ctx, call)                                        \
   do {                                                            \
     int32_t _rc = zkodst::check_cuda((ctx), (call), #call);       \
@@ -121,6 +143,9 @@ int32_t dist_exchange_quotient_rows(zk_ctx* ctx, char* slots, size_t elem_bytes,
 // host_out[i] <- sum over ranks of d_vals[i] (one small all-gather, summed on the host)
 int32_t dist_sum_fields(zk_ctx* ctx, const Fp* d_vals, int count, Fp* host_out);
 void dist_free(zk_ctx* ctx);
+// group contexts: leave the group after a local error; timed host wait that cannot deadlock on a failed peer
+void dist_abort(zk_ctx* ctx);
+cudaError_t dist_stream_sync(zk_ctx* ctx);
 
 // witness.cu
 int32_t launch_witness(zk_ctx* ctx, int32_t k, uint32_t rounds, const uint8_t* d_inputs,
