@@ -523,12 +523,14 @@ def main():
                           % (full_terms, " (rank 0's 1/%d share of each MSM)" % world if split else ""),
         }
         ntt_ms, ntt_launches = per.get("ntt", (0.0, 0.0))
-        # 19 inverse transforms to coefficients, 19 columns x 3 coset transforms, 3 inverse transforms of
-        # h's coset values: all of size n (the quotient lives on three cosets of the n-th roots)
+        # 17 inverse transforms to coefficients (the 19 witness columns less the two never-queried advice
+        # columns), 17 columns x 3 coset transforms, 3 inverse transforms of h's coset values: all of size n
+        # (the quotient lives on three cosets of the n-th roots)
         # (MSM-split group: rank 0 transforms ceil(19 / world) of the columns and evaluates 1 / world of the
         # quotient rows; the 3 transforms of h stay replicated)
         ext = 3 * nrows // share
-        own_cols = -(-19 // share)
+        blk_hi = min(-(-19 // share), 19)   # rank 0's block of the 19 column slots is [0, blk_hi)
+        own_cols = min(blk_hi, 10) + max(0, blk_hi - 12)   # slots 10, 11 (never-queried advice columns) are skipped
         n_transforms = own_cols + own_cols * 3 + 3
         ntt_bytes = n_transforms * 64 * nrows
         ntt_mac = n_transforms * (nrows // 2) * k * MAC_PER_FP_MUL

@@ -68,8 +68,10 @@ int32_t zk_ctx_timing_report(zk_ctx* ctx, float* ms_per_class, uint32_t* launche
 
 /* Integer-pipe micro-benchmark (the compute roofline of the field-arithmetic kernels;
  * SURVEY.md §6 asks for it because no INT32 peak was measured by the driver).
- * mode 0 = mad.lo.u32, 1 = mad.wide.u32, 2 = mad.lo.cc/madc.hi.cc chain.  Writes issued
- * instructions per second over the whole device. */
+ * mode 0 = mad.lo.u32, 1 = mad.wide.u32, 2 = mad.lo.cc/madc.hi.cc chain, 9 = fma.rn.f64, 10 = fma.rn.f64 and
+ * mad.wide.u32 interleaved one to one (do the two pipes issue side by side?): issued instructions per second
+ * over the whole device.  3 = Fq Montgomery products per second, 4 = XYZZ mixed additions per second (5: with
+ * the product as a real call; 6, 7, 8: at 5, 6, 8 resident blocks per SM). */
 int32_t zk_bench_int_pipe(zk_ctx* ctx, int32_t mode, uint32_t iters, double* instr_per_sec);
 
 /* ---- circuit shape ------------------------------------------------------------------- */
@@ -185,7 +187,15 @@ int32_t zk_params_load(zk_ctx* ctx, const uint8_t* bytes, uint64_t len);
 int32_t zk_params_write(zk_ctx* ctx, uint8_t* out, uint64_t* len);
 /* Keys for a circuit of n_compressions regions of `rounds` rounds at the params' k. */
 int32_t zk_blake2f_keygen(zk_ctx* ctx, uint32_t rounds, uint64_t n_compressions);
-/* 10 fixed + 8 permutation commitments (32 B compressed each) followed by vk.transcript_repr. */
+/* The same with record chaining, the in-circuit form of `CompressionConfig::initialize_with_state`
+ * (blake2f-circuit/src/blake2f/table16/compression.rs:1096-1111; the streaming gadget's
+ * `Blake2f::update`, src/blake2f.rs:101-140): chain[j] != 0 (j >= 1; chain[0] must be 0) copy-constrains the
+ * eight h word cells of compression j to the output words h' of compression j - 1, so a proof binds the
+ * whole chain of a multi-block hash (zk_blake2b_records emits such chains; records of different messages
+ * start with chain[j] = 0).  chain: n_compressions bytes, or NULL for independent compressions.  The
+ * chain pattern is part of the verifying key. */
+int32_t zk_blake2f_keygen_chained(zk_ctx* ctx, uint32_t rounds, uint64_t n_compressions, const uint8_t* chain);
+/* 12 fixed + 8 permutation commitments (32 B compressed each) followed by vk.transcript_repr. */
 int32_t zk_vk_bytes(zk_ctx* ctx, uint8_t* out, uint64_t* len);
 /* Inject a genuine halo2 `vk.transcript_repr` (32 B canonical LE) in place of the substitute
  * hash (the Rust `{:?}` rendering of vk.pinned() is not reproducible here). */
@@ -213,7 +223,8 @@ int32_t zk_verify_proof(zk_ctx* ctx, const uint8_t* proof, uint64_t proof_len);
  * the spread table, every copy constraint.  The witness comes from `inputs` (n_compressions x 213 B,
  * host) or, when advice_override is not NULL, from that host buffer (ZK_NUM_ADVICE x 2^k x 32 B,
  * column-major Montgomery cells, the layout of zk_blake2f_witness_batch).  ZK_E_VERIFY on the first
- * failure, described in failure[3] = {kind (1 gate, 2 lookup, 3 copy), row, gate / copy index}. */
+ * failure, described in failure[3] = {kind (1 gate, 2 lookup, 3 copy), row, gate / copy index; a failed
+ * chaining copy of zk_blake2f_keygen_chained reports index 0xffff}. */
 int32_t zk_mock_verify(zk_ctx* ctx, const uint8_t* inputs, uint64_t n_compressions,
                        const void* advice_override, uint64_t failure[3]);
 

@@ -72,8 +72,10 @@ static inline int parse_eip152(const uint8_t in[213], Blake2fInput& out) {
 static const int A2IDX[10] = {7, 8, 9, 1, 2, 0, 3, 4, 5, 6};
 static const int NUM_ADVICE = 12;
 
+// the reference's 12 selectors (compression.rs:561-577), then the two this completion adds to pin the IV
+// words to constants and the final-flag mask to {0, 2^64 - 1} (docs/CIRCUIT.md "Pinned inputs")
 enum Sel {
-  S_A1 = 0, S_B1, S_C1, S_D1, S_A2, S_B2, S_C2, S_D2, S_ABCD, S_EFGH, S_IJKL, S_DIGEST, NUM_SEL
+  S_A1 = 0, S_B1, S_C1, S_D1, S_A2, S_B2, S_C2, S_D2, S_ABCD, S_EFGH, S_IJKL, S_DIGEST, S_CONST, S_FMASK, NUM_SEL
 };
 
 // rows per compression: 35 input words x4 + 3 init XORs x8 + rounds x 8 G x 49 + 8 x (8+8)
@@ -82,6 +84,7 @@ static inline size_t rows_per_compression(uint32_t rounds) { return 292 + 392 * 
 struct Blake2fConfig {
   int a[10];  // advice column index per a-number
   int table_tag, table_dense, table_spread;
+  int constants;  // fixed column holding the constant an `s_const` row pins a_3 to
   int sel[NUM_SEL];
 };
 
@@ -123,6 +126,7 @@ static inline Blake2fConfig blake2f_configure(ConstraintSystem& cs) {
   for (int i = 1; i <= 8; i++) cs.enable_equality(c.a[i]);  // table16.rs:312-314
   // selectors in the reference's declaration order (compression.rs:561-577)
   for (int i = 0; i < NUM_SEL; i++) c.sel[i] = cs.selector();
+  c.constants = cs.fixed_column();  // fixed column 3 (after the three table columns)
 
   auto A = [&](int an, int rot) { return cs.query_advice(c.a[an], rot); };
   const int PREV = -1, CUR = 0, NEXT = 1;
@@ -234,6 +238,19 @@ static inline Blake2fConfig blake2f_configure(ConstraintSystem& cs) {
                    {{"xor", s * (acc - even - odd * pow2(1))},
                     {"word", s * (out - d0 - d1 * pow2(16) - d2 * pow2(32) - d3 * pow2(48))}});
   }
+  // -- pinned inputs (the reference witnesses the IV freely, subregion_initial.rs:11-52, and never builds
+  //    the final-flag word; a proof of F must bind both): the word cell of an IV slot equals the constants
+  //    column; the final-flag word is bit * (2^64 - 1) with bit boolean in a_9
+  {
+    E s = cs.query_selector(c.sel[S_CONST]);
+    cs.create_gate("pin constant", {{"word", s * (A(3, CUR) - cs.query_fixed(c.constants, 0))}});
+  }
+  {
+    E s = cs.query_selector(c.sel[S_FMASK]);
+    E word = A(3, CUR), bit = A(9, CUR);
+    cs.create_gate("final flag", {{"mask", s * (word - bit * (pow2(64) - Fp::one()))},
+                                  {"bit", s * (bit * (bit - e_u64(1)))}});
+  }
   return c;
 }
 
@@ -254,6 +271,7 @@ struct Blake2fAssignment {
   // advice cell values as integers (every cell of this circuit is < 2^64); [halo2 column idx][row]
   std::vector<std::vector<uint64_t>> advice;
   std::vector<std::vector<uint8_t>> selectors;  // [selector][row]
+  std::vector<uint64_t> constants;              // [row]: the constants fixed column (shape pass)
   // copy constraints in call order: (left column idx, left row, right column idx, right row)
   struct Copy { int lc; size_t lr; int rc; size_t rr; };
   std::vector<Copy> copies;
@@ -436,16 +454,37 @@ struct Blake2fSynth {
     return e;
   }
 
-  // one compression region starting at row `base` (docs/CIRCUIT.md §Region)
-  void compression(size_t base, const Blake2fInput& in, std::array<uint64_t, 8>& out) {
+  // rows (relative to the region start) of the word cells the chaining copies connect: h_i enters in
+  // a_3 of its S_ABCD slot, h'_i leaves in a_5 of its S_DIGEST slot (docs/CIRCUIT.md "Chaining")
+  static size_t h_word_row(int i) { return 4 * (size_t)i + 1; }
+  static size_t out_word_row(uint32_t rounds, int i) {
+    return rows_per_compression(rounds) - 128 + 16 * (size_t)i + 10;
+  }
+
+  // one compression region starting at row `base` (docs/CIRCUIT.md §Region); prev_base != SIZE_MAX: the
+  // region continues the compression at prev_base (CompressionConfig::initialize_with_state,
+  // compression.rs:1096-1111): each h_i word cell is copy-constrained to that region's output word h'_i
+  void compression(size_t base, const Blake2fInput& in, std::array<uint64_t, 8>& out,
+                   size_t prev_base = (size_t)-1) {
     size_t r = base;
     WordRef h[8], iv[8], m[16], t0, t1, fm;
-    for (int i = 0; i < 8; i++, r += 4) h[i] = input_word(r, in.h[i]);
-    for (int i = 0; i < 8; i++, r += 4) iv[i] = input_word(r, BLAKE2B_IV[i]);
+    for (int i = 0; i < 8; i++, r += 4) {
+      h[i] = input_word(r, in.h[i]);
+      if (prev_base != (size_t)-1 && as.want_shape)
+        as.copies.push_back({A2IDX[5], prev_base + out_word_row(as.rounds, i), A2IDX[3], r + 1});
+    }
+    for (int i = 0; i < 8; i++, r += 4) {
+      iv[i] = input_word(r, BLAKE2B_IV[i]);
+      enable(S_CONST, r + 1);
+      if (as.want_shape) as.constants[r + 1] = BLAKE2B_IV[i];
+    }
     for (int i = 0; i < 16; i++, r += 4) m[i] = input_word(r, in.m[i]);
     t0 = input_word(r, in.t[0]); r += 4;
     t1 = input_word(r, in.t[1]); r += 4;
-    fm = input_word(r, in.f ? ~0ull : 0ull); r += 4;
+    fm = input_word(r, in.f ? ~0ull : 0ull);
+    put(9, r + 1, in.f ? 1 : 0);
+    enable(S_FMASK, r + 1);
+    r += 4;
     WordRef v[16];
     for (int i = 0; i < 8; i++) {
       v[i] = h[i];
@@ -480,9 +519,10 @@ struct Blake2fSynth {
 };
 
 // Circuit::synthesize for a batch: compression j occupies rows [j*R, (j+1)*R).
+// chain (n_compressions flags, or null): chain[j] != 0 makes compression j continue compression j - 1.
 static inline void blake2f_synthesize(Blake2fAssignment& as, int k, uint32_t rounds,
                                       const Blake2fInput* inputs, size_t n_compressions,
-                                      int blinding_factors) {
+                                      int blinding_factors, const uint8_t* chain = nullptr) {
   as.n = (size_t)1 << k;
   as.rounds = rounds;
   as.n_compressions = n_compressions;
@@ -491,6 +531,8 @@ static inline void blake2f_synthesize(Blake2fAssignment& as, int k, uint32_t rou
   if (n_compressions * R > usable) throw std::runtime_error("not enough rows");
   if (as.want_witness) as.advice.assign(NUM_ADVICE, std::vector<uint64_t>(as.n, 0));
   if (as.want_shape) as.selectors.assign(NUM_SEL, std::vector<uint8_t>(as.n, 0));
+  if (as.want_shape) as.constants.assign(as.n, 0);
+  if (chain && n_compressions && chain[0]) throw std::runtime_error("the first compression cannot continue another");
   as.copies.clear();
   as.outputs.assign(n_compressions, {});
   bool keep_w = as.want_witness;
@@ -501,7 +543,8 @@ static inline void blake2f_synthesize(Blake2fAssignment& as, int k, uint32_t rou
   memset(&dummy, 0, sizeof dummy);
   for (size_t j = 0; j < n_compressions; j++) {
     if (inputs && inputs[j].rounds != rounds) throw std::runtime_error("rounds mismatch");
-    syn.compression(j * R, inputs ? inputs[j] : dummy, as.outputs[j]);
+    syn.compression(j * R, inputs ? inputs[j] : dummy, as.outputs[j],
+                    chain && chain[j] ? (j - 1) * R : (size_t)-1);
   }
 }
 

@@ -158,11 +158,11 @@ int zko_blake2f_witness(int k, uint32_t rounds, const uint8_t* inputs213, size_t
 }
 
 // MockProver-equivalent over an advice matrix given as integers (12 * n u64, column-major).
-int zko_mock_verify_raw(int k, uint32_t rounds, size_t n_compressions, const uint64_t* advice_raw,
-                        char* msg, size_t msg_len) {
+static int mock_verify_raw_impl(int k, uint32_t rounds, size_t n_compressions, const uint8_t* chain,
+                                const uint64_t* advice_raw, char* msg, size_t msg_len) {
   try {
     CircuitShape sh;
-    build_shape(sh, k, rounds, n_compressions);
+    build_shape(sh, k, rounds, n_compressions, chain);
     std::vector<std::vector<uint64_t>> adv(NUM_ADVICE, std::vector<uint64_t>(sh.n));
     for (int c = 0; c < NUM_ADVICE; c++) memcpy(adv[c].data(), advice_raw + c * sh.n, 8 * sh.n);
     MockFailure f = mock_verify(sh, adv);
@@ -173,9 +173,20 @@ int zko_mock_verify_raw(int k, uint32_t rounds, size_t n_compressions, const uin
     return -3;
   }
 }
+int zko_mock_verify_raw(int k, uint32_t rounds, size_t n_compressions, const uint64_t* advice_raw,
+                        char* msg, size_t msg_len) {
+  return mock_verify_raw_impl(k, rounds, n_compressions, nullptr, advice_raw, msg, msg_len);
+}
 // Same, over Montgomery-form cells (what the CUDA path emits).  Any cell >= 2^64 fails.
+// chain: n_compressions flags or NULL (compression j continues compression j - 1).
+int zko_mock_verify_mont_chained(int k, uint32_t rounds, size_t n_compressions, const uint8_t* chain,
+                                 const uint64_t* advice_mont, char* msg, size_t msg_len);
 int zko_mock_verify_mont(int k, uint32_t rounds, size_t n_compressions,
                          const uint64_t* advice_mont, char* msg, size_t msg_len) {
+  return zko_mock_verify_mont_chained(k, rounds, n_compressions, nullptr, advice_mont, msg, msg_len);
+}
+int zko_mock_verify_mont_chained(int k, uint32_t rounds, size_t n_compressions, const uint8_t* chain,
+                                 const uint64_t* advice_mont, char* msg, size_t msg_len) {
   size_t n = (size_t)1 << k;
   std::vector<uint64_t> raw(NUM_ADVICE * n);
   for (size_t i = 0; i < NUM_ADVICE * n; i++) {
@@ -193,7 +204,7 @@ int zko_mock_verify_mont(int k, uint32_t rounds, size_t n_compressions,
     }
     raw[i] = r[0];
   }
-  return zko_mock_verify_raw(k, rounds, n_compressions, raw.data(), msg, msg_len);
+  return mock_verify_raw_impl(k, rounds, n_compressions, chain, raw.data(), msg, msg_len);
 }
 
 static uint64_t fnv1a(uint64_t h, const void* data, size_t len) {
@@ -335,6 +346,20 @@ int zko_keygen(void* h, uint32_t rounds, size_t n_compressions) {
     return 0;
   } catch (std::exception& e) {
     fprintf(stderr, "zko_keygen: %s\n", e.what());
+    return -3;
+  }
+}
+// keygen with record chaining (chain: n_compressions flags; compression j continues j - 1); vk_only as below
+int zko_keygen_chained(void* h, uint32_t rounds, size_t n_compressions, const uint8_t* chain, int vk_only) {
+  auto* p = (OracleProver*)h;
+  try {
+    p->has_pk = false;
+    keygen(p->params, rounds, n_compressions, p->pk, vk_only != 0, chain);
+    p->has_vk = true;
+    p->has_pk = !vk_only;
+    return 0;
+  } catch (std::exception& e) {
+    fprintf(stderr, "zko_keygen_chained: %s\n", e.what());
     return -3;
   }
 }

@@ -22,7 +22,8 @@ struct CircuitShape {
   size_t n_compressions = 0;
   ConstraintSystem cs;
   Blake2fConfig cfg;
-  std::vector<std::vector<uint32_t>> fixed;  // [fixed column][row] small integers
+  std::vector<std::vector<uint64_t>> fixed;  // [fixed column][row] integers (< 2^64)
+  std::vector<uint8_t> chain;                // [compression]: continues the previous one
   std::vector<SelectorAssignment> selector_assignments;
   std::vector<Blake2fAssignment::Copy> copies;
   int blinding_factors = 0;
@@ -30,7 +31,10 @@ struct CircuitShape {
 };
 
 // keygen's witness-less pass: configure, synthesize shape, load table, compress selectors
-static inline void build_shape(CircuitShape& sh, int k, uint32_t rounds, size_t n_compressions) {
+static inline void build_shape(CircuitShape& sh, int k, uint32_t rounds, size_t n_compressions,
+                               const uint8_t* chain = nullptr) {
+  sh.chain.assign(n_compressions, 0);
+  if (chain) sh.chain.assign(chain, chain + n_compressions);
   sh.k = k;
   sh.n = (size_t)1 << k;
   sh.rounds = rounds;
@@ -43,16 +47,21 @@ static inline void build_shape(CircuitShape& sh, int k, uint32_t rounds, size_t 
   Blake2fAssignment as;
   as.want_witness = false;
   as.want_shape = true;
-  blake2f_synthesize(as, k, rounds, nullptr, n_compressions, sh.blinding_factors);
+  blake2f_synthesize(as, k, rounds, nullptr, n_compressions, sh.blinding_factors, chain);
   sh.copies = as.copies;
   // SpreadTableChip::load (spread_table.rs:470-508); tail rows take the first row's value
-  sh.fixed.assign(3, std::vector<uint32_t>(sh.n, 0));
-  for (uint32_t i = 0; i < (1u << 16); i++)
-    spread_table_row(i, sh.fixed[sh.cfg.table_tag][i], sh.fixed[sh.cfg.table_dense][i],
-                     sh.fixed[sh.cfg.table_spread][i]);
+  sh.fixed.assign(sh.cs.num_fixed_columns, std::vector<uint64_t>(sh.n, 0));
+  for (uint32_t i = 0; i < (1u << 16); i++) {
+    uint32_t tag, dense, spread;
+    spread_table_row(i, tag, dense, spread);
+    sh.fixed[sh.cfg.table_tag][i] = tag;
+    sh.fixed[sh.cfg.table_dense][i] = dense;
+    sh.fixed[sh.cfg.table_spread][i] = spread;
+  }
+  sh.fixed[sh.cfg.constants] = as.constants;
   auto combos = compress_selectors(sh.cs, as.selectors, sh.selector_assignments);
   for (auto& c : combos) {
-    std::vector<uint32_t> col(sh.n);
+    std::vector<uint64_t> col(sh.n);
     for (size_t r = 0; r < sh.n; r++) col[r] = c[r];
     sh.fixed.push_back(col);
   }
@@ -85,7 +94,7 @@ static inline MockFailure mock_verify(const CircuitShape& sh,
   // gates
   for (size_t row = 0; row < sh.usable_rows && f.ok; row++) {
     bool any = false;
-    for (size_t c = 3; c < sh.fixed.size(); c++) any |= sh.fixed[c][row] != 0;
+    for (size_t c = 4; c < sh.fixed.size(); c++) any |= sh.fixed[c][row] != 0;  // compressed selector columns
     if (!any) continue;  // every polynomial carries a selector factor
     for (auto& g : sh.cs.gates)
       for (size_t pi = 0; pi < g.polys.size(); pi++) {

@@ -101,13 +101,20 @@ struct ProvingKey {
   std::vector<Poly> perm_values, perm_polys, perm_cosets;  // sigma columns
 };
 
-static const char* CIRCUIT_VERSION = "zkodst-blake2f-table16-v1";
+static const char* CIRCUIT_VERSION = "zkodst-blake2f-table16-v2";
 
 static inline Fp vk_transcript_repr(const VerifyingKey& vk) {
   char head[128];
   snprintf(head, sizeof head, "%s;k=%d;rounds=%u;n=%zu;", CIRCUIT_VERSION, vk.shape.k,
            vk.shape.rounds, vk.shape.n_compressions);
   std::string s = head;
+  bool chained = false;
+  for (uint8_t c : vk.shape.chain) chained |= c != 0;
+  if (chained) {  // which compressions continue their predecessor (one character each)
+    s += "chain=";
+    for (uint8_t c : vk.shape.chain) s += c ? '1' : '0';
+    s += ";";
+  }
   auto hex = [&](const Affine& p) {
     uint8_t b[32];
     p.to_bytes(b);
@@ -127,9 +134,9 @@ static inline Fp vk_transcript_repr(const VerifyingKey& vk) {
   return Fp::from_uniform_bytes(out);
 }
 
-static inline Poly small_to_poly(const std::vector<uint32_t>& v) {
+static inline Poly small_to_poly(const std::vector<uint64_t>& v) {
   Poly p(v.size());
-  std::map<uint32_t, Fp> cache;
+  std::map<uint64_t, Fp> cache;
   for (size_t i = 0; i < v.size(); i++) {
     if (v[i] < 4) {
       auto it = cache.find(v[i]);
@@ -182,9 +189,9 @@ struct PermutationAssembly {
 
 // vk_only: stop after `keygen_vk` (commitments + transcript_repr), which is all `verify_proof` needs
 static inline void keygen(const Params& params, uint32_t rounds, size_t n_compressions,
-                          ProvingKey& pk, bool vk_only = false) {
+                          ProvingKey& pk, bool vk_only = false, const uint8_t* chain = nullptr) {
   VerifyingKey& vk = pk.vk;
-  build_shape(vk.shape, params.k, rounds, n_compressions);
+  build_shape(vk.shape, params.k, rounds, n_compressions, chain);
   const ConstraintSystem& cs = vk.shape.cs;
   vk.cs_degree = cs.degree();
   vk.domain = Domain(vk.cs_degree, params.k);

@@ -43,6 +43,7 @@ extern "C" {
     pub fn zk_params_load(ctx: *mut zk_ctx, bytes: *const u8, len: u64) -> i32;
     pub fn zk_params_write(ctx: *mut zk_ctx, out: *mut u8, len: *mut u64) -> i32;
     pub fn zk_blake2f_keygen(ctx: *mut zk_ctx, rounds: u32, n_compressions: u64) -> i32;
+    pub fn zk_blake2f_keygen_chained(ctx: *mut zk_ctx, rounds: u32, n_compressions: u64, chain: *const u8) -> i32;
     pub fn zk_vk_bytes(ctx: *mut zk_ctx, out: *mut u8, len: *mut u64) -> i32;
     pub fn zk_vk_repr_override(ctx: *mut zk_ctx, repr: *const u8) -> i32;
     pub fn zk_create_proof(ctx: *mut zk_ctx, inputs: *const u8, n_compressions: u64,

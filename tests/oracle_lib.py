@@ -34,6 +34,7 @@ class Oracle:
         lib.zko_blake2f_witness.argtypes = [c.c_int, u32, c.c_char_p, sz, vp, vp, vp]
         lib.zko_mock_verify_raw.argtypes = [c.c_int, u32, sz, vp, c.c_char_p, sz]
         lib.zko_mock_verify_mont.argtypes = [c.c_int, u32, sz, vp, c.c_char_p, sz]
+        lib.zko_mock_verify_mont_chained.argtypes = [c.c_int, u32, sz, c.c_char_p, vp, c.c_char_p, sz]
         lib.zko_layout_hash.argtypes = [u32, c.POINTER(u64), c.POINTER(u64), c.POINTER(u64)]
         lib.zko_describe_circuit.argtypes = [c.c_int, u32, sz, c.c_char_p, sz]
 
@@ -101,9 +102,10 @@ class Oracle:
         rc = self.lib.zko_mock_verify_raw(k, rounds, n, advice_raw.ctypes.data, msg, 512)
         return rc, msg.value.decode()
 
-    def mock_verify_mont(self, k, rounds, n, advice_mont):
+    def mock_verify_mont(self, k, rounds, n, advice_mont, chain=None):
         msg = ctypes.create_string_buffer(512)
-        rc = self.lib.zko_mock_verify_mont(k, rounds, n, advice_mont.ctypes.data, msg, 512)
+        rc = self.lib.zko_mock_verify_mont_chained(k, rounds, n, bytes(chain) if chain is not None else None,
+                                                   advice_mont.ctypes.data, msg, 512)
         return rc, msg.value.decode()
 
     def layout_hash(self, rounds):
@@ -150,6 +152,7 @@ def _setup_prover_api(lib):
     lib.zko_params_points.argtypes = [vp, c.c_int, vp]
     lib.zko_keygen.argtypes = [vp, u32, sz]
     lib.zko_keygen_vk.argtypes = [vp, u32, sz]
+    lib.zko_keygen_chained.argtypes = [vp, u32, sz, c.c_char_p, c.c_int]
     lib.zko_vk_bytes.restype = sz
     lib.zko_vk_bytes.argtypes = [vp, vp, sz]
     lib.zko_create_proof.argtypes = [vp, c.c_char_p, sz, c.c_char_p, vp, c.POINTER(sz)]
@@ -193,6 +196,11 @@ class OracleProver:
 
     def keygen(self, rounds, n_compressions):
         rc = self.o.lib.zko_keygen(self.h, rounds, n_compressions)
+        assert rc == 0, rc
+
+    def keygen_chained(self, rounds, n_compressions, chain, vk_only=False):
+        """keygen with chain[j] != 0 meaning compression j continues compression j - 1."""
+        rc = self.o.lib.zko_keygen_chained(self.h, rounds, n_compressions, bytes(chain), 1 if vk_only else 0)
         assert rc == 0, rc
 
     def keygen_vk(self, rounds, n_compressions):

@@ -13,7 +13,7 @@ def test_call_order_and_argument_errors(zk):
     seed = zk.REFERENCE_SEED
     inputs = zk.synthetic_inputs(2)
     for call in (lambda: ctx.keygen(12, 2), lambda: ctx.create_proof(inputs, 2, seed),
-                 lambda: ctx.verify_proof(b"\x00" * 4000), lambda: ctx.mock_verify(inputs, 2)):
+                 lambda: ctx.verify_proof(b"\x00" * 4064), lambda: ctx.mock_verify(inputs, 2)):
         with pytest.raises(zk.ZkError) as e:
             call()
         assert e.value.code == -6          # ZK_E_STATE: params / keys missing
@@ -36,9 +36,9 @@ def test_call_order_and_argument_errors(zk):
     ln = ctypes.c_uint64(16)
     small = ctypes.create_string_buffer(16)
     rc = lib.zk_create_proof(ctx.h, inputs, 2, bytes(seed), ctypes.cast(small, ctypes.c_void_p), ctypes.byref(ln))
-    assert rc == -8 and ln.value == 4000
+    assert rc == -8 and ln.value == 4064
     proof = ctx.create_proof(inputs, 2, seed)
-    assert len(proof) == 4000 and ctx.verify_proof(proof)
+    assert len(proof) == 4064 and ctx.verify_proof(proof)
     ctx.close()
 
 

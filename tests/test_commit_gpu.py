@@ -174,7 +174,7 @@ def test_config2_proof_bytes_match_oracle_k19(setup19, zk):
     assert ctx.vk_bytes() == op.vk_bytes(), "verifying key differs from the oracle's"
     proof = ctx.create_proof(inputs, n, seed)
     ref = op.create_proof(inputs, n, seed)
-    assert len(proof) == len(ref) == 4128
+    assert len(proof) == len(ref) == 4192
     diff = [i // 32 for i in range(0, len(ref), 32) if proof[i:i + 32] != ref[i:i + 32]]
     assert not diff, "proof chunks %s differ" % diff[:8]
     assert op.verify(proof)[0] == 0

@@ -66,4 +66,23 @@ def test_prove_a_multi_block_hash(zk, ctx, oracle):
     op = oracle_lib.OracleProver(oracle, params_bytes=ctx.params_write())
     op.keygen(12, n)
     assert op.verify(proof)[0] == 0
+    # The chained circuit (zk_blake2f_keygen_chained; CompressionConfig::initialize_with_state,
+    # compression.rs:1096-1111): h of block i + 1 is copy-constrained to the output of block i, so the proof binds
+    # the whole hash.  Keys, proof bytes and verdicts equal the oracle's; unrelated records are rejected.
+    chain = bytes([0, 1, 1])
+    ctx.keygen(12, n, chain=chain)
+    op.keygen_chained(12, n, chain)
+    assert ctx.vk_bytes() == op.vk_bytes()
+    assert ctx.mock_verify(records, n) is None
+    chained = ctx.create_proof(records, n, seed)
+    assert chained == op.create_proof(records, n, seed)
+    assert chained != proof
+    assert ctx.verify_proof(chained) and op.verify(chained)[0] == 0
+    assert not ctx.verify_proof(proof) and op.verify(proof)[0] != 0      # a proof for the unchained keys
+    unrelated = zk.synthetic_inputs(n)
+    fail = ctx.mock_verify(unrelated, n)
+    assert fail is not None and fail[0] == 3 and fail[2] == 0xffff, fail  # a chaining copy
+    assert not ctx.verify_proof(ctx.create_proof(unrelated, n, seed))
+    with pytest.raises(zk.ZkError):
+        ctx.keygen(12, n, chain=bytes([1, 0, 0]))
     op.close()

@@ -54,6 +54,53 @@ def test_layout_matches_product_tables(oracle, zk):
 def test_circuit_description(oracle):
     d = oracle.describe(17, 12, 1)
     assert d["degree"] == "4" and d["blinding_factors"] == "5"
-    assert d["num_advice"] == "12" and d["num_fixed"] == "10"
+    # 3 table columns, the constants column, 8 columns from compress_selectors
+    assert d["num_advice"] == "12" and d["num_fixed"] == "12"
     assert d["permutation_columns"] == "8;9;1;2;0;3;4;5;"
-    assert d["n_polys"] == "23"
+    assert d["n_polys"] == "26"
+    assert d["fixed_queries"] == "".join("%d,0;" % c for c in range(12))
+    # selector:fixed column:root:combination length — {a1} {b1,c1} {d1,b2,d2} {a2} {c2,abcd} {efgh,ijkl}
+    # {digest,const} {fmask} (docs/CIRCUIT.md "Selectors")
+    assert d["selectors"] == ("0:4:1:1;1:5:1:2;2:5:2:2;3:6:1:3;5:6:2:3;7:6:3:3;4:7:1:1;6:8:1:2;8:8:2:2;"
+                              "9:9:1:2;10:9:2:2;11:10:1:2;12:10:2:2;13:11:1:1;")
+
+
+def test_pinned_inputs_are_constrained(oracle, zk):
+    """The IV words and the final-flag mask are no longer free witnesses: changing an IV word cell (and its
+    limbs, consistently) or giving the mask a value other than 0 / 2^64 - 1 must fail a gate."""
+    rec = zk.synthetic_inputs(1)
+    _, raw, _ = oracle.witness(17, 12, rec, 1, mont=False, raw=True)
+    assert oracle.mock_verify_raw(17, 12, 1, raw)[0] == 0
+    # IV_0 lives in the S_ABCD slot at rows 32..35: word in a_3 (column 1) row 33, limbs in a_1 (column 8)
+    bad = raw.copy()
+    bad[1, 33] ^= 1          # word
+    bad[8, 32] ^= 1          # limb 0 (dense), keeps `decompose ABCD` satisfied
+    bad[9, 32] ^= 1          # its spread form (bit 0 spreads to bit 0)
+    rc, msg = oracle.mock_verify_raw(17, 12, 1, bad)
+    assert rc == 1 and "pin constant" in msg, msg
+    # final-flag mask slot: rows 35 * 4 - 4 = 136..139 (h 8, IV 8, m 16, t0, t1 precede it); bit in a_9 (column 6)
+    bad = raw.copy()
+    bad[6, 137] ^= 1
+    rc, msg = oracle.mock_verify_raw(17, 12, 1, bad)
+    assert rc == 1 and "final flag" in msg, msg
+
+
+def test_chained_records(oracle, zk):
+    """Record chaining (CompressionConfig::initialize_with_state, compression.rs:1096-1111): the records of a
+    multi-block hash satisfy the cross-region copies, unrelated records do not."""
+    import hashlib
+    msg = bytes(range(256)) + b"tail"            # 3 blocks
+    records, digest = zk.blake2b_records(msg)
+    assert digest == hashlib.blake2b(msg).digest()
+    n = len(records) // 213
+    assert n == 3
+    adv, _, _ = oracle.witness(17, 12, records, n)
+    chain = bytes([0, 1, 1])
+    assert oracle.mock_verify_mont(17, 12, n, adv, chain)[0] == 0
+    other = zk.synthetic_inputs(n)              # independent records: the chain copies cannot hold
+    adv2, _, _ = oracle.witness(17, 12, other, n)
+    assert oracle.mock_verify_mont(17, 12, n, adv2)[0] == 0
+    rc, why = oracle.mock_verify_mont(17, 12, n, adv2, chain)
+    assert rc == 1 and "Permutation" in why, why
+    rc, why = oracle.mock_verify_mont(17, 12, n, adv, bytes([1, 0, 0]))   # the first record has no predecessor
+    assert rc == -3 and "first compression" in why, why

@@ -56,7 +56,7 @@ def test_proof_bytes_match_oracle(setup17, zk):
     op.keygen(12, 2)
     proof = ctx.create_proof(inputs, 2, seed)
     ref = op.create_proof(inputs, 2, seed)
-    assert len(proof) == len(ref) == 4000
+    assert len(proof) == len(ref) == 4064
     assert first_diff(proof, ref) is None, "proof chunk %s differs" % first_diff(proof, ref)
     rc, msg = op.verify(proof)
     assert rc == 0, msg

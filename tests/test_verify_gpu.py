@@ -81,7 +81,9 @@ def test_mock_verify_passes_and_locates_failures(setup, oracle, zk):
     val = np.array(oracle_lib.Oracle._limbs(oracle.field_op(0, 4, 12345)[1]), dtype=np.uint64)
     kinds = set()
     cells = [(8, 3), (9, 4), (1, 2), (0, 5), (4, 9), (1, 300), (4, 299), (4, 308), (4, 311), (4, 332), (0, 401),
-             (1, 293), (8, 290), (8, 377), (4, R + 700), (2, 2000), (5, 4000), (10, 5)]
+             (1, 293), (8, 290), (8, 377), (4, R + 700), (2, 2000), (5, 4000), (10, 5),
+             # pinned inputs: the IV_0 word cell (pin constant), the final-flag bit and word (final flag)
+             (1, 33), (6, 137), (1, 137), (1, R + 33), (6, R + 137)]
     for col, r in cells:
         bad = adv.copy()
         bad[col, r] = val

@@ -51,6 +51,7 @@ def load_library():
             "zk_params_load": (i32, [vp, vp, u64]),
             "zk_params_write": (i32, [vp, vp, c.POINTER(u64)]),
             "zk_blake2f_keygen": (i32, [vp, u32, u64]),
+            "zk_blake2f_keygen_chained": (i32, [vp, u32, u64, c.c_char_p]),
             "zk_vk_bytes": (i32, [vp, vp, c.POINTER(u64)]),
             "zk_vk_repr_override": (i32, [vp, c.c_char_p]),
             "zk_create_proof": (i32, [vp, vp, u64, c.c_char_p, vp, c.POINTER(u64)]),
@@ -279,8 +280,13 @@ class Context:
         self._check(self.lib.zk_params_write(self.h, ctypes.cast(buf, ctypes.c_void_p), ctypes.byref(ln)))
         return buf.raw[:ln.value]
 
-    def keygen(self, rounds, n_compressions):
-        self._check(self.lib.zk_blake2f_keygen(self.h, rounds, n_compressions))
+    def keygen(self, rounds, n_compressions, chain=None):
+        """chain: n_compressions flags; chain[j] != 0 makes compression j continue compression j - 1."""
+        if chain is None:
+            self._check(self.lib.zk_blake2f_keygen(self.h, rounds, n_compressions))
+        else:
+            assert len(chain) == n_compressions
+            self._check(self.lib.zk_blake2f_keygen_chained(self.h, rounds, n_compressions, bytes(chain)))
 
     def vk_bytes(self):
         ln = ctypes.c_uint64(0)

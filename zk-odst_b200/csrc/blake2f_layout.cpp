@@ -11,6 +11,9 @@ namespace {
 //  idx7..9 = lookup inputs a_0,a_1,a_2).
 const uint8_t COL_OF_A[10] = {7, 8, 9, 1, 2, 0, 3, 4, 5, 6};
 
+const uint64_t IV[8] = {0x6a09e667f3bcc908ULL, 0xbb67ae8584caa73bULL, 0x3c6ef372fe94f82bULL, 0xa54ff53a5f1d36f1ULL,
+                        0x510e527fade682d1ULL, 0x9b05688c2b3e6c1fULL, 0x1f83d9abfb41bd6bULL, 0x5be0cd19137e2179ULL};
+
 const uint8_t SIGMA[10][16] = {
     {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15},
     {14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3},
@@ -182,16 +185,27 @@ void build_region_layout(uint32_t rounds, RegionLayout& L) {
   if (L.trace_words >= (1u << 18)) throw std::runtime_error("rounds too large for descriptors");
   L.desc.assign((size_t)NUM_USED_COLUMNS * L.rows, 0);
   L.selectors.assign((size_t)NUM_SELECTORS * L.rows, 0);
+  L.constants.assign(L.rows, 0);
   L.copies.clear();
   Builder b(L);
   uint32_t r = 0;
   Word h[8], iv[8], m[16], v[16];
-  for (int i = 0; i < 8; i++, r += 4) h[i] = b.input_word(r, TR_H + i);
-  for (int i = 0; i < 8; i++, r += 4) iv[i] = b.input_word(r, TR_IV + i);
+  for (int i = 0; i < 8; i++, r += 4) {
+    h[i] = b.input_word(r, TR_H + i);
+    L.h_word_row[i] = r + 1;
+  }
+  for (int i = 0; i < 8; i++, r += 4) {  // IV words: pinned to the constants column
+    iv[i] = b.input_word(r, TR_IV + i);
+    b.enable(SEL_CONST, r + 1);
+    L.constants[r + 1] = IV[i];
+  }
   for (int i = 0; i < 16; i++, r += 4) m[i] = b.input_word(r, TR_M + i);
   Word t0 = b.input_word(r, TR_T0); r += 4;
   Word t1 = b.input_word(r, TR_T1); r += 4;
-  Word fm = b.input_word(r, TR_FMASK); r += 4;
+  Word fm = b.input_word(r, TR_FMASK);  // final-flag mask = bit * (2^64 - 1), the bit in a_9
+  b.assign(9, r + 1, cell_desc(CK_DENSE, TR_FMASK, 0, 1));
+  b.enable(SEL_FMASK, r + 1);
+  r += 4;
   for (int i = 0; i < 8; i++) {
     v[i] = h[i];
     v[i + 8] = iv[i];
@@ -217,7 +231,9 @@ void build_region_layout(uint32_t rounds, RegionLayout& L) {
   }
   for (int i = 0; i < 8; i++) {
     Word t = b.xor_aligned(r, h[i], v[i], SEL_D1, 0); r += 8;
-    L.digest_word[i] = b.xor_digest(r, t, v[i + 8]); r += 8;
+    L.digest_word[i] = b.xor_digest(r, t, v[i + 8]);
+    L.out_word_row[i] = r + 2;
+    r += 8;
   }
   if (r != L.rows) throw std::logic_error("region row count mismatch");
   if (TR_OPS + 2 * b.next_op != L.trace_words) throw std::logic_error("trace word count mismatch");

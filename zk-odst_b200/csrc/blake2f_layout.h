@@ -26,9 +26,11 @@ static inline uint32_t cell_desc(uint32_t kind, uint32_t word, uint32_t rot, uin
 // words per operation in region order: primary (sum / xor) and secondary (carry / and).
 enum { TR_H = 0, TR_IV = 8, TR_M = 16, TR_T0 = 32, TR_T1 = 33, TR_FMASK = 34, TR_OPS = 35 };
 
+// the reference's 12 selectors (compression.rs:561-577), then the two that pin the IV words to the constants
+// column and the final-flag mask to {0, 2^64 - 1} (docs/CIRCUIT.md "Pinned inputs")
 enum Selector {
   SEL_A1 = 0, SEL_B1, SEL_C1, SEL_D1, SEL_A2, SEL_B2, SEL_C2, SEL_D2,
-  SEL_ABCD, SEL_EFGH, SEL_IJKL, SEL_DIGEST, NUM_SELECTORS
+  SEL_ABCD, SEL_EFGH, SEL_IJKL, SEL_DIGEST, SEL_CONST, SEL_FMASK, NUM_SELECTORS
 };
 
 static const int NUM_ADVICE_COLUMNS = 12;   // halo2 advice column indices 0..11
@@ -48,8 +50,13 @@ struct RegionLayout {
   std::vector<uint32_t> desc;             // [NUM_USED_COLUMNS][rows], by halo2 column index
   std::vector<CopyConstraint> copies;     // in copy_advice call order
   std::vector<uint8_t> selectors;         // [NUM_SELECTORS][rows]
+  std::vector<uint64_t> constants;        // [rows]: the constants fixed column (IV words on SEL_CONST rows)
   uint32_t digest_word[8];                // trace word index of each output word h'_i
+  // Word cells the chaining copies connect (CompressionConfig::initialize_with_state, compression.rs:1096-1111):
+  // h_i enters in a_3 (advice column 1) at h_word_row[i]; h'_i leaves in a_5 (advice column 0) at out_word_row[i].
+  uint32_t h_word_row[8], out_word_row[8];
 };
+static const uint8_t CHAIN_H_COLUMN = 1, CHAIN_OUT_COLUMN = 0;  // halo2 advice indices of a_3 and a_5
 
 static inline uint64_t region_rows(uint32_t rounds) { return 292ull + 392ull * rounds; }
 

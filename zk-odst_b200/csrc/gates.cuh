@@ -1,4 +1,4 @@
-// The 23 custom-gate polynomials of the BLAKE2f Table16 circuit (docs/CIRCUIT.md), written once for
+// The 26 custom-gate polynomials of the BLAKE2f Table16 circuit (docs/CIRCUIT.md), written once for
 // the three places that evaluate them: the fused quotient kernel (values on the extended coset,
 // quotient.cu), the MockProver-equivalent row checker (raw cell values, mock.cu) and the verifier
 // (evaluations at the challenge x read from the proof, verifier.cu).  Product code, host + device.
@@ -27,7 +27,7 @@ struct GateCells {
   Fp a9c;
 };
 static const int A_NUMBER_COLUMN[10] = {7, 8, 9, 1, 2, 0, 3, 4, 5, 6};
-constexpr int NUM_GATE_POLYS = 23;
+constexpr int NUM_GATE_POLYS = 26;
 
 struct GateConsts {
   Fp small[4];   // 0, 1, 2, 3
@@ -42,9 +42,9 @@ ZK_HD Fp selector_expr(const Fp& q, int root, int len, const Fp* small) {
   return e;
 }
 
-// Calls acc.fold(value) once per gate polynomial, in declaration order.
+// Calls acc.fold(value) once per gate polynomial, in declaration order.  cfix = the constants fixed column.
 template <class Acc>
-ZK_HD void fold_gates(Acc& H, const GateCells& v, const Fp* sel, const GateConsts& k) {
+ZK_HD void fold_gates(Acc& H, const GateCells& v, const Fp* sel, const GateConsts& k, const Fp& cfix) {
   const Fp one = Fp::one();
   const Fp &P1 = k.pow2[1], &P2 = k.pow2[2], &P8 = k.pow2[8], &P16 = k.pow2[16], &P30 = k.pow2[30],
            &P32 = k.pow2[32], &P48 = k.pow2[48], &P62 = k.pow2[62], &P64 = k.pow2[64], &P80 = k.pow2[80],
@@ -97,6 +97,11 @@ ZK_HD void fold_gates(Acc& H, const GateCells& v, const Fp* sel, const GateConst
   H.fold(sel[SEL_DIGEST] * (acc32 - (v.a2p + v.a2c * P32 + v.a2n * P64 + v.a5c * P96) -
                             (v.a6c + v.a7c * P32 + v.a8c * P64 + v.a3n * P96) * P1));
   H.fold(sel[SEL_DIGEST] * (v.a5n - v.a1p - v.a1c * P16 - v.a1n * P32 - v.a4n * P48));
+  // pin constant: the word cell of an IV slot equals the constants column
+  H.fold(sel[SEL_CONST] * (v.a3c - cfix));
+  // final flag: mask = bit * (2^64 - 1), bit boolean
+  H.fold(sel[SEL_FMASK] * (v.a3c - v.a9c * (P64 - one)));
+  H.fold(sel[SEL_FMASK] * (v.a9c * (v.a9c - one)));
 }
 
 }  // namespace zkodst

@@ -55,6 +55,44 @@ __global__ void __launch_bounds__(256) imad_kernel(uint32_t* out, uint32_t iters
   out[blockIdx.x * blockDim.x + threadIdx.x] = acc ^ (uint32_t)wacc ^ (uint32_t)(wacc >> 32);
 }
 
+// mode 9: fma.rn.f64 (DFMA), 8 independent chains; mode 10: the same DFMA stream interleaved one to one with
+// mad.wide.u32 — do the FP64 and the integer multiply pipes issue side by side?  (Counts DFMA + IMAD.)
+template <int MIX>
+__global__ void __launch_bounds__(256) dfma_kernel(uint32_t* out, uint32_t iters, uint32_t seed) {
+  double a = 1.0 + 1e-9 * (seed + threadIdx.x), b = 1.0 - 1e-9 * blockIdx.x;
+  double d0 = 1, d1 = 2, d2 = 3, d3 = 4, d4 = 5, d5 = 6, d6 = 7, d7 = 8;
+  uint32_t ia = seed + threadIdx.x, ib = seed * 3 + blockIdx.x;
+  uint64_t w0 = 1, w1 = 2, w2 = 3, w3 = 4, w4 = 5, w5 = 6, w6 = 7, w7 = 8;
+  for (uint32_t i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      if (MIX) {
+        asm volatile("fma.rn.f64 %0, %16, %17, %0;\n\tmad.wide.u32 %8, %18, %19, %8;\n\t"
+                     "fma.rn.f64 %1, %16, %17, %1;\n\tmad.wide.u32 %9, %18, %19, %9;\n\t"
+                     "fma.rn.f64 %2, %16, %17, %2;\n\tmad.wide.u32 %10, %18, %19, %10;\n\t"
+                     "fma.rn.f64 %3, %16, %17, %3;\n\tmad.wide.u32 %11, %18, %19, %11;\n\t"
+                     "fma.rn.f64 %4, %16, %17, %4;\n\tmad.wide.u32 %12, %18, %19, %12;\n\t"
+                     "fma.rn.f64 %5, %16, %17, %5;\n\tmad.wide.u32 %13, %18, %19, %13;\n\t"
+                     "fma.rn.f64 %6, %16, %17, %6;\n\tmad.wide.u32 %14, %18, %19, %14;\n\t"
+                     "fma.rn.f64 %7, %16, %17, %7;\n\tmad.wide.u32 %15, %18, %19, %15;"
+                     : "+d"(d0), "+d"(d1), "+d"(d2), "+d"(d3), "+d"(d4), "+d"(d5), "+d"(d6), "+d"(d7), "+l"(w0),
+                       "+l"(w1), "+l"(w2), "+l"(w3), "+l"(w4), "+l"(w5), "+l"(w6), "+l"(w7)
+                     : "d"(a), "d"(b), "r"(ia), "r"(ib));
+      } else {
+        asm volatile("fma.rn.f64 %0, %8, %9, %0;\n\tfma.rn.f64 %1, %8, %9, %1;\n\t"
+                     "fma.rn.f64 %2, %8, %9, %2;\n\tfma.rn.f64 %3, %8, %9, %3;\n\t"
+                     "fma.rn.f64 %4, %8, %9, %4;\n\tfma.rn.f64 %5, %8, %9, %5;\n\t"
+                     "fma.rn.f64 %6, %8, %9, %6;\n\tfma.rn.f64 %7, %8, %9, %7;"
+                     : "+d"(d0), "+d"(d1), "+d"(d2), "+d"(d3), "+d"(d4), "+d"(d5), "+d"(d6), "+d"(d7)
+                     : "d"(a), "d"(b));
+      }
+    }
+  }
+  const double acc = d0 + d1 + d2 + d3 + d4 + d5 + d6 + d7;
+  const uint64_t wacc = w0 ^ w1 ^ w2 ^ w3 ^ w4 ^ w5 ^ w6 ^ w7;
+  out[blockIdx.x * blockDim.x + threadIdx.x] = (uint32_t)__double_as_longlong(acc) ^ (uint32_t)wacc ^ (uint32_t)(wacc >> 32);
+}
+
 // mode 3: Fq Montgomery multiplications (4 independent chains per thread);
 // mode 4: XYZZ mixed additions (the MSM inner loop)
 __global__ void __launch_bounds__(128) fieldmul_kernel(uint64_t* out, uint32_t iters, uint64_t seed) {
@@ -113,9 +151,10 @@ using namespace zkodst;
 
 extern "C" int32_t zk_bench_int_pipe(zk_ctx* ctx, int32_t mode, uint32_t iters,
                                      double* instr_per_sec) {
-  if (!ctx || !instr_per_sec || mode < 0 || mode > 8) return ZK_E_INVALID;
+  if (!ctx || !instr_per_sec || mode < 0 || mode > 10) return ZK_E_INVALID;
   ZK_CUDA(ctx, cudaSetDevice(ctx->device));
-  const int blocks = ctx->sm_count * (mode >= 3 ? 120 : 8), threads = mode >= 3 ? 128 : 256;
+  const bool field_mode = mode >= 3 && mode <= 8;
+  const int blocks = ctx->sm_count * (field_mode ? 120 : 8), threads = field_mode ? 128 : 256;
   int32_t rc = ensure_buf(ctx, ctx->scratch_digests, (size_t)blocks * threads * 8);
   if (rc) return rc;
   uint32_t* out = (uint32_t*)ctx->scratch_digests.ptr;
@@ -133,6 +172,8 @@ extern "C" int32_t zk_bench_int_pipe(zk_ctx* ctx, int32_t mode, uint32_t iters,
     if (mode == 6) madd_kernel<5><<<blocks, threads, 0, ctx->stream>>>((uint64_t*)out, iters, 12345u + rep);
     if (mode == 7) madd_kernel<6><<<blocks, threads, 0, ctx->stream>>>((uint64_t*)out, iters, 12345u + rep);
     if (mode == 8) madd_kernel<8><<<blocks, threads, 0, ctx->stream>>>((uint64_t*)out, iters, 12345u + rep);
+    if (mode == 9) dfma_kernel<0><<<blocks, threads, 0, ctx->stream>>>(out, iters, 12345u + rep);
+    if (mode == 10) dfma_kernel<1><<<blocks, threads, 0, ctx->stream>>>(out, iters, 12345u + rep);
     if (mode == 5) madd_calls_kernel<<<blocks, threads, 0, ctx->stream>>>((uint64_t*)out, iters, 12345u + rep);
     ctx->launches++;
     ZK_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
@@ -143,7 +184,8 @@ extern "C" int32_t zk_bench_int_pipe(zk_ctx* ctx, int32_t mode, uint32_t iters,
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
-  double per_iter = mode == 3 ? 4.0 : (mode >= 4 ? 1.0 : 64.0);  // field mults / madds / instructions
+  // field mults / madds / instructions per loop iteration
+  double per_iter = mode == 3 ? 4.0 : (field_mode ? 1.0 : (mode == 10 ? 128.0 : 64.0));
   double instr = (double)blocks * threads * (double)iters * per_iter;
   *instr_per_sec = instr / (best * 1e-3);
   return ZK_OK;

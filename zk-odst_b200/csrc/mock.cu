@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(128) mock_rows_kernel(const __grid_constant__ 
   }
   if (any) {
     Checker c;
-    fold_gates(c, v, sel, ma.k);
+    fold_gates(c, v, sel, ma.k, ma.fixed[FIXED_CONSTANTS][r]);
     if (c.bad >= 0) report(first, 1, r, (uint64_t)c.bad);
   }
   // lookup: (a0, a1, a2) must be table row `dense`
@@ -83,6 +83,15 @@ __global__ void mock_copies_kernel(const __grid_constant__ MockArgs ma, const De
   const DevCopy c = copies[i];
   const uint64_t lr = region * region_rows + c.lrow, rr = region * region_rows + c.rrow;
   if (ma.advice[c.lcol][lr] != ma.advice[c.rcol][rr]) report(first, 3, lr, i);
+}
+
+// chaining copies (absolute rows): h_i of a continuing compression == h'_i of its predecessor
+__global__ void mock_chain_kernel(const __grid_constant__ MockArgs ma, const DevCopy* __restrict__ copies, uint32_t ncopies,
+                                  unsigned long long* first) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ncopies) return;
+  const DevCopy c = copies[t];
+  if (ma.advice[c.lcol][c.lrow] != ma.advice[c.rcol][c.rrow]) report(first, 3, c.lrow, 0xffff);
 }
 
 }  // namespace
@@ -153,6 +162,23 @@ extern "C" int32_t zk_mock_verify(zk_ctx* ctx, const uint8_t* inputs, uint64_t n
     mock_copies_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(args, d_copies, ncopies, n_compressions, K.region_rows,
                                                                        d_first);
     ctx->launches++;
+  }
+  {  // record chaining (zk_blake2f_keygen_chained): index 0xffff in the failure report
+    std::vector<DevCopy> cc;
+    for (uint64_t j = 1; j < n_compressions; j++)
+      if (K.chain[j])
+        for (int i = 0; i < 8; i++)
+          cc.push_back(DevCopy{CHAIN_OUT_COLUMN, (uint32_t)((j - 1) * K.region_rows + L->host.out_word_row[i]),
+                               CHAIN_H_COLUMN, (uint32_t)(j * K.region_rows + L->host.h_word_row[i])});
+    if (!cc.empty()) {
+      rc = ensure_buf(ctx, ctx->scratch_b, cc.size() * sizeof(DevCopy));
+      if (rc) return rc;
+      ZK_CUDA(ctx, cudaMemcpyAsync(ctx->scratch_b.ptr, cc.data(), cc.size() * sizeof(DevCopy), cudaMemcpyHostToDevice, st));
+      mock_chain_kernel<<<(unsigned)((cc.size() + 127) / 128), 128, 0, st>>>(args, (const DevCopy*)ctx->scratch_b.ptr,
+                                                                           (uint32_t)cc.size(), d_first);
+      ctx->launches++;
+      ZK_CUDA(ctx, zk_stream_sync(ctx));  // cc leaves scope
+    }
   }
   ZK_CUDA(ctx, cudaGetLastError());
   unsigned long long first = 0;

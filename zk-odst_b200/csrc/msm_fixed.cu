@@ -263,6 +263,110 @@ __device__ __forceinline__ uint32_t bucket_of_position(const uint32_t* __restric
   return lo;
 }
 
+// ---- experimental accumulation variants (ZK_ACC_VARIANT, see msm_fixed_batch) -----------------------------
+// The next point of a thread's chunk is staged in shared memory instead of registers, which frees 16 registers
+// per thread for a fifth resident block per SM.  STAGE = 1: per-thread cp.async (LDGSTS) of the 64-byte table
+// row, 16-byte pieces laid out [buffer][piece][thread] (conflict-free reads); STAGE = 2: one bulk asynchronous
+// copy per row (cp.async.bulk, the TMA engine; completion on a per-thread mbarrier), rows laid out
+// [buffer][thread][64 B].  Both double-buffered: the copy of entry pos + 2 is issued when entry pos has been read.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+template <int STAGE, int MINB>
+__global__ void __launch_bounds__(ACC_THREADS, MINB)
+fixed_accumulate_staged_kernel(const Affine* __restrict__ table, const uint32_t* __restrict__ sorted,
+                               const uint32_t* __restrict__ offsets, uint32_t nbuckets, const Plan* __restrict__ plan,
+                               XYZZ* __restrict__ heads, XYZZ* __restrict__ buckets) {
+  __shared__ __align__(128) uint4 stage[2 * 4 * ACC_THREADS];
+  __shared__ __align__(8) uint64_t bars[2 * ACC_THREADS];
+  const uint32_t tid = threadIdx.x;
+  const uint32_t entries = plan->entries, L = plan->chunk;
+  uint32_t phase[2] = {0, 0};
+  if (STAGE == 2) {
+    for (int b = 0; b < 2; b++)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bars[b * ACC_THREADS + tid])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  auto slot = [&](int buf, int piece) -> uint4* {
+    return STAGE == 1 ? &stage[(buf * 4 + piece) * ACC_THREADS + tid] : &stage[(buf * ACC_THREADS + tid) * 4 + piece];
+  };
+  auto issue = [&](int buf, uint32_t v) {
+    const uint4* src = reinterpret_cast<const uint4*>(table + (v & 0x7fffffffu));
+    if (STAGE == 1) {
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(slot(buf, j))), "l"(src + j) : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    } else {
+      const uint32_t bar = smem_addr(&bars[buf * ACC_THREADS + tid]);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 64;" ::"r"(bar) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 64, [%2];" ::"r"(
+                       smem_addr(slot(buf, 0))),
+                   "l"(src), "r"(bar)
+                   : "memory");
+    }
+  };
+  auto wait_for = [&](int buf, bool newest) {
+    if (STAGE == 1) {
+      if (newest) asm volatile("cp.async.wait_group 0;" ::: "memory");
+      else asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      const uint32_t bar = smem_addr(&bars[buf * ACC_THREADS + tid]);
+      uint32_t done = 0;
+      while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done)
+                     : "r"(bar), "r"(phase[buf])
+                     : "memory");
+      phase[buf] ^= 1;
+    }
+  };
+  auto take = [&](int buf, uint32_t v) {
+    Affine p;
+    uint4 q[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) q[j] = *slot(buf, j);
+    p.x.l[0] = (uint64_t)q[0].x | ((uint64_t)q[0].y << 32); p.x.l[1] = (uint64_t)q[0].z | ((uint64_t)q[0].w << 32);
+    p.x.l[2] = (uint64_t)q[1].x | ((uint64_t)q[1].y << 32); p.x.l[3] = (uint64_t)q[1].z | ((uint64_t)q[1].w << 32);
+    p.y.l[0] = (uint64_t)q[2].x | ((uint64_t)q[2].y << 32); p.y.l[1] = (uint64_t)q[2].z | ((uint64_t)q[2].w << 32);
+    p.y.l[2] = (uint64_t)q[3].x | ((uint64_t)q[3].y << 32); p.y.l[3] = (uint64_t)q[3].z | ((uint64_t)q[3].w << 32);
+    if (v & 0x80000000u) p.y = p.y.neg();
+    return p;
+  };
+  for (uint32_t chunk = blockIdx.x * ACC_THREADS + tid; chunk < plan->nchunks; chunk += gridDim.x * ACC_THREADS) {
+    const uint32_t start = chunk * L;
+    const uint32_t end = start + L < entries ? start + L : entries;
+    uint32_t b = bucket_of_position(offsets, 0, nbuckets - 1, start);
+    uint32_t boundary = offsets[b + 1];
+    bool first = true;
+    XYZZ acc = XYZZ::identity();
+    uint32_t v0 = sorted[start], v1 = start + 1 < end ? sorted[start + 1] : 0;
+    issue(0, v0);
+    if (start + 1 < end) issue(1, v1);
+    for (uint32_t pos = start; pos < end; pos++) {
+      const int buf = (pos - start) & 1;
+      wait_for(buf, pos + 1 >= end);
+      const Affine cur = take(buf, v0);
+      v0 = v1;
+      if (pos + 2 < end) {
+        v1 = sorted[pos + 2];
+        issue(buf, v1);
+      }
+      if (pos >= boundary) {
+        if (first) heads[chunk] = acc; else buckets[b] = acc;
+        first = false;
+        acc = XYZZ::identity();
+        b++;
+        boundary = offsets[b + 1];
+        if (pos >= boundary) {
+          b = bucket_of_position(offsets, b + 1, nbuckets - 1, pos);
+          boundary = offsets[b + 1];
+        }
+      }
+      acc = acc.add_affine(cur);
+    }
+    if (first) heads[chunk] = acc; else buckets[b] = acc;
+  }
+}
+
 // ---- accumulation: one chunk of `plan->chunk` consecutive sorted entries per thread -------------------
 __global__ void __launch_bounds__(ACC_THREADS, ACC_MIN_BLOCKS)
 fixed_accumulate_kernel(const Affine* __restrict__ table, const uint32_t* __restrict__ sorted,
@@ -488,13 +592,26 @@ int32_t msm_fixed_batch(zk_ctx* ctx, const FixedBase& fb, const MsmJob* jobs, in
   const uint64_t stride = count + 4;
   const uint64_t max_entries = (uint64_t)nb * nwin * stride;
   if (max_entries >= 0xffffffffull) return set_error(ctx, ZK_E_INVALID, "msm_fixed: batch too large");
-  static int acc_blocks_per_sm = 0;
-  if (!acc_blocks_per_sm) {
+  // Variant switch (measured: profiles/r02_accumulate_variants.json, 12 full-width columns at 2^19):
+  // 1 = cp.async staging at 5 resident blocks, the product path (15.6 ms); 0 = register prefetch at 4 blocks
+  // (16.1 ms, round 1); 2 = cp.async.bulk (TMA) + mbarrier staging at 5 blocks (17.0 ms: one bulk copy and one
+  // mbarrier round trip per 64-byte row cost more than four LDGSTS); 11 / 12 = the staged forms at 4 blocks.
+  static const int acc_variant = [] {
+    const char* e = getenv("ZK_ACC_VARIANT");
+    return e ? atoi(e) : 1;
+  }();
+  typedef void (*AccKernel)(const Affine*, const uint32_t*, const uint32_t*, uint32_t, const Plan*, XYZZ*, XYZZ*);
+  const AccKernel acc_kernel = acc_variant == 1    ? fixed_accumulate_staged_kernel<1, 5>
+                               : acc_variant == 2  ? fixed_accumulate_staged_kernel<2, 5>
+                               : acc_variant == 11 ? fixed_accumulate_staged_kernel<1, 4>
+                               : acc_variant == 12 ? fixed_accumulate_staged_kernel<2, 4>
+                                                   : fixed_accumulate_kernel;
+  if (!ctx->msm_acc_blocks_per_sm) {  // per context: no state shared between host threads
     int v = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, fixed_accumulate_kernel, ACC_THREADS, 0);
-    acc_blocks_per_sm = v > 0 ? v : ACC_MIN_BLOCKS;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, acc_kernel, ACC_THREADS, 0);
+    ctx->msm_acc_blocks_per_sm = v > 0 ? v : ACC_MIN_BLOCKS;
   }
-  const uint32_t acc_grid = (uint32_t)ctx->sm_count * acc_blocks_per_sm;
+  const uint32_t acc_grid = (uint32_t)ctx->sm_count * (uint32_t)ctx->msm_acc_blocks_per_sm;
   const uint32_t resident = acc_grid * ACC_THREADS;
   // chunk = max(MIN_CHUNK, entries / resident) so there are never more chunks than resident threads
   const uint32_t max_chunks = (uint32_t)std::min<uint64_t>(max_entries / MIN_CHUNK + 1, (uint64_t)resident + 1);
@@ -573,7 +690,7 @@ int32_t msm_fixed_batch(zk_ctx* ctx, const FixedBase& fb, const MsmJob* jobs, in
     fixed_scatter_kernel<<<gt, T, 0, st>>>(dj, tmp, ranks, count, eidx, nwin, stride, fb.npoints, B, offsets, sorted);
     {
       KernelTimer acc_timer(ctx, KC_MSM_ACC);
-      fixed_accumulate_kernel<<<acc_grid, ACC_THREADS, 0, st>>>(fb.table, sorted, offsets, NB, plan, heads, buckets);
+      acc_kernel<<<acc_grid, ACC_THREADS, 0, st>>>(fb.table, sorted, offsets, NB, plan, heads, buckets);
       fixed_fixup_kernel<<<(NB + 127) / 128, 128, 0, st>>>(offsets, NB, plan, heads, buckets, hitems, hb, max_items,
                                                            max_hbuckets);
       fixed_heavy_kernel<<<ctx->sm_count * 2, HEAVY_THREADS, 0, st>>>(heads, hitems, plan, hpart);

@@ -608,11 +608,17 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
     dist_column_block(NUM_WITNESS_POLYS, ctx->dist_rank, world, &blk_lo, &blk_hi, &blk_per);
     const uint64_t spr = blk_per, slot_lo = blk_lo, slot_hi = blk_hi;
     const uint64_t send_slot = spr * (uint64_t)ctx->dist_rank;  // this rank's block of the padded arrays
-    if (slot_hi > slot_lo) {  // one batch of inverse transforms, then one of columns x cosets
+    // Advice columns 10 and 11 are allocated by SpreadTableChip::configure and never queried
+    // (spread_table.rs:435-441, docs/CIRCUIT.md): they are committed, but no gate, evaluation or opening
+    // reads their coefficient or coset form, so slots 10 and 11 are not transformed.
+    const uint64_t sub[2][2] = {{slot_lo, std::min<uint64_t>(slot_hi, NUM_USED_COLUMNS)},
+                                {std::max<uint64_t>(slot_lo, NUM_ADVICE_COLUMNS), slot_hi}};
+    for (auto& sb : sub) {  // per sub-range: one batch of inverse transforms, then one of columns x cosets
+      if (sb[1] <= sb[0]) continue;
       NttOptions o = inv;
-      o.batch = (int)(slot_hi - slot_lo);
+      o.batch = (int)(sb[1] - sb[0]);
       o.in_stride = o.out_stride = n;
-      if ((rc = ntt_run(ctx, W->values_all + slot_lo * n, (uint32_t)n, W->polys_all + slot_lo * n, k, o))) return rc;
+      if ((rc = ntt_run(ctx, W->values_all + sb[0] * n, (uint32_t)n, W->polys_all + sb[0] * n, k, o))) return rc;
       NttOptions c;
       c.batch = NUM_COSETS;
       c.in_stride = 0;
@@ -622,7 +628,7 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
       c.batch2 = o.batch;
       c.in_stride2 = n;
       c.out_stride2 = en;
-      if ((rc = ntt_run(ctx, W->polys_all + slot_lo * n, (uint32_t)n, W->cosets_all + slot_lo * en, k, c))) return rc;
+      if ((rc = ntt_run(ctx, W->polys_all + sb[0] * n, (uint32_t)n, W->cosets_all + sb[0] * en, k, c))) return rc;
     }
     // coefficients: every rank needs every column in full (evaluations, multiopen) -> in-place all-gather.
     // coset values: every rank needs only the rows of its share of the quotient -> row segments exchanged

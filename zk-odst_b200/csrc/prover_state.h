@@ -12,7 +12,9 @@
 
 namespace zkodst {
 
-constexpr int NUM_FIXED = 10;   // 3 table columns + 7 compressed-selector columns
+constexpr int NUM_FIXED = 12;   // 3 table columns, the constants column, 8 compressed-selector columns
+constexpr int FIXED_CONSTANTS = 3;       // fixed column of the pinned constants (IV words)
+constexpr int FIXED_SELECTOR_BASE = 4;   // first column `compress_selectors` allocates
 constexpr int NUM_PERM = 8;     // equality-enabled columns a_1..a_8 (table16.rs:312-314)
 constexpr int NUM_SETS = 4;     // permutation grand products: chunks of degree - 2 = 2 columns
 constexpr int BLINDING = 5;     // ConstraintSystem::blinding_factors() for this circuit
@@ -48,6 +50,7 @@ struct DeviceKeys {
   uint64_t n = 0, en = 0;   // en = NUM_COSETS * n: the quotient is evaluated on three cosets of the n-th roots
   uint32_t rounds = 0;
   uint64_t n_compressions = 0, region_rows = 0;
+  std::vector<uint8_t> chain;  // [n_compressions]: compression j continues compression j - 1 (keygen_chained)
   SelectorExpr selectors[NUM_SELECTORS];
   Fp* fixed_values[NUM_FIXED] = {};
   Fp* fixed_polys[NUM_FIXED] = {};

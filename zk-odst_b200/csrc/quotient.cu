@@ -3,7 +3,7 @@
 // Replaces the `poly::Evaluator` AST walk and `divide_by_vanishing_poly` of halo2_proofs 0.3.0
 // (`vanishing::Argument::construct`, reached from `create_proof`,
 // blake2f-circuit/benches/blake2f.rs:125) for this circuit: one kernel evaluates, per extended
-// row, the 23 custom-gate polynomials of docs/CIRCUIT.md (gate names and order follow
+// row, the 26 custom-gate polynomials of docs/CIRCUIT.md (gate names and order follow
 // compression.rs:605-1056 / compression_gate.rs), the 9 permutation-argument terms and the 5
 // lookup-argument terms, folds them with Horner in y in halo2's order, and multiplies by
 // 1 / (X^n - 1), which is constant on a coset.  halo2 evaluates on all four cosets of its extended
@@ -33,7 +33,7 @@ struct Horner {
 // split, each part fits 4 blocks per SM.
 constexpr int Q_MINB = 4;
 
-// part 1: the 23 gate polynomials.  sum_k y^(22-k) sel_k e_k (what Horner over the gate list yields) is
+// part 1: the 26 gate polynomials.  sum_k y^(25-k) sel_k e_k (what Horner over the gate list yields) is
 // regrouped by expression — gates that share a polynomial (a1/a2, c1/c2, d1/d2) share its evaluation —
 // and every cell and selector is fetched where it is used, which keeps the live set small.  The order
 // of evaluation does not matter: field arithmetic is exact, the value equals fold_gates (gates.cuh).
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(128, Q_MINB) quotient_gates_kernel(const __gri
   auto SEL = [&](int s) {
     return selector_expr(qa.fixed[qa.sel[s].fixed_col][i], qa.sel[s].root, qa.sel[s].len, qa.k.small);
   };
-  const Fp* const YP = qa.ypow;  // YP[k] = y^(22 - k)
+  const Fp* const YP = qa.ypow;  // YP[k] = y^(NUM_GATE_POLYS - 1 - k)
   const Fp* const P = qa.k.pow2;
   const Fp one = Fp::one();
   Fp acc;
@@ -108,8 +108,13 @@ __global__ void __launch_bounds__(128, Q_MINB) quotient_gates_kernel(const __gri
     // s_digest: xor (21), word (22)
     Fp t = (acc32 - (A2[ip] + A2[i] * P[32] + A2[in] * P[64] + a5c * P[96]) -
             (a6c + a7c * P[32] + a8c * P[64] + a3n * P[96]) * P[1]) * YP[21];
-    t = t + (A5[in] - A1[ip] - A1[i] * P[16] - A1[in] * P[32] - A4[in] * P[48]);  // YP[22] = 1
+    t = t + (A5[in] - A1[ip] - A1[i] * P[16] - A1[in] * P[32] - A4[in] * P[48]) * YP[22];
     acc = acc + SEL(SEL_DIGEST) * t;
+  }
+  {  // pinned inputs: pin constant (23); final flag mask (24), bit (25)
+    const Fp a3c = A3[i], a9c = A9[i];
+    acc = acc + SEL(SEL_CONST) * YP[23] * (a3c - qa.fixed[FIXED_CONSTANTS][i]);
+    acc = acc + SEL(SEL_FMASK) * ((a3c - a9c * (P[64] - one)) * YP[24] + a9c * (a9c - one));  // YP[25] = 1
   }
   qa.h[i] = acc;
 }

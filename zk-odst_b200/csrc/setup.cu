@@ -341,7 +341,7 @@ namespace {
 // (selector included) follow docs/CIRCUIT.md; max_degree is the constraint-system degree 4.
 void combine_selectors(const RegionLayout& L, SelectorExpr out[NUM_SELECTORS], int* n_cols,
                        std::vector<std::vector<uint8_t>>& columns) {
-  static const int degree[NUM_SELECTORS] = {4, 2, 3, 2, 4, 2, 3, 2, 2, 2, 3, 2};
+  static const int degree[NUM_SELECTORS] = {4, 2, 3, 2, 4, 2, 3, 2, 2, 2, 3, 2, 2, 3};
   const int max_degree = CS_DEGREE;
   const uint32_t R = L.rows;
   auto active = [&](int s, uint32_t r) { return L.selectors[(size_t)s * R + r] != 0; };
@@ -375,7 +375,7 @@ void combine_selectors(const RegionLayout& L, SelectorExpr out[NUM_SELECTORS], i
     }
     std::vector<uint8_t> vals(R, 0);
     for (size_t c = 0; c < comb.size(); c++) {
-      out[comb[c]] = SelectorExpr{3 + col, (int)c + 1, (int)comb.size()};
+      out[comb[c]] = SelectorExpr{FIXED_SELECTOR_BASE + col, (int)c + 1, (int)comb.size()};
       for (uint32_t r = 0; r < R; r++)
         if (active(comb[c], r)) vals[r] = (uint8_t)(c + 1);
     }
@@ -437,6 +437,26 @@ __global__ void selector_column_kernel(const uint8_t* __restrict__ tmpl, uint32_
   uint64_t comp = i / R;
   uint32_t v = comp < n_comp ? tmpl[i % R] : 0;
   out[i] = Fp::from_u64(v);
+}
+// the constants column: region row r of every compression holds tmpl[r]
+__global__ void constants_column_kernel(const uint64_t* __restrict__ tmpl, uint32_t R, uint64_t n_comp, uint64_t n,
+                                        Fp* __restrict__ out) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t v = i / R < n_comp ? tmpl[i % R] : 0;
+  out[i] = v ? Fp::from_u64(v) : Fp::zero();
+}
+// Chaining copies: the two cells of copy t point at each other (both are in no other copy, so halo2's
+// cycle-merging `copy` leaves exactly this 2-cycle).  cells[4 t ..] = {perm column a, row a, perm column b, row b}.
+__global__ void sigma_chain_kernel(const uint32_t* __restrict__ cells, uint32_t ncopies, uint64_t n,
+                                   const Fp* __restrict__ tw, const Fp* __restrict__ delta_pows,
+                                   Fp* const* __restrict__ sigma) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ncopies) return;
+  const uint32_t ca = cells[4 * t], ra = cells[4 * t + 1], cb = cells[4 * t + 2], rb = cells[4 * t + 3];
+  auto id = [&](uint32_t c, uint64_t r) { return delta_pows[c] * (r < n / 2 ? tw[r] : tw[r - n / 2].neg()); };
+  sigma[ca][ra] = id(cb, rb);
+  sigma[cb][rb] = id(ca, ra);
 }
 // sigma_c[row] = delta^(mapped col) * omega^(mapped row)
 __global__ void sigma_kernel(const uint64_t* __restrict__ tmpl, uint32_t R, uint64_t n_comp, uint64_t n, int col,
@@ -501,7 +521,14 @@ std::string hex32(const uint8_t b[32]) {
 }  // namespace zkodst
 
 extern "C" int32_t zk_blake2f_keygen(zk_ctx* ctx, uint32_t rounds, uint64_t n_compressions) {
+  return zk_blake2f_keygen_chained(ctx, rounds, n_compressions, nullptr);
+}
+
+extern "C" int32_t zk_blake2f_keygen_chained(zk_ctx* ctx, uint32_t rounds, uint64_t n_compressions,
+                                             const uint8_t* chain) {
   if (!ctx) return ZK_E_INVALID;
+  if (chain && n_compressions && chain[0])
+    return set_error(ctx, ZK_E_INVALID, "the first compression cannot continue another");
   ProverState* S = prover_state(ctx);
   if (!S->has_params) return set_error(ctx, ZK_E_STATE, "keygen before params");
   ZK_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -524,6 +551,9 @@ extern "C" int32_t zk_blake2f_keygen(zk_ctx* ctx, uint32_t rounds, uint64_t n_co
   K.rounds = rounds;
   K.n_compressions = n_compressions;
   K.region_rows = L.rows;
+  K.chain.assign(n_compressions, 0);
+  if (chain)
+    for (uint64_t j = 0; j < n_compressions; j++) K.chain[j] = chain[j] ? 1 : 0;
   {
     // c_j = zeta * omega_4n^j (the first three cosets of halo2's extended domain, degree 4 => 4n)
     Fp omega_ext = Fp::root_of_unity();
@@ -563,7 +593,7 @@ extern "C" int32_t zk_blake2f_keygen(zk_ctx* ctx, uint32_t rounds, uint64_t n_co
   int n_sel_cols = 0;
   std::vector<std::vector<uint8_t>> sel_cols;
   combine_selectors(L, K.selectors, &n_sel_cols, sel_cols);
-  if (3 + n_sel_cols != NUM_FIXED) return set_error(ctx, ZK_E_INVALID, "unexpected selector combination");
+  if (FIXED_SELECTOR_BASE + n_sel_cols != NUM_FIXED) return set_error(ctx, ZK_E_INVALID, "unexpected selector combination");
   for (int c = 0; c < NUM_FIXED; c++) {
     ZK_CUDA(ctx, cudaMalloc((void**)&K.fixed_values[c], n * sizeof(Fp)));
     ZK_CUDA(ctx, cudaMalloc((void**)&K.fixed_polys[c], n * sizeof(Fp)));
@@ -585,8 +615,18 @@ extern "C" int32_t zk_blake2f_keygen(zk_ctx* ctx, uint32_t rounds, uint64_t n_co
   for (int c = 0; c < n_sel_cols; c++) {
     ZK_CUDA(ctx, cudaMemcpyAsync(d_tmpl + (size_t)c * L.rows, sel_cols[c].data(), L.rows, cudaMemcpyHostToDevice, st));
     selector_column_kernel<<<blocks, T, 0, st>>>(d_tmpl + (size_t)c * L.rows, L.rows, n_compressions, n,
-                                                 K.fixed_values[3 + c]);
+                                                 K.fixed_values[FIXED_SELECTOR_BASE + c]);
     ctx->launches++;
+  }
+  {  // constants column (fixed column 3): the IV words on the rows SEL_CONST pins
+    uint64_t* d_const = nullptr;
+    DevTemps tmp;
+    tmp.own(&d_const);
+    ZK_CUDA(ctx, cudaMalloc((void**)&d_const, (size_t)L.rows * 8));
+    ZK_CUDA(ctx, cudaMemcpyAsync(d_const, L.constants.data(), (size_t)L.rows * 8, cudaMemcpyHostToDevice, st));
+    constants_column_kernel<<<blocks, T, 0, st>>>(d_const, L.rows, n_compressions, n, K.fixed_values[FIXED_CONSTANTS]);
+    ctx->launches++;
+    ZK_CUDA(ctx, zk_stream_sync(ctx));
   }
   // permutation
   RegionPermutation perm(L.rows);
@@ -603,6 +643,40 @@ extern "C" int32_t zk_blake2f_keygen(zk_ctx* ctx, uint32_t rounds, uint64_t n_co
     sigma_kernel<<<blocks, T, 0, st>>>(d_map, L.rows, n_compressions, n, c, TN->tw_fwd, dp[0], dp[1], dp[2], dp[3],
                                        dp[4], dp[5], dp[6], dp[7], K.sigma_values[c]);
     ctx->launches++;
+  }
+  // record chaining: h_i of a continuing compression and h'_i of its predecessor form a 2-cycle
+  {
+    std::vector<uint32_t> cells;
+    const uint32_t pa = (uint32_t)RegionPermutation::perm_index(CHAIN_OUT_COLUMN),
+                   pb = (uint32_t)RegionPermutation::perm_index(CHAIN_H_COLUMN);
+    for (uint64_t j = 1; j < n_compressions; j++) {
+      if (!K.chain[j]) continue;
+      for (int i = 0; i < 8; i++) {
+        const uint32_t ra = L.out_word_row[i], rb = L.h_word_row[i];
+        // the patch below is halo2's `copy` only if both cells are untouched by the region's own copies
+        if (perm.mapping[perm.at(((uint64_t)pa << 32) | ra)] != (((uint64_t)pa << 32) | ra) ||
+            perm.mapping[perm.at(((uint64_t)pb << 32) | rb)] != (((uint64_t)pb << 32) | rb))
+          return set_error(ctx, ZK_E_INVALID, "chaining cells take part in other copy constraints");
+        cells.insert(cells.end(), {pa, (uint32_t)((j - 1) * L.rows + ra), pb, (uint32_t)(j * L.rows + rb)});
+      }
+    }
+    if (!cells.empty()) {
+      uint32_t* d_cells = nullptr;
+      Fp* d_dp = nullptr;
+      Fp** d_sigma = nullptr;
+      DevTemps tmp;
+      tmp.own(&d_cells); tmp.own(&d_dp); tmp.own(&d_sigma);
+      ZK_CUDA(ctx, cudaMalloc((void**)&d_cells, cells.size() * 4));
+      ZK_CUDA(ctx, cudaMalloc((void**)&d_dp, sizeof dp));
+      ZK_CUDA(ctx, cudaMalloc((void**)&d_sigma, sizeof(Fp*) * NUM_PERM));
+      ZK_CUDA(ctx, cudaMemcpyAsync(d_cells, cells.data(), cells.size() * 4, cudaMemcpyHostToDevice, st));
+      ZK_CUDA(ctx, cudaMemcpyAsync(d_dp, dp, sizeof dp, cudaMemcpyHostToDevice, st));
+      ZK_CUDA(ctx, cudaMemcpyAsync(d_sigma, K.sigma_values, sizeof(Fp*) * NUM_PERM, cudaMemcpyHostToDevice, st));
+      const uint32_t nc = (uint32_t)(cells.size() / 4);
+      sigma_chain_kernel<<<(nc + 127) / 128, 128, 0, st>>>(d_cells, nc, n, TN->tw_fwd, d_dp, d_sigma);
+      ctx->launches++;
+      ZK_CUDA(ctx, zk_stream_sync(ctx));
+    }
   }
   ZK_CUDA(ctx, cudaGetLastError());
   // commitments, coefficient forms, extended cosets
@@ -644,8 +718,15 @@ extern "C" int32_t zk_blake2f_keygen(zk_ctx* ctx, uint32_t rounds, uint64_t n_co
   // through zk_vk_repr_override.
   {
     char head[128];
-    snprintf(head, sizeof head, "zkodst-blake2f-table16-v1;k=%d;rounds=%u;n=%zu;", k, rounds, (size_t)n_compressions);
+    snprintf(head, sizeof head, "zkodst-blake2f-table16-v2;k=%d;rounds=%u;n=%zu;", k, rounds, (size_t)n_compressions);
     std::string s = head;
+    bool chained = false;
+    for (uint8_t c : K.chain) chained |= c != 0;
+    if (chained) {  // which compressions continue their predecessor (one character each)
+      s += "chain=";
+      for (uint8_t c : K.chain) s += c ? '1' : '0';
+      s += ";";
+    }
     uint8_t b[32];
     for (auto& c : K.fixed_commitments) {
       point_to_bytes(c, b);

@@ -139,7 +139,7 @@ int32_t verify_impl(zk_ctx* ctx, const uint8_t* proof, size_t proof_len) {
   for (int s = 0; s < NUM_SELECTORS; s++)
     sel[s] = selector_expr(fixed_e[K.selectors[s].fixed_col], K.selectors[s].root, K.selectors[s].len, kc.small);
   Horner H{Fp::zero(), y};
-  fold_gates(H, v, sel, kc);
+  fold_gates(H, v, sel, kc, fixed_e[FIXED_CONSTANTS]);
   // permutation argument (columns in enable_equality order: a1,a2 | a3,a4 | a5,a6 | a7,a8, all cur)
   H.fold(l_0 * (one - z_e[0]));
   H.fold(l_last * (z_e[NUM_SETS - 1] * z_e[NUM_SETS - 1] - z_e[NUM_SETS - 1]));

@@ -62,6 +62,7 @@ struct zk_ctx {
   std::map<int, zkodst::NttTables> ntt_tables;
   int* d_status = nullptr;  // device-side error flag (bad EIP-152 record seen by a kernel)
   int sm_count = 148;
+  int msm_acc_blocks_per_sm = 0;  // resident blocks of the MSM accumulation kernel (msm_fixed.cu), queried once
   // MSM split across GPUs (dist.cu): NCCL communicator (ncclComm_t), this rank, group size
   void* nccl_comm = nullptr;
   int dist_rank = 0, dist_world = 1;
