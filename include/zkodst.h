@@ -89,6 +89,17 @@ int32_t zk_blake2f_min_k(uint32_t rounds, uint64_t n_compressions, int32_t* k);
 int32_t zk_blake2f_layout_hash(uint32_t rounds, uint64_t* copies_hash, uint64_t* selectors_hash,
                                uint64_t* n_copies);
 
+/* The layout of one region as tables, for a host-language `Circuit::synthesize` over halo2's own `Layouter`
+ * (rust/zkodst-backend/src/halo2_chip.rs): the copy constraints in `copy_advice` call order as quadruples
+ * (left advice column, left row, right advice column, right row; rows relative to the region start; *n_copies:
+ * in = capacity in quadruples, out = count, copies NULL = size query), the selector activations
+ * ([ZK_NUM_SELECTORS][rows] bytes), the constants fixed column ([rows] u64) and the rows of the word cells record
+ * chaining connects (chain_rows[0..8) = h_i in advice column 1, chain_rows[8..16) = h'_i in advice column 0).
+ * Any output pointer may be NULL.  Replaces the row arithmetic of compression/compression_util.rs:32-43,112-205. */
+#define ZK_NUM_SELECTORS 14
+int32_t zk_blake2f_layout_tables(uint32_t rounds, uint32_t* copies, uint64_t* n_copies, uint8_t* selectors,
+                                 uint64_t* constants, uint32_t chain_rows[16]);
+
 /* ---- EIP-152 wire format and the multi-block hashing driver (host-only helpers) ------------------
  * zk_eip152_validate: the precompile's input checks — length must be 213, f must be 0 or 1
  * (ZK_E_INPUT otherwise); writes the big-endian round count.
@@ -197,8 +208,17 @@ int32_t zk_blake2f_keygen(zk_ctx* ctx, uint32_t rounds, uint64_t n_compressions)
 int32_t zk_blake2f_keygen_chained(zk_ctx* ctx, uint32_t rounds, uint64_t n_compressions, const uint8_t* chain);
 /* 12 fixed + 8 permutation commitments (32 B compressed each) followed by vk.transcript_repr. */
 int32_t zk_vk_bytes(zk_ctx* ctx, uint8_t* out, uint64_t* len);
-/* Inject a genuine halo2 `vk.transcript_repr` (32 B canonical LE) in place of the substitute
- * hash (the Rust `{:?}` rendering of vk.pinned() is not reproducible here). */
+/* vk.transcript_repr is derived as halo2_proofs 0.3.0 `VerifyingKey::from_parts` does (reached from `keygen_vk`,
+ * blake2f-circuit/benches/blake2f.rs:102): BLAKE2b-512 ("Halo2-Verify-Key") of the length-prefixed Rust `{:?}`
+ * rendering of `vk.pinned()`, reduced with from_uniform_bytes.  zk_vk_pinned_debug returns that string (not
+ * NUL-terminated; *len: in = capacity, out = length, ZK_E_BUFFER if short) so that it can be compared character by
+ * character with `format!("{:?}", vk.pinned())` of the Rust circuit (rust/xcheck) — the rendering is restated from
+ * the published halo2 sources and has not been run against them in this image. */
+int32_t zk_vk_pinned_debug(zk_ctx* ctx, char* out, uint64_t* len);
+/* Host-only form for commitments computed elsewhere (e.g. by halo2's own keygen_vk): `commitments` = the 12 fixed
+ * then the 8 permutation commitments as 64-byte affine points (Montgomery x, y). */
+int32_t zk_blake2f_pinned_debug(int32_t k, uint32_t rounds, const void* commitments, char* out, uint64_t* len);
+/* Inject a `vk.transcript_repr` obtained from halo2 itself (32 B canonical LE) in place of the derived one. */
 int32_t zk_vk_repr_override(zk_ctx* ctx, const uint8_t repr[32]);
 /* inputs: n_compressions x 213 B (host).  seed: 16-byte XorShiftRng seed (the reference harness
  * seeds its prover RNG the same way, benchmarking/src/blake2f_circuit_bench.rs:41-44).

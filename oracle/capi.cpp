@@ -389,6 +389,23 @@ size_t zko_vk_bytes(void* h, uint8_t* out, size_t cap) {
   vk.transcript_repr.to_repr(out + off);
   return need;
 }
+// vk commitments as raw affine points (Montgomery x, y; 64 bytes each): fixed then permutation; returns the count
+size_t zko_vk_points(void* h, uint64_t* out) {
+  auto* p = (OracleProver*)h;
+  const VerifyingKey& vk = p->pk.vk;
+  size_t i = 0;
+  for (auto& c : vk.fixed_commitments) memcpy(out + 8 * i++, &c, 64);
+  for (auto& c : vk.permutation_commitments) memcpy(out + 8 * i++, &c, 64);
+  return i;
+}
+// the `{:?}` rendering of vk.pinned() that transcript_repr hashes; returns the length, writes if it fits
+size_t zko_vk_pinned_debug(void* h, char* out, size_t cap) {
+  auto* p = (OracleProver*)h;
+  if (!p->has_vk) return 0;
+  const std::string s = vk_pinned_debug(p->pk.vk);
+  if (out && cap >= s.size()) memcpy(out, s.data(), s.size());
+  return s.size();
+}
 int zko_create_proof(void* h, const uint8_t* inputs213, size_t n_compressions, const uint8_t seed[16],
                      uint8_t* proof_out, size_t* proof_len) {
   auto* p = (OracleProver*)h;

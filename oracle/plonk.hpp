@@ -101,30 +101,90 @@ struct ProvingKey {
   std::vector<Poly> perm_values, perm_polys, perm_cosets;  // sigma columns
 };
 
-static const char* CIRCUIT_VERSION = "zkodst-blake2f-table16-v2";
+// ---- vk.pinned() Debug rendering and VerifyingKey::from_parts (plonk.rs, plonk/circuit.rs) ------------------
+// halo2_proofs 0.3.0 hashes `format!("{:?}", vk.pinned())` (length-prefixed, BLAKE2b-512 personalised
+// "Halo2-Verify-Key") into vk.transcript_repr.  Rendered here generically from the constraint system:
+// Expression's Debug prints Constant(c) / Fixed { query_index, column_index, rotation } / Advice { .. } /
+// Negated(e) / Sum(a, b) / Product(a, b) / Scaled(e, c); field elements print as 0x + 64 hex digits
+// big-endian, points as (x, y).  Restated from the published sources; not run against halo2 here
+// (rust/xcheck prints halo2's own string for comparison).  Parity unpinned.
+static inline std::string debug_fp_hex(const u64 raw[4]) {
+  char buf[67];
+  snprintf(buf, sizeof buf, "0x%016llx%016llx%016llx%016llx", (unsigned long long)raw[3],
+           (unsigned long long)raw[2], (unsigned long long)raw[1], (unsigned long long)raw[0]);
+  return buf;
+}
+template <class F>
+static inline std::string debug_field(const F& v) {
+  u64 raw[4];
+  v.to_raw(raw);
+  return debug_fp_hex(raw);
+}
+static inline std::string debug_point(const Affine& p) {
+  if (p.is_identity()) return "Infinity";
+  return "(" + debug_field(p.x) + ", " + debug_field(p.y) + ")";
+}
+static inline std::string debug_expr(const E& e) {
+  auto rot = [](int r) { return "Rotation(" + std::to_string(r) + ")"; };
+  switch (e->kind) {
+    case Expr::Constant: return "Constant(" + debug_field(e->c) + ")";
+    case Expr::Selector: return "Selector(Selector(" + std::to_string(e->index) + ", true))";
+    case Expr::Fixed:
+      return "Fixed { query_index: " + std::to_string(e->index) + ", column_index: " + std::to_string(e->column) +
+             ", rotation: " + rot(e->rotation) + " }";
+    case Expr::Advice:
+      return "Advice { query_index: " + std::to_string(e->index) + ", column_index: " + std::to_string(e->column) +
+             ", rotation: " + rot(e->rotation) + " }";
+    case Expr::Negated: return "Negated(" + debug_expr(e->a) + ")";
+    case Expr::Sum: return "Sum(" + debug_expr(e->a) + ", " + debug_expr(e->b) + ")";
+    case Expr::Product: return "Product(" + debug_expr(e->a) + ", " + debug_expr(e->b) + ")";
+    case Expr::Scaled: return "Scaled(" + debug_expr(e->a) + ", " + debug_field(e->c) + ")";
+  }
+  return "";
+}
+static inline std::string vk_pinned_debug(const VerifyingKey& vk) {
+  const ConstraintSystem& cs = vk.shape.cs;
+  auto list = [](const std::vector<std::string>& v) {
+    std::string s = "[";
+    for (size_t i = 0; i < v.size(); i++) s += (i ? ", " : "") + v[i];
+    return s + "]";
+  };
+  auto column = [](int index, const char* type) {
+    return "Column { index: " + std::to_string(index) + ", column_type: " + type + " }";
+  };
+  auto queries = [&](const std::vector<Query>& qs, const char* type) {
+    std::vector<std::string> v;
+    for (auto& q : qs) v.push_back("(" + column(q.column, type) + ", Rotation(" + std::to_string(q.rotation) + "))");
+    return list(v);
+  };
+  std::vector<std::string> gates, perm, lookups, fixed_cm, perm_cm;
+  for (auto& g : cs.gates)
+    for (auto& p : g.polys) gates.push_back(debug_expr(p));
+  for (int c : cs.permutation_columns) perm.push_back(column(c, "Advice"));
+  for (auto& l : cs.lookups) {
+    std::vector<std::string> in, tab;
+    for (auto& e : l.input_expressions) in.push_back(debug_expr(e));
+    for (auto& e : l.table_expressions) tab.push_back(debug_expr(e));
+    lookups.push_back("Argument { input_expressions: " + list(in) + ", table_expressions: " + list(tab) + " }");
+  }
+  for (auto& c : vk.fixed_commitments) fixed_cm.push_back(debug_point(c));
+  for (auto& c : vk.permutation_commitments) perm_cm.push_back(debug_point(c));
+  const std::string min_degree = cs.minimum_degree < 0 ? "None" : "Some(" + std::to_string(cs.minimum_degree) + ")";
+  return "PinnedVerificationKey { base_modulus: \"" + debug_fp_hex(FqParams::MOD) + "\", scalar_modulus: \"" +
+         debug_fp_hex(FpParams::MOD) + "\", domain: PinnedEvaluationDomain { k: " + std::to_string(vk.domain.k) +
+         ", extended_k: " + std::to_string(vk.domain.extended_k) + ", omega: " + debug_field(vk.domain.omega) +
+         " }, cs: PinnedConstraintSystem { num_fixed_columns: " + std::to_string(cs.num_fixed_columns) +
+         ", num_advice_columns: " + std::to_string(cs.num_advice_columns) +
+         ", num_instance_columns: " + std::to_string(cs.num_instance_columns) +
+         ", num_selectors: " + std::to_string(cs.num_selectors) + ", gates: " + list(gates) +
+         ", advice_queries: " + queries(cs.advice_queries, "Advice") + ", instance_queries: [], fixed_queries: " +
+         queries(cs.fixed_queries, "Fixed") + ", permutation: Argument { columns: " + list(perm) + " }, lookups: " +
+         list(lookups) + ", constants: [], minimum_degree: " + min_degree + " }, fixed_commitments: " + list(fixed_cm) +
+         ", permutation: VerifyingKey { commitments: " + list(perm_cm) + " } }";
+}
 
 static inline Fp vk_transcript_repr(const VerifyingKey& vk) {
-  char head[128];
-  snprintf(head, sizeof head, "%s;k=%d;rounds=%u;n=%zu;", CIRCUIT_VERSION, vk.shape.k,
-           vk.shape.rounds, vk.shape.n_compressions);
-  std::string s = head;
-  bool chained = false;
-  for (uint8_t c : vk.shape.chain) chained |= c != 0;
-  if (chained) {  // which compressions continue their predecessor (one character each)
-    s += "chain=";
-    for (uint8_t c : vk.shape.chain) s += c ? '1' : '0';
-    s += ";";
-  }
-  auto hex = [&](const Affine& p) {
-    uint8_t b[32];
-    p.to_bytes(b);
-    char buf[65];
-    for (int i = 0; i < 32; i++) snprintf(buf + 2 * i, 3, "%02x", b[i]);
-    s += buf;
-    s += ";";
-  };
-  for (auto& c : vk.fixed_commitments) hex(c);
-  for (auto& c : vk.permutation_commitments) hex(c);
+  const std::string s = vk_pinned_debug(vk);
   Blake2b h("Halo2-Verify-Key");
   uint64_t len = s.size();
   h.update(&len, 8);

@@ -6,9 +6,14 @@
 //!                                                      blake2f-circuit/src/blake2f.rs:40-72
 //!   * `Circuit::synthesize`                            blake2f-circuit/src/blake2f.rs:270-277
 //!   * `create_proof` call shape                        blake2f-circuit/benches/blake2f.rs:124-127
-//! and routes the heavy lifting through the C ABI.  `configure` stays pure Rust (it only declares
-//! columns, gates and the lookup exactly as docs/CIRCUIT.md lists them) so that halo2's own
-//! `keygen_vk`, `MockProver` and `verify_proof` keep working on the same circuit.
+//! and routes the heavy lifting through the C ABI.  Two layers:
+//!   * `halo2_chip` — `Table16Chip::configure(meta: &mut ConstraintSystem<pallas::Base>)` in pure Rust (the 12
+//!     advice columns, 3 table columns, the constants column, the selector-less lookup, 14 selectors and 26 gate
+//!     polynomials of docs/CIRCUIT.md in declaration order) and a `Circuit` whose `synthesize` assigns the cells
+//!     `zk_blake2f_witness_batch` computes, so that halo2's own `keygen_vk`, `MockProver` and `verify_proof` run
+//!     on the same circuit (rust/xcheck drives them and compares with the library);
+//!   * `gadget` — the streaming `Blake2fInstructions` / `Blake2f` surface over a recording layouter, the
+//!     counterpart of include/zkodst.hpp.
 //!
 //! NOTE: this crate is shipped as source; the build image has no Rust toolchain, so it has not
 //! been compiled.  INTEGRATION.md walks through the steps a maintainer follows.  The same surface
@@ -16,6 +21,9 @@
 //! (tests/cpp/facade_test.cpp); `gadget` below follows it line for line.
 use std::ffi::CStr;
 use std::ptr;
+
+/// `Table16Chip::configure` over halo2's own `ConstraintSystem` and the batch `Circuit` (see the module docs).
+pub mod halo2_chip;
 
 use zkodst_sys as sys;
 
@@ -85,6 +93,31 @@ impl GpuProver {
     /// `keygen_vk` + `keygen_pk` (benches/blake2f.rs:102-103) for `n` compressions of `rounds`.
     pub fn keygen(&mut self, rounds: u32, n: u64) -> Result<(), Error> {
         self.check(unsafe { sys::zk_blake2f_keygen(self.ctx, rounds, n) })
+    }
+
+    /// The same with record chaining: `chain[j]` makes compression j continue compression j - 1
+    /// (`CompressionConfig::initialize_with_state`, table16/compression.rs:1096-1111).
+    pub fn keygen_chained(&mut self, rounds: u32, chain: &[bool]) -> Result<(), Error> {
+        let flags: Vec<u8> = chain.iter().map(|&c| c as u8).collect();
+        self.check(unsafe { sys::zk_blake2f_keygen_chained(self.ctx, rounds, flags.len() as u64, flags.as_ptr()) })
+    }
+
+    /// The `{:?}` rendering of `vk.pinned()` the library hashed into `vk.transcript_repr`.
+    pub fn vk_pinned_debug(&mut self) -> Result<String, Error> {
+        let mut len = 0u64;
+        unsafe { sys::zk_vk_pinned_debug(self.ctx, ptr::null_mut(), &mut len) };
+        let mut buf = vec![0u8; len as usize];
+        self.check(unsafe { sys::zk_vk_pinned_debug(self.ctx, buf.as_mut_ptr() as *mut _, &mut len) })?;
+        Ok(String::from_utf8_lossy(&buf).into_owned())
+    }
+
+    /// 12 fixed + 8 permutation commitments (32 B compressed each), then `vk.transcript_repr`.
+    pub fn vk_bytes(&mut self) -> Result<Vec<u8>, Error> {
+        let mut len = 0u64;
+        unsafe { sys::zk_vk_bytes(self.ctx, ptr::null_mut(), &mut len) };
+        let mut buf = vec![0u8; len as usize];
+        self.check(unsafe { sys::zk_vk_bytes(self.ctx, buf.as_mut_ptr(), &mut len) })?;
+        Ok(buf)
     }
 
     /// `create_proof(.., rng, &mut transcript); transcript.finalize()` (benches/blake2f.rs:124-127).

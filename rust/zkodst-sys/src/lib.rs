@@ -17,6 +17,8 @@ pub const ZK_E_STATE: i32 = -6;
 pub const ZK_E_VERIFY: i32 = -7;
 pub const ZK_E_BUFFER: i32 = -8;
 pub const ZK_BLAKE2F_INPUT_BYTES: usize = 213;
+pub const ZK_NUM_SELECTORS: usize = 14;
+pub const ZK_NUM_ADVICE: usize = 12;
 
 extern "C" {
     pub fn zk_ctx_create(device_id: i32, out: *mut *mut zk_ctx) -> i32;
@@ -28,6 +30,8 @@ extern "C" {
     pub fn zk_ctx_launch_count(ctx: *const zk_ctx) -> u64;
     pub fn zk_blake2f_rows_per_compression(rounds: u32, rows: *mut u64) -> i32;
     pub fn zk_blake2f_min_k(rounds: u32, n_compressions: u64, k: *mut i32) -> i32;
+    pub fn zk_blake2f_layout_tables(rounds: u32, copies: *mut u32, n_copies: *mut u64, selectors: *mut u8,
+        constants: *mut u64, chain_rows: *mut u32) -> i32;
     pub fn zk_blake2f_witness_batch(ctx: *mut zk_ctx, k: i32, rounds: u32, inputs: *const u8,
         n_compressions: u64, advice_out: *mut c_void, digests_out: *mut u64) -> i32;
     pub fn zk_msm_vesta(ctx: *mut zk_ctx, scalars: *const c_void, bases: *const c_void, n: u64,
@@ -45,6 +49,8 @@ extern "C" {
     pub fn zk_blake2f_keygen(ctx: *mut zk_ctx, rounds: u32, n_compressions: u64) -> i32;
     pub fn zk_blake2f_keygen_chained(ctx: *mut zk_ctx, rounds: u32, n_compressions: u64, chain: *const u8) -> i32;
     pub fn zk_vk_bytes(ctx: *mut zk_ctx, out: *mut u8, len: *mut u64) -> i32;
+    pub fn zk_vk_pinned_debug(ctx: *mut zk_ctx, out: *mut c_char, len: *mut u64) -> i32;
+    pub fn zk_blake2f_pinned_debug(k: i32, rounds: u32, commitments: *const c_void, out: *mut c_char, len: *mut u64) -> i32;
     pub fn zk_vk_repr_override(ctx: *mut zk_ctx, repr: *const u8) -> i32;
     pub fn zk_create_proof(ctx: *mut zk_ctx, inputs: *const u8, n_compressions: u64,
         seed: *const u8, proof_out: *mut u8, proof_len: *mut u64) -> i32;

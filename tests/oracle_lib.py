@@ -152,6 +152,10 @@ def _setup_prover_api(lib):
     lib.zko_params_points.argtypes = [vp, c.c_int, vp]
     lib.zko_keygen.argtypes = [vp, u32, sz]
     lib.zko_keygen_vk.argtypes = [vp, u32, sz]
+    lib.zko_vk_points.restype = sz
+    lib.zko_vk_points.argtypes = [vp, vp]
+    lib.zko_vk_pinned_debug.restype = sz
+    lib.zko_vk_pinned_debug.argtypes = [vp, c.c_char_p, sz]
     lib.zko_keygen_chained.argtypes = [vp, u32, sz, c.c_char_p, c.c_int]
     lib.zko_vk_bytes.restype = sz
     lib.zko_vk_bytes.argtypes = [vp, vp, sz]
@@ -207,6 +211,19 @@ class OracleProver:
         """keygen_vk only (commitments + transcript_repr): enough for vk_bytes() and verify()."""
         rc = self.o.lib.zko_keygen_vk(self.h, rounds, n_compressions)
         assert rc == 0, rc
+
+    def vk_points(self):
+        """The fixed then the permutation commitments as (count, 8) u64: affine Montgomery x, y."""
+        out = np.zeros((64, 8), dtype=np.uint64)
+        cnt = self.o.lib.zko_vk_points(self.h, out.ctypes.data)
+        return np.ascontiguousarray(out[:cnt])
+
+    def vk_pinned_debug(self):
+        """The Rust `{:?}` rendering of vk.pinned() as the oracle derives it from its constraint system."""
+        need = self.o.lib.zko_vk_pinned_debug(self.h, None, 0)
+        buf = ctypes.create_string_buffer(need)
+        self.o.lib.zko_vk_pinned_debug(self.h, buf, need)
+        return buf.raw[:need].decode()
 
     def vk_bytes(self):
         need = self.o.lib.zko_vk_bytes(self.h, None, 0)

@@ -12,6 +12,8 @@ from .binding import (  # noqa: F401
     rows_per_compression,
     min_k,
     layout_hash,
+    pinned_debug,
+    layout_tables,
     dist_unique_id,
     eip152_validate,
     blake2f_compress,

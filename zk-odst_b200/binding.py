@@ -47,6 +47,7 @@ def load_library():
             "zk_blake2f_rows_per_compression": (i32, [u32, c.POINTER(u64)]),
             "zk_blake2f_min_k": (i32, [u32, u64, c.POINTER(i32)]),
             "zk_blake2f_layout_hash": (i32, [u32, c.POINTER(u64), c.POINTER(u64), c.POINTER(u64)]),
+            "zk_blake2f_layout_tables": (i32, [u32, vp, c.POINTER(u64), vp, vp, vp]),
             "zk_params_generate_substitute": (i32, [vp, i32, c.c_char_p]),
             "zk_params_load": (i32, [vp, vp, u64]),
             "zk_params_write": (i32, [vp, vp, c.POINTER(u64)]),
@@ -54,6 +55,8 @@ def load_library():
             "zk_blake2f_keygen_chained": (i32, [vp, u32, u64, c.c_char_p]),
             "zk_vk_bytes": (i32, [vp, vp, c.POINTER(u64)]),
             "zk_vk_repr_override": (i32, [vp, c.c_char_p]),
+            "zk_vk_pinned_debug": (i32, [vp, vp, c.POINTER(u64)]),
+            "zk_blake2f_pinned_debug": (i32, [i32, u32, vp, vp, c.POINTER(u64)]),
             "zk_create_proof": (i32, [vp, vp, u64, c.c_char_p, vp, c.POINTER(u64)]),
             "zk_create_proof_device_inputs": (i32, [vp, vp, u64, c.c_char_p, vp, c.POINTER(u64)]),
             "zk_msm_vesta": (i32, [vp, vp, vp, u64, i32, vp]),
@@ -156,6 +159,19 @@ def dist_quotient_rows(n, rank, world):
     return (lo.value, hi.value), [(segs[2 * i], segs[2 * i + 1]) for i in range(cnt.value)]
 
 
+def pinned_debug(k, rounds, commitments):
+    """Host-only: the `{:?}` rendering of vk.pinned() for 20 commitments (12 fixed, 8 permutation) given as an
+    array of 64-byte affine Montgomery points."""
+    lib = load_library()
+    ln = ctypes.c_uint64(0)
+    lib.zk_blake2f_pinned_debug(k, rounds, _ptr(commitments), None, ctypes.byref(ln))
+    buf = ctypes.create_string_buffer(ln.value)
+    rc = lib.zk_blake2f_pinned_debug(k, rounds, _ptr(commitments), ctypes.cast(buf, ctypes.c_void_p), ctypes.byref(ln))
+    if rc:
+        raise ZkError(rc)
+    return buf.raw[:ln.value].decode()
+
+
 def rows_per_compression(rounds):
     out = ctypes.c_uint64()
     rc = load_library().zk_blake2f_rows_per_compression(rounds, ctypes.byref(out))
@@ -178,6 +194,26 @@ def layout_hash(rounds):
     if rc:
         raise ZkError(rc)
     return a.value, b.value, n.value
+
+
+def layout_tables(rounds):
+    """(copies (n, 4) u32, selectors (14, R) u8, constants (R,) u64, chain_rows (16,) u32) of one region."""
+    import numpy as np
+    lib = load_library()
+    n = ctypes.c_uint64(0)
+    rc = lib.zk_blake2f_layout_tables(rounds, None, ctypes.byref(n), None, None, None)
+    if rc:
+        raise ZkError(rc)
+    R = rows_per_compression(rounds)
+    copies = np.zeros((n.value, 4), dtype=np.uint32)
+    sel = np.zeros((14, R), dtype=np.uint8)
+    const = np.zeros(R, dtype=np.uint64)
+    chain = np.zeros(16, dtype=np.uint32)
+    rc = lib.zk_blake2f_layout_tables(rounds, copies.ctypes.data, ctypes.byref(n), sel.ctypes.data, const.ctypes.data,
+                                      chain.ctypes.data)
+    if rc:
+        raise ZkError(rc)
+    return copies, sel, const, chain
 
 
 def _ptr(x):
@@ -294,6 +330,14 @@ class Context:
         buf = ctypes.create_string_buffer(ln.value)
         self._check(self.lib.zk_vk_bytes(self.h, ctypes.cast(buf, ctypes.c_void_p), ctypes.byref(ln)))
         return buf.raw[:ln.value]
+
+    def vk_pinned_debug(self):
+        """The Rust `{:?}` rendering of vk.pinned() that transcript_repr hashes."""
+        ln = ctypes.c_uint64(0)
+        self.lib.zk_vk_pinned_debug(self.h, None, ctypes.byref(ln))
+        buf = ctypes.create_string_buffer(ln.value)
+        self._check(self.lib.zk_vk_pinned_debug(self.h, ctypes.cast(buf, ctypes.c_void_p), ctypes.byref(ln)))
+        return buf.raw[:ln.value].decode()
 
     def create_proof(self, inputs, n_compressions, seed, on_device=False):
         keep = bytes(inputs) if isinstance(inputs, (bytes, bytearray)) else inputs

@@ -247,6 +247,34 @@ int32_t zk_blake2f_layout_hash(uint32_t rounds, uint64_t* copies_hash, uint64_t*
   return ZK_OK;
 }
 
+// The region's layout tables themselves, for a host-language `Circuit::synthesize` that must issue the same
+// `constrain_equal` / `Selector::enable` / `assign_fixed` calls as the library's keygen assumes.
+int32_t zk_blake2f_layout_tables(uint32_t rounds, uint32_t* copies, uint64_t* n_copies, uint8_t* selectors,
+                                 uint64_t* constants, uint32_t* chain_rows) {
+  if (!n_copies) return ZK_E_INVALID;
+  RegionLayout L;
+  try {
+    build_region_layout(rounds, L);
+  } catch (std::exception&) {
+    return ZK_E_INVALID;
+  }
+  const uint64_t cap = *n_copies;
+  *n_copies = L.copies.size();
+  if (copies) {
+    if (cap < L.copies.size()) return ZK_E_BUFFER;
+    for (size_t i = 0; i < L.copies.size(); i++) {
+      const CopyConstraint& c = L.copies[i];
+      copies[4 * i] = c.left_col, copies[4 * i + 1] = c.left_row, copies[4 * i + 2] = c.right_col,
+                 copies[4 * i + 3] = c.right_row;
+    }
+  }
+  if (selectors) memcpy(selectors, L.selectors.data(), L.selectors.size());
+  if (constants) memcpy(constants, L.constants.data(), L.constants.size() * 8);
+  if (chain_rows)
+    for (int i = 0; i < 8; i++) chain_rows[i] = L.h_word_row[i], chain_rows[8 + i] = L.out_word_row[i];
+  return ZK_OK;
+}
+
 int32_t zk_blake2f_witness_batch_device(zk_ctx* ctx, int32_t k, uint32_t rounds,
                                         const uint8_t* d_inputs, uint64_t n_compressions,
                                         void* d_advice, uint64_t* d_digests) {

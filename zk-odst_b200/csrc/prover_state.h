@@ -4,6 +4,7 @@
 // (blake2f-circuit/benches/blake2f.rs:83-97); `DeviceKeys` replaces `ProvingKey`/`VerifyingKey`
 // from `keygen_vk` / `keygen_pk` (benches/blake2f.rs:102-103) for the BLAKE2f Table16 circuit.
 #pragma once
+#include <string>
 #include <vector>
 
 #include "ec.cuh"
@@ -61,6 +62,7 @@ struct DeviceKeys {
   Fp *l0 = nullptr, *l_last = nullptr, *l_active = nullptr;  // extended cosets
   std::vector<Affine> fixed_commitments, sigma_commitments;
   Fp transcript_repr;
+  std::string pinned_debug;  // the `{:?}` rendering of vk.pinned() transcript_repr hashes (vk_repr.cpp)
   // Quotient domain: h has degree < 3n, so three cosets c_j <omega_n> (c_j = zeta omega_4n^j, j = 0..2:
   // three of the four cosets halo2's extended domain consists of) determine it; stored coset-major.
   Fp coset_gen[NUM_COSETS];     // c_j
@@ -76,6 +78,11 @@ struct ProverState {
   DeviceParams params;
   DeviceKeys keys;
 };
+
+// vk_repr.cpp: the Debug string of halo2's vk.pinned() for this circuit, and VerifyingKey::from_parts' hash of it
+std::string vk_pinned_debug(int k, const SelectorExpr sel[NUM_SELECTORS], const std::vector<Affine>& fixed_commitments,
+                            const std::vector<Affine>& sigma_commitments);
+Fp vk_transcript_repr(const std::string& pinned);
 
 ProverState* prover_state(zk_ctx* ctx);
 void free_keys(DeviceKeys& k);

@@ -713,39 +713,10 @@ extern "C" int32_t zk_blake2f_keygen_chained(zk_ctx* ctx, uint32_t rounds, uint6
   ZK_CUDA(ctx, zk_stream_sync(ctx));
   cudaFree(d_tmpl);
   cudaFree(d_map);
-  // vk.transcript_repr: substitute for the Rust `{:?}` rendering of vk.pinned():
-  // BLAKE2b("Halo2-Verify-Key", len || circuit-version string || commitments), replaceable
-  // through zk_vk_repr_override.
-  {
-    char head[128];
-    snprintf(head, sizeof head, "zkodst-blake2f-table16-v2;k=%d;rounds=%u;n=%zu;", k, rounds, (size_t)n_compressions);
-    std::string s = head;
-    bool chained = false;
-    for (uint8_t c : K.chain) chained |= c != 0;
-    if (chained) {  // which compressions continue their predecessor (one character each)
-      s += "chain=";
-      for (uint8_t c : K.chain) s += c ? '1' : '0';
-      s += ";";
-    }
-    uint8_t b[32];
-    for (auto& c : K.fixed_commitments) {
-      point_to_bytes(c, b);
-      s += hex32(b) + ";";
-    }
-    for (auto& c : K.sigma_commitments) {
-      point_to_bytes(c, b);
-      s += hex32(b) + ";";
-    }
-    Blake2bState h("Halo2-Verify-Key");
-    uint64_t len = s.size();
-    h.update(&len, 8);
-    h.update(s.data(), s.size());
-    uint8_t out[64];
-    h.finalize(out);
-    uint64_t w[8];
-    memcpy(w, out, 64);
-    K.transcript_repr = Fp::from_u512(w);
-  }
+  // vk.transcript_repr as VerifyingKey::from_parts derives it: hash of the `{:?}` rendering of vk.pinned()
+  // (vk_repr.cpp); a value obtained from halo2 itself can still be injected with zk_vk_repr_override
+  K.pinned_debug = vk_pinned_debug(k, K.selectors, K.fixed_commitments, K.sigma_commitments);
+  K.transcript_repr = vk_transcript_repr(K.pinned_debug);
   S->has_keys = true;
   return ZK_OK;
 }
@@ -771,6 +742,49 @@ extern "C" int32_t zk_vk_bytes(zk_ctx* ctx, uint8_t* out, uint64_t* len) {
     off += 32;
   }
   fe_to_repr(S->keys.transcript_repr, out + off);
+  return ZK_OK;
+}
+
+// Host-only: the same rendering for given commitments (12 fixed then 8 permutation commitments, 64-byte affine
+// Montgomery x, y each), without a device — what a Rust caller with its own keygen_vk output would compare.
+extern "C" int32_t zk_blake2f_pinned_debug(int32_t k, uint32_t rounds, const void* commitments, char* out,
+                                           uint64_t* len) {
+  if (!commitments || !len || k < 17 || k > 28) return ZK_E_INVALID;
+  RegionLayout L;
+  try {
+    build_region_layout(rounds, L);
+  } catch (std::exception&) {
+    return ZK_E_INVALID;
+  }
+  SelectorExpr sel[NUM_SELECTORS];
+  int n_sel_cols = 0;
+  std::vector<std::vector<uint8_t>> sel_cols;
+  combine_selectors(L, sel, &n_sel_cols, sel_cols);
+  if (FIXED_SELECTOR_BASE + n_sel_cols != NUM_FIXED) return ZK_E_INVALID;
+  const Affine* pts = (const Affine*)commitments;
+  const std::vector<Affine> fixed(pts, pts + NUM_FIXED), sigma(pts + NUM_FIXED, pts + NUM_FIXED + NUM_PERM);
+  const std::string d = vk_pinned_debug(k, sel, fixed, sigma);
+  if (!out || *len < d.size()) {
+    *len = d.size();
+    return ZK_E_BUFFER;
+  }
+  memcpy(out, d.data(), d.size());
+  *len = d.size();
+  return ZK_OK;
+}
+
+// the Rust `{:?}` rendering of vk.pinned() the transcript_repr was hashed from (not NUL-terminated)
+extern "C" int32_t zk_vk_pinned_debug(zk_ctx* ctx, char* out, uint64_t* len) {
+  if (!ctx || !len) return ZK_E_INVALID;
+  ProverState* S = prover_state(ctx);
+  if (!S->has_keys) return set_error(ctx, ZK_E_STATE, "no keys");
+  const std::string& d = S->keys.pinned_debug;
+  if (!out || *len < d.size()) {
+    *len = d.size();
+    return ZK_E_BUFFER;
+  }
+  memcpy(out, d.data(), d.size());
+  *len = d.size();
   return ZK_OK;
 }
 
