@@ -45,9 +45,14 @@ constexpr int MIN_CHUNK = 16;
 constexpr int SERIAL_HEADS = 8;     // buckets spilling into more chunks than this take the heavy path
 constexpr int PIECE = 2048;         // heads per heavy work item
 constexpr int HEAVY_THREADS = 256;
-constexpr int SEG = 8;
 constexpr int TREE_THREADS = 128;
-constexpr int TREE_PER_THREAD = 8;
+// Bucket reduction shape (ZK_REDUCE_VARIANT): buckets per level-1 segment (serial running sums, 2 SEG additions
+// deep) and segment sums per thread of the tree kernel.  Measured at k = 19, MSM ms per proof on one stream
+// (profiles/r02_reduce_variants.json): {8, 8} 36.09, {4, 4} 35.51, {4, 8} 35.49 (default), {8, 4} 35.76.
+struct ReduceShape {
+  int seg, per_thread;
+};
+constexpr ReduceShape REDUCE_SHAPES[4] = {{8, 8}, {4, 4}, {4, 8}, {8, 4}};
 
 struct HeavyItem {
   uint32_t start, len;
@@ -142,6 +147,9 @@ __global__ void fixed_digits_kernel(DevJobs jobs, uint64_t count, uint64_t lo, c
       }
     }
     my_tmp[(size_t)w * stride] = e;
+    // (measured and dropped, profiles/r02_msm_helper_variants.json: plain atomicAdd for jobs whose digits are
+    // uniform — the match / shuffle round looks like pure latency in ncu, short_scoreboard 12.5 — is 0.5 ms per
+    // proof SLOWER: an atomic that returns its old value pays an L2 round trip per lane either way)
     const uint32_t rank = aggregated_add(my_counts, (e & 0x7fffffffu) - 1, e != 0);
     if (e) my_rank[(size_t)w * stride] = rank;
   }
@@ -239,6 +247,8 @@ __global__ void fixed_scatter_kernel(DevJobs jobs, const uint32_t* __restrict__ 
   const uint32_t* my_tmp = entries_tmp + (size_t)job * nwin * stride + t;
   const uint32_t* my_rank = ranks_tmp + (size_t)job * nwin * stride + t;
   const uint32_t* my_offsets = offsets + (size_t)job * B;
+  // (measured and dropped: four windows in flight per thread — loads, offset gathers, stores grouped — 0.1 ms
+  // per proof slower; the kernel is bound by the 32-byte sector each scattered 4-byte store dirties)
   for (int w = 0; w < nwin; w++) {
     const uint32_t e = my_tmp[(size_t)w * stride];
     if (e)
@@ -472,6 +482,7 @@ __global__ void fixed_heavy_finalize_kernel(const HeavyBucket* __restrict__ hbuc
 
 // ---- reduction: W = sum_{b=1..B} b * bucket[b-1], per job (blockIdx.z / .y selects the job) -----------
 // level 1: per segment s of SEG buckets:  S_s = sum B,  A_s = sum (b_local + 1) B
+template <int SEG>
 __global__ void __launch_bounds__(128)
 fixed_reduce_level1_kernel(const XYZZ* __restrict__ buckets, uint32_t nsegs_total, XYZZ* __restrict__ outA,
                            XYZZ* __restrict__ outS) {
@@ -489,6 +500,7 @@ fixed_reduce_level1_kernel(const XYZZ* __restrict__ buckets, uint32_t nsegs_tota
 }
 // W = sum_s A_s + SEG * sum_s s * S_s,  and  sum_s s * S_s = sum_j 2^j * (sum_{s: bit j} S_s).
 // Tree kernel: blockIdx.y = 0 sums all A_s; blockIdx.y = 1 + j sums the S_s with bit j of s set.
+template <int TREE_PER_THREAD>
 __global__ void __launch_bounds__(TREE_THREADS)
 fixed_reduce_tree_kernel(const XYZZ* __restrict__ A, const XYZZ* __restrict__ S, uint32_t nsegs,
                          XYZZ* __restrict__ partials, uint32_t blocks_x, uint32_t nout) {
@@ -510,15 +522,20 @@ fixed_reduce_tree_kernel(const XYZZ* __restrict__ A, const XYZZ* __restrict__ S,
   }
   if (threadIdx.x == 0) partials[((size_t)job * nout + which) * blocks_x + blockIdx.x] = sh[0];
 }
-// second stage: one block per (output, job) sums its blocks_x partials
+// second stage: one warp per (output, job) sums its blocks_x partials (strided, then a 5-level tree)
 __global__ void __launch_bounds__(32)
 fixed_reduce_final_kernel(const XYZZ* __restrict__ partials, uint32_t blocks_x, XYZZ* __restrict__ out) {
+  __shared__ XYZZ sh[32];
   const size_t o = blockIdx.x;
-  if (threadIdx.x == 0) {
-    XYZZ acc = partials[o * blocks_x];
-    for (uint32_t k = 1; k < blocks_x; k++) acc = acc.add(partials[o * blocks_x + k]);
-    out[o] = acc;
+  XYZZ acc = XYZZ::identity();
+  for (uint32_t k = threadIdx.x; k < blocks_x; k += 32) acc = acc.add(partials[o * blocks_x + k]);
+  sh[threadIdx.x] = acc;
+  __syncwarp();
+  for (int stride = 16; stride > 0; stride >>= 1) {
+    if ((int)threadIdx.x < stride && threadIdx.x + stride < blocks_x) sh[threadIdx.x] = sh[threadIdx.x].add(sh[threadIdx.x + stride]);
+    __syncwarp();
   }
+  if (threadIdx.x == 0) out[o] = sh[0];
 }
 
 int window_bits_override() {
@@ -617,6 +634,12 @@ int32_t msm_fixed_batch(zk_ctx* ctx, const FixedBase& fb, const MsmJob* jobs, in
   const uint32_t max_chunks = (uint32_t)std::min<uint64_t>(max_entries / MIN_CHUNK + 1, (uint64_t)resident + 1);
   const uint32_t max_hbuckets = max_chunks / (SERIAL_HEADS + 1) + 16;
   const uint32_t max_items = max_chunks / PIECE + max_hbuckets + 16;
+  static const int reduce_variant = [] {
+    const char* e = getenv("ZK_REDUCE_VARIANT");
+    const int v = e ? atoi(e) : 2;   // 4-bucket segments, 8 segment sums per tree thread
+    return v >= 0 && v < 4 ? v : 2;
+  }();
+  const int SEG = REDUCE_SHAPES[reduce_variant].seg, TREE_PER_THREAD = REDUCE_SHAPES[reduce_variant].per_thread;
   const uint32_t nsegs = B / SEG;
   int nbits = 0;
   while ((1u << nbits) < nsegs) nbits++;
@@ -697,9 +720,11 @@ int32_t msm_fixed_batch(zk_ctx* ctx, const FixedBase& fb, const MsmJob* jobs, in
       fixed_heavy_finalize_kernel<<<(max_hbuckets + 63) / 64, 64, 0, st>>>(hb, plan, hpart, buckets);
     }
     const uint32_t nsegs_total = (uint32_t)nb * nsegs;
-    fixed_reduce_level1_kernel<<<(nsegs_total + 127) / 128, 128, 0, st>>>(buckets, nsegs_total, A, S);
-    fixed_reduce_tree_kernel<<<dim3(blocks_x, nout, (unsigned)nb), TREE_THREADS, 0, st>>>(A, S, nsegs, part, blocks_x,
-                                                                                         nout);
+    if (SEG == 8) fixed_reduce_level1_kernel<8><<<(nsegs_total + 127) / 128, 128, 0, st>>>(buckets, nsegs_total, A, S);
+    else fixed_reduce_level1_kernel<4><<<(nsegs_total + 127) / 128, 128, 0, st>>>(buckets, nsegs_total, A, S);
+    const dim3 tree_grid(blocks_x, nout, (unsigned)nb);
+    if (TREE_PER_THREAD == 8) fixed_reduce_tree_kernel<8><<<tree_grid, TREE_THREADS, 0, st>>>(A, S, nsegs, part, blocks_x, nout);
+    else fixed_reduce_tree_kernel<4><<<tree_grid, TREE_THREADS, 0, st>>>(A, S, nsegs, part, blocks_x, nout);
     fixed_reduce_final_kernel<<<(unsigned)nb * nout, 32, 0, st>>>(part, blocks_x, out);
     ctx->launches += 12;
   }

@@ -95,7 +95,9 @@ __device__ __forceinline__ void ntt_round(Fp* __restrict__ sm, const NttPassArgs
 #pragma unroll
         for (int mh = 0; mh < (1 << (Q - q - 1)); mh++) {
           const int i0 = (mh << (q + 1)) | mlow, i1 = i0 | (1 << q);
-          const Fp y = (q == 0 && unit_twiddle) ? x[i1] : x[i1] * w;
+          // omega^0: stage 0 of the transform, and the mlow = 0 butterflies of stage 1 in the same first round
+          // (r = 0, s0 = 0, no column offset: j = mlow)
+          const Fp y = (unit_twiddle && (q == 0 || (q == 1 && mlow == 0 && logW == 0))) ? x[i1] : x[i1] * w;
           x[i1] = x[i0] - y;
           x[i0] = x[i0] + y;
         }

@@ -11,6 +11,8 @@
 //
 // Roofline: ~60 coset values read per row (32 B each, rotations hit L2) and ~200 Fp
 // multiplications per row: integer-pipe bound; both fractions are reported by bench.py.
+#include <cstdlib>
+
 #include "polyops.cuh"
 #include "prover_state.h"
 #include "quotient.h"
@@ -118,7 +120,6 @@ __global__ void __launch_bounds__(128, Q_MINB) quotient_gates_kernel(const __gri
   }
   qa.h[i] = acc;
 }
-
 // part 2: the permutation argument (columns in enable_equality order: a1,a2 | a3,a4 | a5,a6 | a7,a8)
 __global__ void __launch_bounds__(128, Q_MINB) quotient_perm_kernel(const __grid_constant__ QuotientArgs qa, uint64_t n, uint64_t mask, uint64_t lo, uint64_t hi) {
   const uint64_t i = lo + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -185,6 +186,9 @@ int32_t quotient_run(zk_ctx* ctx, const QuotientArgs& args, uint64_t n, uint64_t
   if (lo == hi) return ZK_OK;
   KernelTimer timer(ctx, KC_QUOTIENT);
   const unsigned grid = (unsigned)((hi - lo + 127) / 128);
+  // (measured and dropped, profiles/r02_quotient_variants.json: the gate kernel at 3 blocks per SM / 168 registers,
+  // 4.68 ms per proof, and with the pinned-input terms in a launch of their own, 4.64 ms, against 4.75 ms as is —
+  // within run-to-run noise, and the extra launch lengthens the proof)
   quotient_gates_kernel<<<grid, 128, 0, ctx->stream>>>(args, n, n - 1, lo, hi);
   quotient_perm_kernel<<<grid, 128, 0, ctx->stream>>>(args, n, n - 1, lo, hi);
   quotient_lookup_kernel<<<grid, 128, 0, ctx->stream>>>(args, n, n - 1, lo, hi);
