@@ -300,13 +300,22 @@ def split_section(args, zk, torch, dist, rank, world, local_rank, barrier, max_o
         "compressions_per_sec": n / (ms_split * 1e-3),
         "ranks_agree": agree, "equals_single_gpu": single_same, "setup_s": setup_s, "steps": steps,
         "rank0_class_ms": classes,
-        # what rank 0's timed kernel classes do not cover: grand-product scans, batch inversions, lookup
-        # permutation, evaluations, multiopen, host transcript round trips and the NCCL exchanges
+        # what rank 0's timed kernel classes do not cover: the lookup permutation and the random polynomials
+        # (replicated), rank 0's share of the grand products, evaluations and multiopen (sharded by range), the
+        # replicated vector updates of the folding rounds, host transcript round trips and the NCCL exchanges
         "replicated_ms": ms_split - sharded,
-        "allgather_bytes": {"coefficient_columns_received_per_rank": per_rank_slots * world * nrows * 32,
-                            "coset_row_segments_received_per_rank": int(19 * (3 * nrows // world + 21) * 32 * (world - 1) / world),
-                            "h_rows_received_per_rank": 3 * nrows * 32,
-                            "partial_points_per_msm_batch": 128 * 16 * world},
+        # bytes a rank receives per proof over NCCL (rank 0's figures; 17 of the 19 column slots are transformed)
+        "allgather_bytes": {
+            # its own coefficient range of the columns other ranks transformed (grouped send/recv)
+            "coefficient_ranges_received_per_rank": (17 - min(per_rank_slots, 10)) * (nrows // world) * 32,
+            # its quotient rows (+ rotation halo) of the coset columns other ranks transformed (grouped send/recv)
+            "coset_row_segments_received_per_rank": int(17 * (3 * nrows // world + 21) * 32 * (world - 1) / world),
+            # rows of the quotient cosets it inverse-transforms, then its coefficient range of the others
+            "h_rows_and_ranges_received_per_rank": int(-(-3 // world) * nrows * 32 * (world - 1) / world) +
+                                                   (3 - -(-3 // world)) * (nrows // world) * 32,
+            # all-gathers: grand-product rows (5 columns), p' before the folding rounds, folded generators
+            "allgathered_rows_per_rank": 6 * nrows * 32 + (nrows // 32) * 128 * world,
+            "partial_points_per_msm_batch": 128 * 16 * world},
     }
     return parity, strong
 

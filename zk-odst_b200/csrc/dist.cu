@@ -178,6 +178,74 @@ int32_t dist_exchange_quotient_rows(zk_ctx* ctx, char* slots, size_t elem_bytes,
   return ZK_OK;
 }
 
+// Column-sharded slot arrays -> range-sharded: `slots` holds nslots arrays of n elements; the rank that owns slot s
+// (dist_column_block) holds it in full and sends every peer that peer's range [q n / world, (q + 1) n / world) of it;
+// every rank receives its own range of the peers' slots in place.  1 / world of an all-gather's traffic: what the
+// evaluations and the multiopen argument read (they work by coefficient range).  Slots [skip_lo, skip_hi) are not sent.
+int32_t dist_exchange_ranges(zk_ctx* ctx, char* slots, size_t elem_bytes, uint64_t n, uint32_t nslots, uint32_t skip_lo,
+                             uint32_t skip_hi) {
+  const int world = ctx->dist_world, me = ctx->dist_rank;
+  if (world <= 1) return ZK_OK;
+  if (!ctx->nccl_comm) return set_error(ctx, ZK_E_STATE, "the context left its group after an error");
+  const uint64_t cnt = n / (uint64_t)world;
+  ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+  ncclResult_t r = nccl().GroupStart();
+  if (r != ncclSuccess) return nccl_error(ctx, r, "ncclGroupStart");
+  for (int q = 0; q < world && r == ncclSuccess; q++) {
+    if (q == me) continue;
+    uint32_t lo, hi, per;
+    dist_column_block(nslots, me, world, &lo, &hi, &per);
+    for (uint32_t s = lo; s < hi && r == ncclSuccess; s++)
+      if (s < skip_lo || s >= skip_hi)
+        r = nccl().Send(slots + ((size_t)s * n + (size_t)q * cnt) * elem_bytes, cnt * elem_bytes, ncclUint8, q, comm,
+                        ctx->stream);
+    dist_column_block(nslots, q, world, &lo, &hi, &per);
+    for (uint32_t s = lo; s < hi && r == ncclSuccess; s++)
+      if (s < skip_lo || s >= skip_hi)
+        r = nccl().Recv(slots + ((size_t)s * n + (size_t)me * cnt) * elem_bytes, cnt * elem_bytes, ncclUint8, q, comm,
+                        ctx->stream);
+  }
+  const ncclResult_t e = nccl().GroupEnd();
+  if (r != ncclSuccess) return nccl_error(ctx, r, "ncclSend/ncclRecv");
+  if (e != ncclSuccess) return nccl_error(ctx, e, "ncclGroupEnd");
+  return ZK_OK;
+}
+
+// The quotient h on NUM_COSETS cosets of n rows (coset-major, `h`), evaluated by row range rows_per_rank * rank: the
+// rows of coset c are collected on rank c mod world (phase 0: before the inverse transforms, in place in `h`); after
+// that rank transformed its cosets into `hc`, every rank receives its coefficient range of every coset (phase 1, in
+// place in `hc`).  Only 1 / world of h ever moves twice, and no rank transforms more than ceil(cosets / world) cosets.
+int32_t dist_exchange_h(zk_ctx* ctx, char* buf, size_t elem_bytes, uint64_t n, int ncosets, int phase) {
+  const int world = ctx->dist_world, me = ctx->dist_rank;
+  if (world <= 1) return ZK_OK;
+  if (!ctx->nccl_comm) return set_error(ctx, ZK_E_STATE, "the context left its group after an error");
+  const uint64_t en = (uint64_t)ncosets * n, rows = en / (uint64_t)world, cnt = n / (uint64_t)world;
+  ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+  ncclResult_t r = nccl().GroupStart();
+  if (r != ncclSuccess) return nccl_error(ctx, r, "ncclGroupStart");
+  for (int c = 0; c < ncosets && r == ncclSuccess; c++) {
+    const int owner = c % world;
+    const uint64_t c0 = (uint64_t)c * n, c1 = c0 + n;
+    for (int q = 0; q < world && r == ncclSuccess; q++) {
+      if (q == owner) continue;
+      if (phase == 0) {  // rows of coset c that rank q evaluated -> owner
+        const uint64_t a = std::max<uint64_t>(c0, rows * q), b = std::min<uint64_t>(c1, rows * (q + 1));
+        if (a >= b) continue;
+        if (me == q) r = nccl().Send(buf + a * elem_bytes, (b - a) * elem_bytes, ncclUint8, owner, comm, ctx->stream);
+        else if (me == owner) r = nccl().Recv(buf + a * elem_bytes, (b - a) * elem_bytes, ncclUint8, q, comm, ctx->stream);
+      } else {  // coefficient range of rank q: owner -> q
+        const uint64_t a = c0 + cnt * q;
+        if (me == owner) r = nccl().Send(buf + a * elem_bytes, cnt * elem_bytes, ncclUint8, q, comm, ctx->stream);
+        else if (me == q) r = nccl().Recv(buf + a * elem_bytes, cnt * elem_bytes, ncclUint8, owner, comm, ctx->stream);
+      }
+    }
+  }
+  const ncclResult_t e = nccl().GroupEnd();
+  if (r != ncclSuccess) return nccl_error(ctx, r, "ncclSend/ncclRecv");
+  if (e != ncclSuccess) return nccl_error(ctx, e, "ncclGroupEnd");
+  return ZK_OK;
+}
+
 // results[m] <- sum over ranks of their results[m]; identical on every rank afterwards
 int32_t dist_sum_points(zk_ctx* ctx, XYZZ* results, int nb) {
   if (ctx->dist_world <= 1) return ZK_OK;
@@ -219,6 +287,20 @@ int32_t dist_sum_fields(zk_ctx* ctx, const Fp* d_vals, int count, Fp* host_out) 
     for (int q = 1; q < world; q++) acc = acc + all[(size_t)q * count + i];
     host_out[i] = acc;
   }
+  return ZK_OK;
+}
+
+// host_out[q * count + i] <- rank q's d_vals[i]: one small all-gather, identical on every rank
+int32_t dist_gather_fields(zk_ctx* ctx, const Fp* d_vals, int count, Fp* host_out) {
+  const int world = ctx->dist_world;
+  if (!ctx->nccl_comm) return set_error(ctx, ZK_E_STATE, "the context left its group after an error");
+  const size_t bytes = (size_t)count * sizeof(Fp);
+  int32_t rc = ensure_buf(ctx, ctx->dist_buf, bytes * world);
+  if (rc) return rc;
+  ncclResult_t r = nccl().AllGather(d_vals, ctx->dist_buf.ptr, bytes, ncclUint8, (ncclComm_t)ctx->nccl_comm, ctx->stream);
+  if (r != ncclSuccess) return nccl_error(ctx, r, "ncclAllGather");
+  ZK_CUDA(ctx, cudaMemcpyAsync(host_out, ctx->dist_buf.ptr, bytes * world, cudaMemcpyDeviceToHost, ctx->stream));
+  ZK_CUDA(ctx, zk_stream_sync(ctx));
   return ZK_OK;
 }
 

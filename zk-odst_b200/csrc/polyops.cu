@@ -200,7 +200,8 @@ __global__ void __launch_bounds__(128) batch_invert_kernel(Fp* __restrict__ data
 }
 
 // ---- evaluation ----------------------------------------------------------------------------------
-constexpr int EV_THREADS = 256, EV_PER = 64, EV_BLOCK = EV_THREADS * EV_PER;  // 64: the two power computations per thread amortise over more coefficients (2.4 -> 1.3 products per coefficient)
+constexpr int EV_THREADS = 256, EV_PER = 64, EV_BLOCK = EV_THREADS * EV_PER;
+static_assert(EV_BLOCK == EVAL_BLOCK, "evaluation block size");  // 64: the two power computations per thread amortise over more coefficients (2.4 -> 1.3 products per coefficient)
 
 __device__ __forceinline__ Fp block_sum(Fp v, Fp* sh) {
   sh[threadIdx.x] = v;
@@ -270,7 +271,7 @@ int32_t poly_eval_batch(zk_ctx* ctx, const EvalJob* jobs, int njobs, uint64_t n,
   cudaStream_t st = ctx->stream;
   const uint32_t all_blocks = (uint32_t)((n + EV_BLOCK - 1) / EV_BLOCK);
   uint64_t b_lo = 0, b_hi = all_blocks;
-  const bool split = ctx->dist_world > 1 && all_blocks >= 4u * (uint32_t)ctx->dist_world;
+  const bool split = dist_ranges_ok(n, ctx->dist_world);  // whole blocks per rank: reads stay inside the rank's range
   if (split) dist_range(all_blocks, ctx->dist_rank, ctx->dist_world, &b_lo, &b_hi);
   const uint32_t nblocks = (uint32_t)(b_hi - b_lo);
   for (int base = 0; base < njobs; base += 48) {

@@ -26,6 +26,22 @@ inline void launch_map(zk_ctx* ctx, uint64_t n, F f, int threads = 256) {
   ctx->launches++;
 }
 
+// the same over the index range [lo, lo + count): f(i) for i in the range (row / coefficient ranges of a group)
+template <class F>
+__global__ void map_range_kernel(uint64_t lo, uint64_t count, F f) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x)
+    f(lo + i);
+}
+template <class F>
+inline void launch_map_range(zk_ctx* ctx, uint64_t lo, uint64_t count, F f, int threads = 256) {
+  if (count == 0) return;
+  uint64_t blocks = (count + threads - 1) / threads;
+  uint64_t cap = (uint64_t)ctx->sm_count * 32;
+  if (blocks > cap) blocks = cap;
+  map_range_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(lo, count, f);
+  ctx->launches++;
+}
+
 // ---- affine recurrence scan ----------------------------------------------------------------------
 // y_0 = init;  y_{i+1} = y_i * m_i + a_i      (i = 0 .. n-1), output y_0 .. y_{n-1}  (exclusive)
 // With a == nullptr the recurrence is the running product used by the permutation and lookup
@@ -47,7 +63,13 @@ struct EvalJob {
   const Fp* poly;   // coefficients, length n
   Fp point;
 };
+// Coefficients per evaluation block: a group shards every evaluation by coefficient range in whole blocks.
+constexpr uint64_t EVAL_BLOCK = 16384;
+// A group of `world` ranks works on rows / coefficients by contiguous range when every rank gets whole
+// evaluation blocks: rank r owns [r n / world, (r + 1) n / world) (the point ranges of the split MSMs as well).
+static inline bool dist_ranges_ok(uint64_t n, int world) { return world > 1 && n % ((uint64_t)world * EVAL_BLOCK) == 0; }
 // results[j] = poly_j(point_j); all jobs share the length n.  Results are copied to the host.
+// In a group (dist_ranges_ok) every rank reads only its own coefficient range of each polynomial.
 int32_t poly_eval_batch(zk_ctx* ctx, const EvalJob* jobs, int njobs, uint64_t n, Fp* results_host);
 // <a, b> over n elements
 int32_t inner_product(zk_ctx* ctx, const Fp* a, const Fp* b, uint64_t n, Fp* result_host);

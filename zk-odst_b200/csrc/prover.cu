@@ -59,6 +59,7 @@ struct ProofWorkspace {
   uint32_t* left_off = nullptr;  // exclusive scan of left_cnt
   uint32_t* first_flag_scan = nullptr;  // n: number of first-occurrence positions before p
   uint32_t* left_rank = nullptr;        // n: leftover list (rank per entry), ascending
+  Fp* pow_tabs = nullptr;               // group only: [4][n / world] powers of the opening points (multiopen)
   std::vector<void*> all;
 };
 
@@ -124,6 +125,7 @@ int32_t get_workspace(zk_ctx* ctx, DeviceKeys& K, ProofWorkspace** out) {
     A(table_vals, 65536); A(table_sorted, 65536);
     A(rank_of, 65536); A(counts, 65536 + 8); A(offsets, 65536 + 8); A(left_cnt, 65536 + 8); A(left_off, 65536 + 8);
     A(first_flag_scan, n + 8); A(left_rank, n + 8);
+    if (dist_ranges_ok(n, ctx->dist_world)) A(pow_tabs, 4 * (n / (uint64_t)ctx->dist_world));
 #undef A
   }
   *out = (ProofWorkspace*)K.workspace;
@@ -389,6 +391,26 @@ __global__ void scan_u32_kernel(const uint32_t* __restrict__ in, uint32_t* __res
   if (threadIdx.x == 0 && total) *total = carry;
 }
 
+// z[0] = init, z[i + 1] = z[i] * ratio[i] over n rows.  In a group working by row range (polyops.cuh
+// dist_ranges_ok) every rank scans its own rows [lo, lo + cnt) from 1, the range products are exchanged (one
+// field element per rank), the rows are scaled by the product of the ranges before them and the ranges are
+// all-gathered in place: the maps, the inversion and the scan cost 1 / world of the replicated form.
+int32_t grand_product(zk_ctx* ctx, const Fp* ratio, uint64_t n, uint64_t lo, uint64_t cnt, const Fp& init, Fp* z) {
+  if (cnt == n) return affine_scan(ctx, ratio, Fp::zero(), nullptr, n, init, z);
+  int32_t rc = affine_scan(ctx, ratio + lo, Fp::zero(), nullptr, cnt, Fp::one(), z + lo);
+  if (rc) return rc;
+  if ((rc = ensure_buf(ctx, ctx->eval_ws, 64 * sizeof(Fp)))) return rc;
+  Fp* d_tot = (Fp*)ctx->eval_ws.ptr;
+  const uint64_t last = lo + cnt - 1;
+  launch_map(ctx, 1, [=] __device__(uint64_t) { d_tot[0] = z[last] * ratio[last]; });
+  std::vector<Fp> tot((size_t)ctx->dist_world);
+  if ((rc = dist_gather_fields(ctx, d_tot, 1, tot.data()))) return rc;
+  Fp prefix = init;
+  for (int q = 0; q < ctx->dist_rank; q++) prefix = prefix * tot[q];
+  launch_map_range(ctx, lo, cnt, [=] __device__(uint64_t i) { z[i] = z[i] * prefix; });
+  return dist_allgather_device(ctx, z + lo, z, cnt * sizeof(Fp));
+}
+
 }  // namespace
 
 // ---- the prover ------------------------------------------------------------------------------------------
@@ -413,6 +435,12 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
   const uint64_t n = K.n, en = K.en;
   const int k = K.k;
   const uint64_t usable = n - (BLINDING + 1);
+  // A group shards the row- and coefficient-wise steps that are not MSMs or transforms by contiguous range
+  // (grand products, multiopen, the evaluations): rank r works on [r_lo, r_lo + r_cnt), the same range its
+  // share of every MSM covers; a single GPU (or a group size that does not divide the blocks) works on [0, n).
+  const bool by_range = dist_ranges_ok(n, ctx->dist_world);
+  const uint64_t r_cnt = by_range ? n / (uint64_t)ctx->dist_world : n;
+  const uint64_t r_lo = by_range ? r_cnt * (uint64_t)ctx->dist_rank : 0;
   NttOptions inv;
   inv.inverse = true;
   const unsigned T = 256;
@@ -540,15 +568,15 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
       Fp* den = W->tmp_a;
       Fp* num = W->tmp_b;
       const Fp d0 = delta_pow[c0] * beta, d1 = delta_pow[c1] * beta;
-      launch_map(ctx, n, [=] __device__(uint64_t i) {
+      launch_map_range(ctx, r_lo, r_cnt, [=] __device__(uint64_t i) {
         den[i] = (beta * s0[i] + gamma + v0[i]) * (beta * s1[i] + gamma + v1[i]);
         Fp w = i < n / 2 ? tw[i] : tw[i - n / 2].neg();
         num[i] = (d0 * w + gamma + v0[i]) * (d1 * w + gamma + v1[i]);
       });
-      if ((rc = batch_invert(ctx, den, n))) return rc;
-      launch_map(ctx, n, [=] __device__(uint64_t i) { num[i] = num[i] * den[i]; });
+      if ((rc = batch_invert(ctx, den + r_lo, r_cnt))) return rc;
+      launch_map_range(ctx, r_lo, r_cnt, [=] __device__(uint64_t i) { num[i] = num[i] * den[i]; });
       Fp* z = W->z_vals[s];
-      if ((rc = affine_scan(ctx, num, Fp::zero(), nullptr, n, last_z, z))) return rc;
+      if ((rc = grand_product(ctx, num, n, r_lo, r_cnt, last_z, z))) return rc;
       Fp tails[5];
       for (auto& t : tails) t = tape.next();
       if ((rc = upload_fp(ctx, z + n - BLINDING, tails, BLINDING))) return rc;
@@ -564,10 +592,11 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
   {
     Fp *den = W->tmp_a, *num = W->tmp_b, *z = W->z_vals[NUM_SETS];
     const Fp *pin = W->pin, *ptab = W->ptab, *cin = W->cin, *ctab = W->ctab;
-    launch_map(ctx, n, [=] __device__(uint64_t i) { den[i] = (beta + pin[i]) * (gamma + ptab[i]); });
-    if ((rc = batch_invert(ctx, den, n))) return rc;
-    launch_map(ctx, n, [=] __device__(uint64_t i) { num[i] = den[i] * (cin[i] + beta) * (ctab[i] + gamma); });
-    if ((rc = affine_scan(ctx, num, Fp::zero(), nullptr, n, Fp::one(), z))) return rc;
+    launch_map_range(ctx, r_lo, r_cnt, [=] __device__(uint64_t i) { den[i] = (beta + pin[i]) * (gamma + ptab[i]); });
+    if ((rc = batch_invert(ctx, den + r_lo, r_cnt))) return rc;
+    launch_map_range(ctx, r_lo, r_cnt,
+                     [=] __device__(uint64_t i) { num[i] = den[i] * (cin[i] + beta) * (ctab[i] + gamma); });
+    if ((rc = grand_product(ctx, num, n, r_lo, r_cnt, Fp::one(), z))) return rc;
     Fp tails[5];
     for (auto& t : tails) t = tape.next();
     if ((rc = upload_fp(ctx, z + n - BLINDING, tails, BLINDING))) return rc;
@@ -635,7 +664,15 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
     // point to point (world x less traffic than gathering the columns in full)
     const bool shard_rows = world > 1 && en % (uint64_t)world == 0;
     if (world > 1) {
-      if ((rc = dist_allgather_device(ctx, W->polys_all + send_slot * n, W->polys_all, spr * n * sizeof(Fp)))) return rc;
+      // coefficients: with the evaluations and the multiopen argument working by coefficient range, a rank needs
+      // only its own range of the columns it did not transform (1 / world of an all-gather)
+      if (by_range) {
+        if ((rc = dist_exchange_ranges(ctx, (char*)W->polys_all, sizeof(Fp), n, NUM_WITNESS_POLYS, NUM_USED_COLUMNS,
+                                       NUM_ADVICE_COLUMNS)))
+          return rc;
+      } else if ((rc = dist_allgather_device(ctx, W->polys_all + send_slot * n, W->polys_all, spr * n * sizeof(Fp)))) {
+        return rc;
+      }
       if (shard_rows) {
         if ((rc = dist_exchange_quotient_rows(ctx, (char*)W->cosets_all, sizeof(Fp), n, en, NUM_WITNESS_POLYS)))
           return rc;
@@ -677,22 +714,37 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
     for (int e = 1; e < 127; e++) qa.k.pow2[e] = qa.k.pow2[e - 1].dbl();
     // rows shard too: every rank now holds all coset columns, evaluates its own range of the 3n rows and
     // the ranges of h are all-gathered in place
+    const bool h_by_coset = shard_rows && by_range;  // cosets transformed by their owners, pieces by range
     if (shard_rows) {
       const uint64_t rows = en / (uint64_t)world, row_lo = rows * (uint64_t)ctx->dist_rank;
       if ((rc = quotient_run(ctx, qa, n, row_lo, row_lo + rows))) return rc;
-      if ((rc = dist_allgather_device(ctx, W->h + row_lo, W->h, rows * sizeof(Fp)))) return rc;
+      if (h_by_coset) {
+        if ((rc = dist_exchange_h(ctx, (char*)W->h, sizeof(Fp), n, NUM_COSETS, 0))) return rc;
+      } else if ((rc = dist_allgather_device(ctx, W->h + row_lo, W->h, rows * sizeof(Fp)))) {
+        return rc;
+      }
     } else {
       if ((rc = quotient_run(ctx, qa, n, 0, en))) return rc;
     }
     // back to coefficients.  On coset j, h(c_j w^i) = sum_p (c_j^n)^p h_p(c_j w^i): the size-n inverse
     // transform of the coset's values, unscaled by c_j^-i, is e_j = sum_p gamma_j^p h_p coefficient-wise,
     // and the 3 x 3 Vandermonde system gives the three pieces h_p (K.h_solve = V^-1).
-    NttOptions o;
-    o.inverse = true;
-    o.batch = NUM_COSETS;
-    o.in_stride = n;
-    o.out_stride = n;
-    if ((rc = ntt_run(ctx, W->h, (uint32_t)n, W->h_coeffs, k, o))) return rc;
+    if (h_by_coset) {
+      for (int c = 0; c < NUM_COSETS; c++) {
+        if (c % world != ctx->dist_rank) continue;
+        NttOptions o;
+        o.inverse = true;
+        if ((rc = ntt_run(ctx, W->h + (size_t)c * n, (uint32_t)n, W->h_coeffs + (size_t)c * n, k, o))) return rc;
+      }
+      if ((rc = dist_exchange_h(ctx, (char*)W->h_coeffs, sizeof(Fp), n, NUM_COSETS, 1))) return rc;
+    } else {
+      NttOptions o;
+      o.inverse = true;
+      o.batch = NUM_COSETS;
+      o.in_stride = n;
+      o.out_stride = n;
+      if ((rc = ntt_run(ctx, W->h, (uint32_t)n, W->h_coeffs, k, o))) return rc;
+    }
     {
       Fp* hc = W->h_coeffs;
       const Fp* un = K.coset_unscale;
@@ -701,7 +753,8 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
         for (int j = 0; j < NUM_COSETS; j++) m[p][j] = K.h_solve[p][j];
       const Fp m00 = m[0][0], m01 = m[0][1], m02 = m[0][2], m10 = m[1][0], m11 = m[1][1], m12 = m[1][2],
                m20 = m[2][0], m21 = m[2][1], m22 = m[2][2];
-      launch_map(ctx, n, [=] __device__(uint64_t i) {
+      // (only the commitments of the pieces and h_poly read h_coeffs: by coefficient range in a group)
+      launch_map_range(ctx, r_lo, r_cnt, [=] __device__(uint64_t i) {
         const Fp e0 = hc[i] * un[i], e1 = hc[n + i] * un[n + i], e2 = hc[2 * n + i] * un[2 * n + i];
         hc[i] = m00 * e0 + m01 * e1 + m02 * e2;
         hc[n + i] = m10 * e0 + m11 * e1 + m12 * e2;
@@ -737,7 +790,9 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
     const Fp* hc = W->h_coeffs;
     Fp* hp = W->h_poly;
     const Fp xn2 = xn * xn;
-    launch_map(ctx, n, [=] __device__(uint64_t i) { hp[i] = hc[i] + hc[n + i] * xn + hc[2 * n + i] * xn2; });
+    // (only the multiopen argument reads h_poly: a rank of a group needs its own coefficient range)
+    launch_map_range(ctx, r_lo, r_cnt,
+                     [=] __device__(uint64_t i) { hp[i] = hc[i] + hc[n + i] * xn + hc[2 * n + i] * xn2; });
   }
   const Fp h_blind = h_blinds[0] + h_blinds[1] * xn + h_blinds[2] * xn * xn;
   std::vector<EvalJob> jobs;
@@ -824,39 +879,67 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
   // set index (`or_insert(num_sets)`), iteration order does not matter for the prover.
   std::vector<Fp> q_blinds(sets.size(), Fp::zero());
   std::vector<bool> started(sets.size(), false);
+  // Everything below works on the coefficient range [r_lo, r_lo + r_cnt) (all of [0, n) on one GPU): the
+  // linear combinations are coefficient-wise, the commitment of q' is an MSM over the same range of g, the
+  // evaluations at x3 are sums over ranges; only the division by (X - p) couples ranges, through one carry.
   for (auto& op : polys) {
     Fp* acc = W->q_polys[op.set];
     const Fp* np = op.poly;
     if (!started[op.set]) {
-      ZK_CUDA(ctx, cudaMemcpyAsync(acc, np, n * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
+      ZK_CUDA(ctx, cudaMemcpyAsync(acc + r_lo, np + r_lo, r_cnt * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
       started[op.set] = true;
     } else {
-      launch_map(ctx, n, [=] __device__(uint64_t i) { acc[i] = acc[i] * x1 + np[i]; });
+      launch_map_range(ctx, r_lo, r_cnt, [=] __device__(uint64_t i) { acc[i] = acc[i] * x1 + np[i]; });
     }
     q_blinds[op.set] = q_blinds[op.set] * x1 + op.blind;
   }
-  // q'(X) = sum_sets x2^.. * q_set(X) / prod (X - p): synthetic division as an affine scan over
-  // the reversed coefficient vector
+  // q'(X) = sum_sets x2^.. * q_set(X) / prod (X - p).  Division by (X - p) is the recurrence y_0 = 0,
+  // y_{j+1} = y_j p + c_{n-1-j} over the coefficients from the top down (quotient coefficient i = y_{n-1-i}; the
+  // vectors keep length n, a zero top coefficient costs nothing) — an affine scan.  By range: rank r scans its
+  // own coefficients from 0, which leaves out carry_r p^t at distance t from the top of its range, where carry_r
+  // is the value that enters the range from the ranks above; the per-range end values are exchanged, the carries
+  // follow on the host, and the correction uses a table of powers of p (built once per opening point).
+  const uint64_t r_hi = r_lo + r_cnt;
+  std::vector<Fp*> pow_tab(points.size(), nullptr);
+  if (by_range) {
+    if (points.size() > 4) return set_error(ctx, ZK_E_INVALID, "too many opening points");
+    for (size_t pi = 0; pi < points.size(); pi++) {
+      pow_tab[pi] = W->pow_tabs + pi * r_cnt;
+      if ((rc = affine_scan(ctx, nullptr, points[pi], nullptr, r_cnt, Fp::one(), pow_tab[pi]))) return rc;
+    }
+  }
   for (size_t s = 0; s < sets.size(); s++) {
     Fp* cur = W->tmp_a;
-    ZK_CUDA(ctx, cudaMemcpyAsync(cur, W->q_polys[s], n * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
-    uint64_t len = n;
+    ZK_CUDA(ctx, cudaMemcpyAsync(cur + r_lo, W->q_polys[s] + r_lo, r_cnt * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
     for (int pi : sets[s]) {
       const Fp pt = points[pi];
-      Fp* rev = W->tmp_b;
-      Fp* scanned = W->tmp_c;
-      const uint64_t L = len;
-      launch_map(ctx, L, [=] __device__(uint64_t j) { rev[j] = cur[L - 1 - j]; });
-      // y_0 = 0, y_{j+1} = y_j * pt + rev[j];  quotient coefficient i = y_{L-1-i}
-      if ((rc = affine_scan(ctx, nullptr, pt, rev, L, Fp::zero(), scanned))) return rc;
-      launch_map(ctx, n, [=] __device__(uint64_t i) { cur[i] = i + 1 < L ? scanned[L - 1 - i] : Fp::zero(); });
-      len = L - 1;
+      Fp* rev = W->tmp_b;      // rev[t] = cur[r_hi - 1 - t]: the range's coefficients from the top down
+      Fp* scanned = W->tmp_c;  // y at distance t from the top of the range, without the carry
+      launch_map(ctx, r_cnt, [=] __device__(uint64_t t) { rev[t] = cur[r_hi - 1 - t]; });
+      if ((rc = affine_scan(ctx, nullptr, pt, rev, r_cnt, Fp::zero(), scanned))) return rc;
+      if (!by_range) {
+        launch_map(ctx, r_cnt, [=] __device__(uint64_t t) { cur[r_hi - 1 - t] = scanned[t]; });
+        continue;
+      }
+      // the value leaving this range at its lower end, were nothing entering it: scanned[cnt - 1] p + rev[cnt - 1]
+      if ((rc = ensure_buf(ctx, ctx->eval_ws, 64 * sizeof(Fp)))) return rc;
+      Fp* d_end = (Fp*)ctx->eval_ws.ptr;
+      const uint64_t lastt = r_cnt - 1;
+      launch_map(ctx, 1, [=] __device__(uint64_t) { d_end[0] = scanned[lastt] * pt + rev[lastt]; });
+      std::vector<Fp> ends((size_t)ctx->dist_world);
+      if ((rc = dist_gather_fields(ctx, d_end, 1, ends.data()))) return rc;
+      // carries from the top rank down: carry_{world-1} = 0, carry_{q-1} = carry_q p^cnt + end_q
+      const Fp p_cnt = pt.pow_u64(r_cnt);
+      Fp carry = Fp::zero();
+      for (int q = ctx->dist_world - 1; q > ctx->dist_rank; q--) carry = carry * p_cnt + ends[q];
+      const Fp* pw = pow_tab[pi];
+      launch_map(ctx, r_cnt, [=] __device__(uint64_t t) { cur[r_hi - 1 - t] = scanned[t] + carry * pw[t]; });
     }
     Fp* qp = W->q_prime;
     if (s == 0) {
-      ZK_CUDA(ctx, cudaMemcpyAsync(qp, cur, n * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
+      ZK_CUDA(ctx, cudaMemcpyAsync(qp + r_lo, cur + r_lo, r_cnt * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
     } else {
-      launch_map(ctx, n, [=] __device__(uint64_t i) { qp[i] = qp[i] * x2 + cur[i]; });
+      launch_map_range(ctx, r_lo, r_cnt, [=] __device__(uint64_t i) { qp[i] = qp[i] * x2 + cur[i]; });
     }
   }
   const Fp q_prime_blind = tape.next();
@@ -877,10 +960,10 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
   Fp p_blind = q_prime_blind;
   {
     Fp* pp = W->p_poly;
-    ZK_CUDA(ctx, cudaMemcpyAsync(pp, W->q_prime, n * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
+    ZK_CUDA(ctx, cudaMemcpyAsync(pp + r_lo, W->q_prime + r_lo, r_cnt * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
     for (size_t s = 0; s < sets.size(); s++) {
       const Fp* q = W->q_polys[s];
-      launch_map(ctx, n, [=] __device__(uint64_t i) { pp[i] = pp[i] * x4 + q[i]; });
+      launch_map_range(ctx, r_lo, r_cnt, [=] __device__(uint64_t i) { pp[i] = pp[i] * x4 + q[i]; });
       p_blind = p_blind * x4 + q_blinds[s];
     }
   }
@@ -903,11 +986,13 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
     const Fp xi = tr.squeeze_challenge();
     const Fp z = tr.squeeze_challenge();
     Fp* pp = W->p_poly;  // becomes p'
-    launch_map(ctx, n, [=] __device__(uint64_t i) { pp[i] = sp[i] * xi + pp[i]; });
+    launch_map_range(ctx, r_lo, r_cnt, [=] __device__(uint64_t i) { pp[i] = sp[i] * xi + pp[i]; });
     {
       EvalJob j{pp, x3};
       Fp v;
       if ((rc = poly_eval_batch(ctx, &j, 1, n, &v))) return rc;
+      // the folding rounds pair coefficient i with i + half: from here on every rank holds p' in full
+      if (by_range && (rc = dist_allgather_device(ctx, pp + r_lo, pp, r_cnt * sizeof(Fp)))) return rc;
       launch_map(ctx, 1, [=] __device__(uint64_t) { pp[0] = pp[0] - v; });
     }
     Fp f = s_blind * xi + p_blind;

@@ -141,8 +141,15 @@ int32_t dist_allgather_device(zk_ctx* ctx, const void* send, void* recv, size_t 
 // column-sharded slot arrays -> the row segments each rank's share of the quotient reads (dist.cu)
 int32_t dist_exchange_quotient_rows(zk_ctx* ctx, char* slots, size_t elem_bytes, uint64_t n, uint64_t en,
                                     uint32_t nslots);
+// column-sharded slot arrays -> every rank's own element range of every slot (dist.cu)
+int32_t dist_exchange_ranges(zk_ctx* ctx, char* slots, size_t elem_bytes, uint64_t n, uint32_t nslots, uint32_t skip_lo,
+                             uint32_t skip_hi);
+// rows of the quotient -> the rank that transforms their coset (phase 0); coefficient ranges back (phase 1)
+int32_t dist_exchange_h(zk_ctx* ctx, char* buf, size_t elem_bytes, uint64_t n, int ncosets, int phase);
 // host_out[i] <- sum over ranks of d_vals[i] (one small all-gather, summed on the host)
 int32_t dist_sum_fields(zk_ctx* ctx, const Fp* d_vals, int count, Fp* host_out);
+// host_out[q * count + i] <- rank q's d_vals[i] (device, `count` field elements)
+int32_t dist_gather_fields(zk_ctx* ctx, const Fp* d_vals, int count, Fp* host_out);
 void dist_free(zk_ctx* ctx);
 // group contexts: leave the group after a local error; timed host wait that cannot deadlock on a failed peer
 void dist_abort(zk_ctx* ctx);
