@@ -237,6 +237,14 @@ int32_t zk_create_proof_device_inputs(zk_ctx* ctx, const uint8_t* d_inputs, uint
  * against the context's params and keys.  ZK_OK = accepted; ZK_E_VERIFY = rejected (reason in
  * zk_last_error: malformed encoding, truncated / trailing bytes, final MSM not the identity). */
 int32_t zk_verify_proof(zk_ctx* ctx, const uint8_t* proof, uint64_t proof_len);
+/* Batch verification (halo2_proofs 0.3.0 `plonk::verifier::BatchVerifier`; the reference verifies one proof per
+ * criterion iteration, benches/blake2f.rs:138-144): `count` proofs of the context's circuit, concatenated in `proofs`
+ * with lengths `proof_lens`.  The transcript phase of each proof runs on the host; their final multi-scalar
+ * multiplications are combined with weights drawn from XorShiftRng(seed) into ONE size-n fixed-base MSM and one
+ * variable-base MSM.  ZK_OK = all accepted; ZK_E_VERIFY = at least one is rejected (malformed proofs are reported as
+ * they are met; a failing combined MSM does not say which proof is wrong — fall back to zk_verify_proof). */
+int32_t zk_verify_proofs_batch(zk_ctx* ctx, const uint8_t* proofs, const uint64_t* proof_lens, uint64_t count,
+                               const uint8_t seed[16]);
 
 /* `MockProver::run(k, &circuit, vec![]).verify()` (blake2f/table16/spread_table.rs:759-763) for the
  * BLAKE2f circuit of the context's keys: every gate on every usable row, every lookup input against

@@ -61,6 +61,8 @@ extern "C" {
     pub fn zk_blake2b_records(msg: *const u8, len: u64, rounds: u32, records_out: *mut u8,
         n_records: *mut u64, digest_out: *mut u8) -> i32;
     pub fn zk_verify_proof(ctx: *mut zk_ctx, proof: *const u8, proof_len: u64) -> i32;
+    pub fn zk_verify_proofs_batch(ctx: *mut zk_ctx, proofs: *const u8, proof_lens: *const u64, count: u64,
+        seed: *const u8) -> i32;
     pub fn zk_mock_verify(ctx: *mut zk_ctx, inputs: *const u8, n_compressions: u64,
         advice_override: *const c_void, failure: *mut u64) -> i32;
     pub fn zk_dist_unique_id(out: *mut u8) -> i32;

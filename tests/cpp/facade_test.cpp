@@ -3,6 +3,7 @@
 // rewritten against include/zkodst.hpp.  Built and run by tests/test_facade.py (needs a GPU to run).
 #include <cstdio>
 #include <cstdlib>
+#include <stdexcept>
 #include <string>
 
 #include "zkodst.hpp"
@@ -143,6 +144,36 @@ int main(int argc, char** argv) {
       CHECK(again.finalize() == proof);
       const std::vector<uint8_t> file = params.write();
       CHECK(file.size() == 4 + (2 * (size_t(1) << k) + 2) * 32);
+    }
+    {  // benches/blake2f.rs:79-97,119-136: params and proof cached on disk, read back, the cached proof verified
+      const std::string dir = std::string(getenv("TMPDIR") ? getenv("TMPDIR") : "/tmp") + "/blake2f_assets";
+      (void)!system(("mkdir -p " + dir).c_str());
+      const std::string params_path = dir + "/blake2f_params", proof_path = dir + "/blake2f_proof";
+      auto write_file = [](const std::string& path, const std::vector<uint8_t>& bytes) -> void {
+        FILE* f = fopen(path.c_str(), "wb");
+        if (!f || fwrite(bytes.data(), 1, bytes.size(), f) != bytes.size()) throw std::runtime_error("cannot write " + path);
+        fclose(f);
+      };
+      auto read_file = [](const std::string& path) -> std::vector<uint8_t> {
+        std::vector<uint8_t> bytes;
+        FILE* f = fopen(path.c_str(), "rb");
+        if (!f) throw std::runtime_error("cannot read " + path);
+        uint8_t buf[1 << 16];
+        for (size_t got; (got = fread(buf, 1, sizeof buf, f)) > 0;) bytes.insert(bytes.end(), buf, buf + got);
+        fclose(f);
+        return bytes;
+      };
+      write_file(params_path, params.write());
+      write_file(proof_path, proof);
+      const Params cached = Params::read(dev, read_file(params_path));     // Params::read (benches/blake2f.rs:95-97)
+      const VerifyingKey vk2 = keygen_vk(cached, *empty_circuit);
+      const ProvingKey pk2 = keygen_pk(cached, vk2, *empty_circuit);
+      const std::vector<uint8_t> cached_proof = read_file(proof_path);
+      CHECK(cached_proof == proof);
+      Blake2bRead rd = Blake2bRead::init(cached_proof);
+      verify_proof(cached, pk2.get_vk(), SingleVerifier::new_(cached), {{}}, rd);
+      remove(params_path.c_str());
+      remove(proof_path.c_str());
     }
     {  // a circuit of another shape (11 rounds) is refused before anything reaches the device
       Blake2fWitness w = vector5();

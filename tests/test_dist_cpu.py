@@ -156,3 +156,79 @@ def test_quotient_row_segments_cover_the_rotations():
                     got.update(range(start, start + length))
                 assert got == need, (n, world, r)
             assert prev == 3 * n
+
+
+# ---- the range-sharded steps of a group: grand product and division by (X - p) ---------------------
+P_MOD = 0x40000000000000000000000000000000224698fc094cf91b992d30ed00000001
+
+
+def _range_worker(rank, world, port, n, out_path):
+    """What prover.cu does per rank in a group, on Python integers: scan the own range from a neutral start, exchange
+    one field element per rank (all_gather over gloo), correct the range.  Compared with the serial recurrences."""
+    import random
+    import torch
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    rnd = random.Random(5)
+    ratio = [rnd.randrange(1, P_MOD) for _ in range(n)]
+    coeffs = [rnd.randrange(P_MOD) for _ in range(n)]
+    pt, init = rnd.randrange(P_MOD), rnd.randrange(1, P_MOD)
+    cnt = n // world
+    lo, hi = rank * cnt, (rank + 1) * cnt
+
+    def gather(v):  # one field element per rank
+        t = torch.tensor([(v >> (62 * i)) & ((1 << 62) - 1) for i in range(5)], dtype=torch.int64)
+        out = [torch.zeros(5, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [sum(int(o[i]) << (62 * i) for i in range(5)) for o in out]
+
+    # grand product (prover.cu grand_product): z[0] = init, z[i + 1] = z[i] * ratio[i]
+    z_local, acc = [], 1
+    for i in range(lo, hi):
+        z_local.append(acc)
+        acc = acc * ratio[i] % P_MOD
+    totals = gather(acc)
+    prefix = init
+    for q in range(rank):
+        prefix = prefix * totals[q] % P_MOD
+    z_mine = [v * prefix % P_MOD for v in z_local]
+    z_ref, acc = [], init
+    for i in range(n):
+        z_ref.append(acc)
+        acc = acc * ratio[i] % P_MOD
+    ok = z_mine == z_ref[lo:hi]
+
+    # division by (X - pt) (multiopen): y_0 = 0, y_{j+1} = y_j pt + c_{n-1-j}; quotient coefficient i = y_{n-1-i}
+    scanned, y = [], 0
+    for t in range(cnt):           # t = distance from the top of the range
+        scanned.append(y)
+        y = (y * pt + coeffs[hi - 1 - t]) % P_MOD
+    ends = gather(y)
+    p_cnt = pow(pt, cnt, P_MOD)
+    carry = 0
+    for q in range(world - 1, rank, -1):
+        carry = (carry * p_cnt + ends[q]) % P_MOD
+    quot_mine = {hi - 1 - t: (scanned[t] + carry * pow(pt, t, P_MOD)) % P_MOD for t in range(cnt)}
+    quot_ref, y = [0] * n, 0
+    for j in range(n):
+        quot_ref[n - 1 - j] = y
+        y = (y * pt + coeffs[n - 1 - j]) % P_MOD
+    ok = ok and all(quot_mine[i] == quot_ref[i] for i in range(lo, hi))
+    # (the quotient really is the division: q(X) (X - pt) + rem == c(X), checked at a point)
+    if rank == 0:
+        x = rnd.randrange(P_MOD)
+        ev = lambda cs: sum(c * pow(x, i, P_MOD) for i, c in enumerate(cs)) % P_MOD
+        ok = ok and (ev(quot_ref) * (x - pt) + y) % P_MOD == ev(coeffs)
+    with open(out_path + ".%d" % rank, "w") as f:
+        f.write("ok" if ok else "mismatch")
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_range_sharded_scans(tmp_path, world):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    out = str(tmp_path / "r")
+    mp.spawn(_range_worker, args=(world, port, 64, out), nprocs=world, join=True)
+    for r in range(world):
+        assert open(out + ".%d" % r).read() == "ok", r

@@ -93,3 +93,25 @@ def test_mock_verify_passes_and_locates_failures(setup, oracle, zk):
         if fail is not None:
             kinds.add(int(fail[0]))
     assert {1, 2} <= kinds
+
+
+def test_batch_verification(setup, zk):
+    """zk_verify_proofs_batch (halo2's BatchVerifier): several proofs, one combined final MSM; a single bad proof
+    anywhere in the batch is caught, as are malformed bytes."""
+    ctx, op, seed, inputs = setup
+    proofs = [ctx.create_proof(inputs, 2, bytes([i]) * 16) for i in range(1, 5)]
+    assert len(set(proofs)) == 4
+    wseed = bytes(range(16))
+    assert ctx.verify_proofs_batch(proofs, wseed)
+    assert ctx.verify_proofs_batch(proofs[:1], wseed)
+    for victim in range(4):
+        bad = list(proofs)
+        b = bytearray(bad[victim])
+        b[-20] ^= 1                      # the final scalar f: only the combined MSM can notice
+        bad[victim] = bytes(b)
+        assert not ctx.verify_proofs_batch(bad, wseed), victim
+        assert op.verify(bad[victim])[0] != 0
+    b = bytearray(proofs[2])
+    b[5] ^= 0x40                         # a commitment: a different transcript, rejected by the batch as well
+    assert not ctx.verify_proofs_batch([proofs[0], bytes(b)], wseed)
+    assert not ctx.verify_proofs_batch([proofs[0], proofs[1][:-1]], wseed)

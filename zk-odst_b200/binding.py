@@ -70,6 +70,7 @@ def load_library():
             "zk_blake2f_compress": (i32, [c.c_char_p, c.c_char_p]),
             "zk_blake2b_records": (i32, [c.c_char_p, u64, u32, c.c_char_p, c.POINTER(u64), c.c_char_p]),
             "zk_verify_proof": (i32, [vp, c.c_char_p, u64]),
+            "zk_verify_proofs_batch": (i32, [vp, c.c_char_p, c.POINTER(u64), u64, c.c_char_p]),
             "zk_mock_verify": (i32, [vp, vp, u64, vp, c.POINTER(u64)]),
             "zk_dist_unique_id": (i32, [c.c_char_p]),
             "zk_dist_init": (i32, [vp, c.c_char_p, i32, i32]),
@@ -351,6 +352,16 @@ class Context:
     def verify_proof(self, proof):
         """True if accepted; False (reason in .last_error()) if rejected."""
         rc = self.lib.zk_verify_proof(self.h, bytes(proof), len(proof))
+        if rc == 0:
+            return True
+        if rc == -7:
+            return False
+        self._check(rc)
+
+    def verify_proofs_batch(self, proofs, seed):
+        """True if every proof of the list is accepted (one combined final MSM); False if any is rejected."""
+        lens = (ctypes.c_uint64 * len(proofs))(*[len(p) for p in proofs])
+        rc = self.lib.zk_verify_proofs_batch(self.h, b"".join(bytes(p) for p in proofs), lens, len(proofs), bytes(seed))
         if rc == 0:
             return True
         if rc == -7:

@@ -39,6 +39,9 @@ constexpr int NTT_MAX_ROUNDS = 5;
 // proof): 3 stages / 3 blocks (168 registers) 7.71, 3 / 4 (128 registers, spills) 7.22, 2 / 6 (80 registers)
 // 6.87, 2 / 8 (64 registers, spills) 7.07 — the butterflies are bound by the half-rate IMAD.WIDE.X
 // chains, so what the wider rounds save in shared-memory trips they lose in resident warps.
+// Round 2 (profiles/r02_ntt_variants.json): 256-thread blocks — one radix-4 unit per thread and round — at 3 or 4
+// blocks per SM are 1.6-1.9 % slower than 128 threads x 6 blocks; the six resident blocks are what the 221 KB of
+// shared memory allow either way.
 constexpr int NTT_ROUND_STAGES = 2;
 constexpr int NTT_MIN_BLOCKS = 6;
 

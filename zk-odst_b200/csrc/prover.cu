@@ -8,6 +8,8 @@
 // (K7), grand products (K8), the quotient (K6), evaluations (K9), multiopen (K10) and the inner
 // product argument (K11).  The order of transcript writes, challenge squeezes and RNG draws is
 // halo2's; proof bytes are compared with the CPU oracle byte for byte in tests/.
+#include <nvtx3/nvToolsExt.h>
+
 #include <chrono>
 #include <cstdlib>
 
@@ -212,18 +214,30 @@ int32_t upload_fp(zk_ctx* ctx, Fp* dst, const Fp* src, size_t count) {
   return ZK_OK;
 }
 
-// ---- optional wall-clock phase trace (ZK_PHASE_TRACE=1): syncs at phase boundaries, stderr only ---------
+// ---- phases of one proof: NVTX ranges (always; a no-op without a profiler attached) and an optional
+// wall-clock trace (ZK_PHASE_TRACE=1: syncs at phase boundaries, stderr only) -----------------------------------
+static const char* const PROOF_PHASES[] = {"witness", "advice commit + iNTT", "lookup permute + commit",
+                                           "permutation products", "lookup product", "random poly commit",
+                                           "cosets + quotient + iNTT", "h commit", "evaluations", "multiopen", "ipa"};
 struct PhaseTrace {
   bool on;
   cudaStream_t st;
   std::chrono::steady_clock::time_point t;
+  size_t next = 0;  // index of the phase that is running
   explicit PhaseTrace(cudaStream_t s) : on(getenv("ZK_PHASE_TRACE") != nullptr), st(s) {
     if (on) {
       cudaStreamSynchronize(st);
       t = std::chrono::steady_clock::now();
     }
+    nvtxRangePushA(PROOF_PHASES[0]);
   }
+  ~PhaseTrace() {
+    if (next < sizeof PROOF_PHASES / sizeof *PROOF_PHASES) nvtxRangePop();  // error return inside a phase
+  }
+  // ends the running phase (whose name is passed for the trace) and starts the next one
   void mark(const char* name) {
+    nvtxRangePop();
+    if (++next < sizeof PROOF_PHASES / sizeof *PROOF_PHASES) nvtxRangePushA(PROOF_PHASES[next]);
     if (!on) return;
     cudaStreamSynchronize(st);
     auto now = std::chrono::steady_clock::now();

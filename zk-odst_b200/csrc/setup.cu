@@ -611,6 +611,10 @@ extern "C" int32_t zk_blake2f_keygen_chained(zk_ctx* ctx, uint32_t rounds, uint6
   fixed_columns_kernel<<<blocks, T, 0, st>>>(K.fixed_values[0], K.fixed_values[1], K.fixed_values[2], n);
   ctx->launches++;
   uint8_t* d_tmpl = nullptr;
+  uint64_t* d_map = nullptr;
+  DevTemps keygen_tmp;  // keygen's device temporaries: freed on every return path
+  keygen_tmp.own(&d_tmpl);
+  keygen_tmp.own(&d_map);
   ZK_CUDA(ctx, cudaMalloc((void**)&d_tmpl, (size_t)n_sel_cols * L.rows));
   for (int c = 0; c < n_sel_cols; c++) {
     ZK_CUDA(ctx, cudaMemcpyAsync(d_tmpl + (size_t)c * L.rows, sel_cols[c].data(), L.rows, cudaMemcpyHostToDevice, st));
@@ -631,7 +635,6 @@ extern "C" int32_t zk_blake2f_keygen_chained(zk_ctx* ctx, uint32_t rounds, uint6
   // permutation
   RegionPermutation perm(L.rows);
   for (auto& cc : L.copies) perm.copy(cc);
-  uint64_t* d_map = nullptr;
   ZK_CUDA(ctx, cudaMalloc((void**)&d_map, perm.mapping.size() * 8));
   ZK_CUDA(ctx, cudaMemcpyAsync(d_map, perm.mapping.data(), perm.mapping.size() * 8, cudaMemcpyHostToDevice, st));
   NttTables* TN = nullptr;
@@ -697,6 +700,8 @@ extern "C" int32_t zk_blake2f_keygen_chained(zk_ctx* ctx, uint32_t rounds, uint6
   // l_0, l_last, l_blind -> l_active = 1 - (l_last + l_blind)
   {
     Fp *tmp = nullptr, *tmp2 = nullptr, *lblind = nullptr;
+    DevTemps ltmp;
+    ltmp.own(&tmp); ltmp.own(&tmp2); ltmp.own(&lblind);
     ZK_CUDA(ctx, cudaMalloc((void**)&tmp, n * sizeof(Fp)));
     ZK_CUDA(ctx, cudaMalloc((void**)&tmp2, n * sizeof(Fp)));
     ZK_CUDA(ctx, cudaMalloc((void**)&lblind, K.en * sizeof(Fp)));
@@ -706,13 +711,8 @@ extern "C" int32_t zk_blake2f_keygen_chained(zk_ctx* ctx, uint32_t rounds, uint6
     if ((rc = build(2, lblind))) return rc;
     combine_active(ctx, K, lblind);
     ZK_CUDA(ctx, zk_stream_sync(ctx));
-    cudaFree(tmp);
-    cudaFree(tmp2);
-    cudaFree(lblind);
   }
   ZK_CUDA(ctx, zk_stream_sync(ctx));
-  cudaFree(d_tmpl);
-  cudaFree(d_map);
   // vk.transcript_repr as VerifyingKey::from_parts derives it: hash of the `{:?}` rendering of vk.pinned()
   // (vk_repr.cpp); a value obtained from halo2 itself can still be injected with zk_vk_repr_override
   K.pinned_debug = vk_pinned_debug(k, K.selectors, K.fixed_commitments, K.sigma_commitments);

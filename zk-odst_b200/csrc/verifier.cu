@@ -15,6 +15,7 @@
 #include "polyops.cuh"
 #include "prover_state.h"
 #include "transcript.h"
+#include "xorshift_jump.h"
 
 namespace zkodst {
 
@@ -41,25 +42,35 @@ struct Horner {
 
 // s_m = neg_c * prod_b us[k - 1 - b]^(bit b of m)   (commitment::Guard::compute_s), plus a constant
 // term on s_0
+// (batch verification: accumulate != 0 adds to s instead of overwriting; neg_c and constant then carry the proof's
+// random weight)
 __global__ void compute_s_kernel(Fp* __restrict__ s, uint64_t n, int k, const Fp* __restrict__ us, Fp neg_c,
-                                 Fp constant) {
+                                 Fp constant, int accumulate) {
   uint64_t m = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (m >= n) return;
   Fp acc = neg_c;
   for (int b = 0; b < k; b++)
     if ((m >> b) & 1) acc = acc * us[k - 1 - b];
   if (m == 0) acc = acc + constant;
-  s[m] = acc;
+  s[m] = accumulate ? s[m] + acc : acc;
 }
 
-int32_t verify_impl(zk_ctx* ctx, const uint8_t* proof, size_t proof_len) {
+// What the transcript phase of one proof leaves for the final check:
+//   sum_t terms[t].scalar * terms[t].point + sum_m s_m g_m + u_scalar U + w_scalar W == identity,
+//   s_m = neg_c * prod_b us[k-1-b]^(bit b of m) + [m = 0] s0_constant
+struct Guard {
+  std::vector<Term> terms;
+  std::vector<Fp> us;
+  Fp neg_c, s0_constant, u_scalar, w_scalar;
+};
+
+// host part: transcript, constraint evaluation at x, multiopen bookkeeping (throws on malformed proofs)
+int32_t verify_transcript(zk_ctx* ctx, const uint8_t* proof, size_t proof_len, Guard& out) {
   ProverState* S = prover_state(ctx);
   if (!S->has_params || !S->has_keys) return set_error(ctx, ZK_E_STATE, "verify_proof before params/keygen");
   const DeviceKeys& K = S->keys;
-  const DeviceParams& P = S->params;
   const uint64_t n = K.n;
   const int k = K.k;
-  cudaStream_t st = ctx->stream;
   NttTables* TN = nullptr;
   int32_t rc = ntt_tables(ctx, k, &TN);
   if (rc) return rc;
@@ -330,28 +341,52 @@ int32_t verify_impl(zk_ctx* ctx, const uint8_t* proof, size_t proof_len) {
     b = b * (one + us[j] * cur);
     cur = cur.sqr();
   }
-  const Fp neg_c = c.neg();
-  const Fp u_scalar = neg_c * b * zc, w_scalar = f.neg();
+  out.terms = std::move(acc.terms);
+  out.us = us;
+  out.neg_c = c.neg();
+  out.s0_constant = vv.neg();
+  out.u_scalar = out.neg_c * b * zc;
+  out.w_scalar = f.neg();
+  return ZK_OK;
+}
 
-  // ---- final MSM on the device -------------------------------------------------------------------------------
-  const size_t nt = acc.terms.size();
-  std::vector<Fp> hs(nt);
-  std::vector<Affine> hp(nt);
-  for (size_t i = 0; i < nt; i++) {
-    hs[i] = acc.terms[i].scalar;
-    hp[i] = acc.terms[i].point;
+// device part: the final MSM of one or several proofs.  With several, proof i is weighted by weights[i]: the sum
+// of the proofs' MSMs is the identity for random weights only if every one of them is (halo2's BatchVerifier) —
+// one size-n fixed-base MSM and one variable-base MSM for the whole batch.
+int32_t verify_final_msm(zk_ctx* ctx, const std::vector<Guard>& guards, const std::vector<Fp>& weights) {
+  ProverState* S = prover_state(ctx);
+  const DeviceKeys& K = S->keys;
+  const DeviceParams& P = S->params;
+  const uint64_t n = K.n;
+  const int k = K.k;
+  cudaStream_t st = ctx->stream;
+  int32_t rc;
+  std::vector<Fp> hs;
+  std::vector<Affine> hp;
+  Fp u_scalar = Fp::zero(), w_scalar = Fp::zero();
+  for (size_t i = 0; i < guards.size(); i++) {
+    for (auto& t : guards[i].terms) {
+      hs.push_back(t.scalar * weights[i]);
+      hp.push_back(t.point);
+    }
+    u_scalar = u_scalar + guards[i].u_scalar * weights[i];
+    w_scalar = w_scalar + guards[i].w_scalar * weights[i];
   }
+  const size_t nt = hs.size();
   if ((rc = ensure_buf(ctx, ctx->scratch_a, (size_t)(n + k + 8) * sizeof(Fp) + nt * sizeof(Fp)))) return rc;
   if ((rc = ensure_buf(ctx, ctx->scratch_b, nt * sizeof(Affine)))) return rc;
   Fp* d_s = (Fp*)ctx->scratch_a.ptr;
   Fp* d_us = d_s + n;
   Fp* d_ts = d_us + k + 8;
   Affine* d_tp = (Affine*)ctx->scratch_b.ptr;
-  ZK_CUDA(ctx, cudaMemcpyAsync(d_us, us.data(), (size_t)k * sizeof(Fp), cudaMemcpyHostToDevice, st));
   ZK_CUDA(ctx, cudaMemcpyAsync(d_ts, hs.data(), nt * sizeof(Fp), cudaMemcpyHostToDevice, st));
   ZK_CUDA(ctx, cudaMemcpyAsync(d_tp, hp.data(), nt * sizeof(Affine), cudaMemcpyHostToDevice, st));
-  compute_s_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_s, n, k, d_us, neg_c, vv.neg());
-  ctx->launches++;
+  for (size_t i = 0; i < guards.size(); i++) {
+    ZK_CUDA(ctx, cudaMemcpyAsync(d_us, guards[i].us.data(), (size_t)k * sizeof(Fp), cudaMemcpyHostToDevice, st));
+    compute_s_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_s, n, k, d_us, guards[i].neg_c * weights[i],
+                                                                  guards[i].s0_constant * weights[i], i ? 1 : 0);
+    ctx->launches++;
+  }
   ZK_CUDA(ctx, cudaGetLastError());
   const Fp extra[2] = {u_scalar, w_scalar};
   const uint32_t extra_idx[2] = {(uint32_t)n + 1, (uint32_t)n};
@@ -371,7 +406,44 @@ extern "C" int32_t zk_verify_proof(zk_ctx* ctx, const uint8_t* proof, uint64_t p
   if (!ctx || !proof) return ZK_E_INVALID;
   ZK_CUDA(ctx, cudaSetDevice(ctx->device));
   try {
-    return verify_impl(ctx, proof, proof_len);
+    std::vector<Guard> g(1);
+    int32_t rc = verify_transcript(ctx, proof, proof_len, g[0]);
+    if (rc) return rc;
+    return verify_final_msm(ctx, g, {Fp::one()});
+  } catch (std::exception& e) {
+    return set_error(ctx, ZK_E_VERIFY, e.what());
+  }
+}
+
+// Batch verification: the transcript phase of every proof on the host, then ONE final MSM for all of them,
+// proof i weighted by a field element drawn from XorShiftRng(seed) (the first weight is 1).
+extern "C" int32_t zk_verify_proofs_batch(zk_ctx* ctx, const uint8_t* proofs, const uint64_t* proof_lens,
+                                          uint64_t count, const uint8_t seed[16]) {
+  if (!ctx || !proofs || !proof_lens || !seed || count == 0) return ZK_E_INVALID;
+  ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+  try {
+    std::vector<Guard> guards(count);
+    std::vector<Fp> weights(count);
+    XsState st;
+    memcpy(st.s, seed, 16);
+    if (!(st.s[0] | st.s[1] | st.s[2] | st.s[3])) st.s[0] = st.s[1] = st.s[2] = st.s[3] = 0x0BAD5EED;
+    uint64_t off = 0;
+    for (uint64_t i = 0; i < count; i++) {
+      int32_t rc = verify_transcript(ctx, proofs + off, proof_lens[i], guards[i]);
+      if (rc) return rc;
+      off += proof_lens[i];
+      if (i == 0) {
+        weights[i] = Fp::one();
+      } else {
+        uint64_t w[8];
+        for (int j = 0; j < 8; j++) {
+          const uint64_t lo = xs_step(st);
+          w[j] = lo | ((uint64_t)xs_step(st) << 32);
+        }
+        weights[i] = Fp::from_u512(w);
+      }
+    }
+    return verify_final_msm(ctx, guards, weights);
   } catch (std::exception& e) {
     return set_error(ctx, ZK_E_VERIFY, e.what());
   }
