@@ -92,3 +92,41 @@ def test_contexts_are_independent_across_threads(zk):
     assert all(p == alone for o in out for p in o)
     for c in ctxs:
         c.close()
+
+
+def test_status_flag_is_per_call(zk):
+    """A record rejected by a kernel in one call must not fail the next call (round-1 advisor finding): the
+    asynchronous device-buffer witness entry latches a status bit when it meets f = 2; neither zk_mock_verify nor
+    zk_create_proof with valid records may inherit it, and zk_mock_verify validates its own records."""
+    import torch
+    ctx = zk.Context(0)
+    seed = zk.REFERENCE_SEED
+    ctx.params_generate_substitute(17, seed)
+    ctx.keygen(12, 2)
+    good = zk.synthetic_inputs(2)
+    bad = bytearray(good)
+    bad[212] = 2
+    # mock_verify: host-side EIP-152 validation, as create_proof
+    with pytest.raises(zk.ZkError) as e:
+        ctx.mock_verify(bytes(bad), 2)
+    assert e.value.code == -5
+    wrong_rounds = bytearray(good)
+    wrong_rounds[3] = 11
+    with pytest.raises(zk.ZkError) as e:
+        ctx.mock_verify(bytes(wrong_rounds), 2)
+    assert e.value.code == -5
+    assert ctx.mock_verify(good, 2) is None
+    # a stale status bit: the device-buffer witness call is asynchronous and is NOT followed by zk_ctx_synchronize
+    d_bad = torch.frombuffer(bad, dtype=torch.uint8).cuda()
+    d_adv = torch.empty((12, 1 << 17, 4), dtype=torch.int64, device="cuda")
+    ctx.witness_batch_device(17, 12, d_bad, 2, d_adv)
+    torch.cuda.synchronize()
+    assert ctx.mock_verify(good, 2) is None                       # clears and owns the flag
+    ctx.witness_batch_device(17, 12, d_bad, 2, d_adv)
+    torch.cuda.synchronize()
+    assert ctx.verify_proof(ctx.create_proof(good, 2, seed))      # starts from a clean flag
+    # absurd batch sizes are refused before any size is multiplied out (no 64-bit wrap)
+    with pytest.raises(zk.ZkError) as e:
+        ctx.witness_batch_device(17, 12, d_bad, (1 << 64) // 4996 + 1, d_adv)
+    assert e.value.code == -4
+    ctx.close()
