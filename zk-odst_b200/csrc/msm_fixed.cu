@@ -221,6 +221,11 @@ __global__ void fscan_add_kernel(uint32_t* __restrict__ out, const uint32_t* __r
     const uint32_t entries = v + counts[i];
     out[n] = entries;
     uint32_t chunk = (entries + resident_threads - 1) / resident_threads;
+    // small MSMs (the IPA's second stage: 2^14 points, 2,048 buckets of ~180 entries) would get 16-entry chunks
+    // and send every bucket down the heavy path (more than SERIAL_HEADS chunks per bucket, 68 us per launch):
+    // keep an average bucket within ~6 chunks instead
+    const uint32_t per_bucket = entries / n;
+    if (chunk < per_bucket / 6) chunk = per_bucket / 6;
     chunk = (chunk + 3) & ~3u;
     if (chunk < MIN_CHUNK) chunk = MIN_CHUNK;
     Plan p;
