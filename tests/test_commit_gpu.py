@@ -180,3 +180,49 @@ def test_config2_proof_bytes_match_oracle_k19(setup19, zk):
     assert op.verify(proof)[0] == 0
     assert ctx.verify_proof(ref)
     assert ctx.mock_verify(inputs, n) is None
+
+
+def test_k18_proof_bytes_match_oracle(oracle, zk):
+    """The smallest batch that leaves k = 17 (27 compressions -> k = 18): another transform plan (9 + 9 stages) and
+    MSM size; keys and proof bytes equal the oracle's."""
+    n = 27
+    k = zk.min_k(12, n)
+    assert k == 18
+    seed = zk.REFERENCE_SEED
+    ctx = zk.Context(0)
+    ctx.params_generate_substitute(k, seed)
+    ctx.keygen(12, n)
+    op = oracle_lib.OracleProver(oracle, k=k, seed=seed)
+    op.keygen(12, n)
+    assert ctx.vk_bytes() == op.vk_bytes()
+    inputs = zk.synthetic_inputs(n)
+    proof = ctx.create_proof(inputs, n, seed)
+    assert proof == op.create_proof(inputs, n, seed)
+    assert len(proof) == 4064 + 64          # two more IPA rounds than k = 17: one (L, R) pair
+    op.close()
+    ctx.close()
+
+
+def test_k20_proof_accepted_by_oracle_verifier(oracle, zk):
+    """k = 20 (128 compressions): the oracle's keygen_vk of the same circuit gives the same verifying key and its
+    verify_proof accepts the GPU proof (the oracle's own prover would take minutes at this size)."""
+    n = 128
+    k = zk.min_k(12, n)
+    assert k == 20
+    seed = zk.REFERENCE_SEED
+    ctx = zk.Context(0)
+    ctx.params_generate_substitute(k, seed)
+    ctx.keygen(12, n)
+    inputs = zk.synthetic_inputs(n)
+    proof = ctx.create_proof(inputs, n, seed)
+    assert ctx.verify_proof(proof) and ctx.mock_verify(inputs, n) is None
+    op = oracle_lib.OracleProver(oracle, k=k, seed=seed)
+    op.keygen_vk(12, n)
+    assert ctx.vk_bytes() == op.vk_bytes()
+    rc, msg = op.verify(proof)
+    assert rc == 0, msg
+    bad = bytearray(proof)
+    bad[700] ^= 4
+    assert op.verify(bytes(bad))[0] != 0 and not ctx.verify_proof(bytes(bad))
+    op.close()
+    ctx.close()
