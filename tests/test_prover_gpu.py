@@ -80,3 +80,24 @@ def test_eip152_sweep_proofs(setup17, idx):
     ref = op.create_proof(rec, 1, seed)
     assert first_diff(proof, ref) is None, "proof chunk %s differs" % first_diff(proof, ref)
     assert op.verify(proof)[0] == 0
+
+
+@pytest.mark.parametrize("fold_rounds", [3, 6, 8])
+def test_ipa_fold_round_count_does_not_change_the_proof(zk, monkeypatch, fold_rounds):
+    """The inner-product argument keeps the first r rounds on the original generators and folds them once
+    (prover_state.h ipa_fold_rounds: r = 5 on one GPU, 5 + log2(world) in a group).  r is a cost choice only:
+    every value gives the default's proof bytes (which test_proof_bytes_match_oracle ties to the oracle)."""
+    seed = zk.REFERENCE_SEED
+    inputs = zk.synthetic_inputs(3)
+
+    def prove():
+        c = zk.Context(0)
+        c.params_generate_substitute(17, seed)   # the 8-bit fold tables are built here, for the r in force
+        c.keygen(12, 3)
+        proof = c.create_proof(inputs, 3, seed)
+        c.close()
+        return proof
+
+    want = prove()
+    monkeypatch.setenv("ZK_IPA_FOLD_ROUNDS", str(fold_rounds))
+    assert prove() == want

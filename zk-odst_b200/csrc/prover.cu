@@ -234,6 +234,14 @@ struct PhaseTrace {
   ~PhaseTrace() {
     if (next < sizeof PROOF_PHASES / sizeof *PROOF_PHASES) nvtxRangePop();  // error return inside a phase
   }
+  // trace only: elapsed time of a step inside the running phase
+  void note(const char* name) {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[phase]   . %-26s %8.3f ms\n", name, std::chrono::duration<double, std::milli>(now - t).count());
+    t = now;
+  }
   // ends the running phase (whose name is passed for the trace) and starts the next one
   void mark(const char* name) {
     nvtxRangePop();
@@ -673,6 +681,7 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
       c.out_stride2 = en;
       if ((rc = ntt_run(ctx, W->polys_all + sb[0] * n, (uint32_t)n, W->cosets_all + sb[0] * en, k, c))) return rc;
     }
+    phase.note("quotient: column transforms");
     // coefficients: every rank needs every column in full (evaluations, multiopen) -> in-place all-gather.
     // coset values: every rank needs only the rows of its share of the quotient -> row segments exchanged
     // point to point (world x less traffic than gathering the columns in full)
@@ -695,6 +704,7 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
         return rc;
       }
     }
+    phase.note("quotient: exchanges");
     NttTables* TNq = nullptr;
     if ((rc = ntt_tables(ctx, k, &TNq))) return rc;
     QuotientArgs qa;
@@ -740,6 +750,7 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
     } else {
       if ((rc = quotient_run(ctx, qa, n, 0, en))) return rc;
     }
+    phase.note("quotient: rows (+ h exchange)");
     // back to coefficients.  On coset j, h(c_j w^i) = sum_p (c_j^n)^p h_p(c_j w^i): the size-n inverse
     // transform of the coset's values, unscaled by c_j^-i, is e_j = sum_p gamma_j^p h_p coefficient-wise,
     // and the 3 x 3 Vandermonde system gives the three pieces h_p (K.h_solve = V^-1).
@@ -997,6 +1008,7 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
     Affine cm;
     if ((rc = commit(ctx, sp, P.fb_g, n,s_blind, &cm))) return rc;
     tr.write_point(cm);
+    phase.note("ipa: s poly + commit");
     const Fp xi = tr.squeeze_challenge();
     const Fp z = tr.squeeze_challenge();
     Fp* pp = W->p_poly;  // becomes p'
@@ -1024,15 +1036,18 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
     // latency-bound on a GPU) never runs.
     Fp* svec = W->tmp_a;
     Fp* cvec = W->tmp_b;
-    const bool two_stage = P.fb_g8.table != nullptr && k > IPA_FOLD_ROUNDS + 8;
-    const int fold_at = two_stage ? IPA_FOLD_ROUNDS : k;
+    const int fold_rounds = ipa_fold_rounds(ctx->dist_world);
+    const bool two_stage = P.fb_g8.table != nullptr && k > fold_rounds + 8 && (1 << fold_rounds) % ctx->dist_world == 0;
+    const int fold_at = two_stage ? fold_rounds : k;
     const FixedBase* fb = &P.fb_g;
     FixedBase fb_h;
     uint64_t base_n = n;  // size of the current generator vector (n, then n >> r)
     launch_map(ctx, n, [=] __device__(uint64_t m) { svec[m] = Fp::one(); });
     std::vector<Fp> us;
+    phase.note("ipa: p', b, setup");
     for (int j = 0; j < k; j++) {
       const uint64_t half = 1ull << (k - j - 1);
+      if (j == fold_at) phase.note("ipa: rounds on g");
       if (j == fold_at) {
         base_n = n >> fold_at;
         if ((rc = ensure_fold_workspace(ctx, W, base_n))) return rc;
@@ -1041,6 +1056,7 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
         if ((rc = fixed_base_build_inplace(ctx, base_n, 2, IPA_STAGE2_C, W->h_table, W->h_tmp, &fb_h))) return rc;
         fb = &fb_h;
         launch_map(ctx, base_n, [=] __device__(uint64_t m) { svec[m] = Fp::one(); });
+        phase.note("ipa: fold + table");
       }
       const uint64_t bn = base_n;
       launch_map(ctx, bn, [=] __device__(uint64_t m) {
@@ -1079,6 +1095,7 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
       });
       f = f + l_rand * u_inv + r_rand * u;
     }
+    phase.note("ipa: rounds on H");
     Fp c;
     ZK_CUDA(ctx, cudaMemcpyAsync(&c, pp, sizeof(Fp), cudaMemcpyDeviceToHost, st));
     ZK_CUDA(ctx, zk_stream_sync(ctx));

@@ -4,6 +4,7 @@
 // (blake2f-circuit/benches/blake2f.rs:83-97); `DeviceKeys` replaces `ProvingKey`/`VerifyingKey`
 // from `keygen_vk` / `keygen_pk` (benches/blake2f.rs:102-103) for the BLAKE2f Table16 circuit.
 #pragma once
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -21,7 +22,20 @@ constexpr int NUM_SETS = 4;     // permutation grand products: chunks of degree 
 constexpr int BLINDING = 5;     // ConstraintSystem::blinding_factors() for this circuit
 constexpr int CS_DEGREE = 4;
 constexpr int NUM_COSETS = 3;        // quotient degree: h = h_0 + X^n h_1 + X^2n h_2
-constexpr int IPA_FOLD_ROUNDS = 5;   // IPA rounds on the original generators before they are folded once
+// IPA rounds on the original generators before they are folded once.  The rounds on g are MSMs split over a
+// multi-GPU group by point range; the fold's bucket reduction, the window table over the folded generators and
+// the rounds on them are not, and each halves with every extra round on g: a group of 2^e ranks folds e rounds
+// later (n = 2^23 on 8 GPUs: the argument takes 89 ms at 5 rounds).  ZK_IPA_FOLD_ROUNDS
+// overrides (1..8, for measurements).
+inline int ipa_fold_rounds(int world) {
+  int r = 5;
+  for (int w = world; w > 1 && r < 8; w >>= 1) r++;
+  if (const char* e = getenv("ZK_IPA_FOLD_ROUNDS")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= 8) r = v;
+  }
+  return r;
+}
 constexpr int IPA_STAGE2_C = 12;     // window bits of the table over the folded generators
 
 // halo2 advice column index of each permutation column, in enable_equality order

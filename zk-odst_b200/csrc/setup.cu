@@ -162,7 +162,7 @@ int32_t install_params(zk_ctx* ctx, int k, Affine* g, Affine* g_lagrange, const 
   if (rc) return rc;
   // 8-bit windows for the IPA generator fold (ipa_fold.cu); in a multi-GPU group the fold needs every
   // rank's range to be a whole number of n / 2^r blocks
-  if (k >= 15 && (1 << IPA_FOLD_ROUNDS) % ctx->dist_world == 0) {
+  if (k >= 15 && (1 << ipa_fold_rounds(ctx->dist_world)) % ctx->dist_world == 0) {
     rc = fixed_base_build(ctx, g, n, 2, &S->params.fb_g8, 8);
     if (rc) return rc;
   }
