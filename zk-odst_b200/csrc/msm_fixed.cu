@@ -212,7 +212,7 @@ __global__ void fscan_sums_kernel(uint32_t* tile_sums, uint32_t ntiles) {  // si
 // offsets += tile offsets; the last thread also writes the sentinel offsets[n] and the plan
 __global__ void fscan_add_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ tile_sums,
                                  const uint32_t* __restrict__ counts, uint32_t n, uint32_t resident_threads,
-                                 Plan* __restrict__ plan) {
+                                 uint32_t min_chunk, Plan* __restrict__ plan) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t v = out[i] + tile_sums[i / SCAN_TILE];
@@ -227,7 +227,7 @@ __global__ void fscan_add_kernel(uint32_t* __restrict__ out, const uint32_t* __r
     const uint32_t per_bucket = entries / n;
     if (chunk < per_bucket / 6) chunk = per_bucket / 6;
     chunk = (chunk + 3) & ~3u;
-    if (chunk < MIN_CHUNK) chunk = MIN_CHUNK;
+    if (chunk < min_chunk) chunk = min_chunk;
     Plan p;
     p.entries = entries;
     p.chunk = chunk;
@@ -636,7 +636,15 @@ int32_t msm_fixed_batch(zk_ctx* ctx, const FixedBase& fb, const MsmJob* jobs, in
   const uint32_t acc_grid = (uint32_t)ctx->sm_count * (uint32_t)ctx->msm_acc_blocks_per_sm;
   const uint32_t resident = acc_grid * ACC_THREADS;
   // chunk = max(MIN_CHUNK, entries / resident) so there are never more chunks than resident threads
-  const uint32_t max_chunks = (uint32_t)std::min<uint64_t>(max_entries / MIN_CHUNK + 1, (uint64_t)resident + 1);
+  // Small MSMs (the IPA rounds on the folded generators, < 2^20 entries) are bound by their chains of dependent
+  // point additions, not by throughput: 2 segment sums per tree thread instead of 8 (profiles/r02_ipa_stage2_sweep.jsonl:
+  // 7.18 -> 6.97 ms over the 14 rounds of a k = 19 proof; an 8-entry minimum chunk changed nothing and stays out).
+  // ZK_SMALL_MIN_CHUNK / ZK_SMALL_TREE_PER override for tools/ipa_sweep.py.
+  static const int small_min_chunk = [] { const char* e = getenv("ZK_SMALL_MIN_CHUNK"); return e ? atoi(e) : MIN_CHUNK; }();
+  static const int small_tree_per = [] { const char* e = getenv("ZK_SMALL_TREE_PER"); return e ? atoi(e) : 2; }();
+  const bool small = max_entries < (1u << 20);
+  const uint32_t min_chunk = small ? (uint32_t)small_min_chunk : (uint32_t)MIN_CHUNK;
+  const uint32_t max_chunks = (uint32_t)std::min<uint64_t>(max_entries / min_chunk + 1, (uint64_t)resident + 1);
   const uint32_t max_hbuckets = max_chunks / (SERIAL_HEADS + 1) + 16;
   const uint32_t max_items = max_chunks / PIECE + max_hbuckets + 16;
   static const int reduce_variant = [] {
@@ -644,7 +652,8 @@ int32_t msm_fixed_batch(zk_ctx* ctx, const FixedBase& fb, const MsmJob* jobs, in
     const int v = e ? atoi(e) : 2;   // 4-bucket segments, 8 segment sums per tree thread
     return v >= 0 && v < 4 ? v : 2;
   }();
-  const int SEG = REDUCE_SHAPES[reduce_variant].seg, TREE_PER_THREAD = REDUCE_SHAPES[reduce_variant].per_thread;
+  const int SEG = REDUCE_SHAPES[reduce_variant].seg;
+  const int TREE_PER_THREAD = small && small_tree_per ? small_tree_per : REDUCE_SHAPES[reduce_variant].per_thread;
   const uint32_t nsegs = B / SEG;
   int nbits = 0;
   while ((1u << nbits) < nsegs) nbits++;
@@ -714,7 +723,7 @@ int32_t msm_fixed_batch(zk_ctx* ctx, const FixedBase& fb, const MsmJob* jobs, in
     fixed_digits_kernel<<<gt, T, 0, st>>>(dj, count, fb.lo, d_extra, c, nwin, stride, B, tmp, ranks, counts);
     fscan_tiles_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(counts, offsets, tiles, NB);
     fscan_sums_kernel<<<1, 1024, 0, st>>>(tiles, ntiles);
-    fscan_add_kernel<<<(NB + T - 1) / T, T, 0, st>>>(offsets, tiles, counts, NB, resident, plan);
+    fscan_add_kernel<<<(NB + T - 1) / T, T, 0, st>>>(offsets, tiles, counts, NB, resident, min_chunk, plan);
     fixed_scatter_kernel<<<gt, T, 0, st>>>(dj, tmp, ranks, count, eidx, nwin, stride, fb.npoints, B, offsets, sorted);
     {
       KernelTimer acc_timer(ctx, KC_MSM_ACC);
@@ -729,6 +738,8 @@ int32_t msm_fixed_batch(zk_ctx* ctx, const FixedBase& fb, const MsmJob* jobs, in
     else fixed_reduce_level1_kernel<4><<<(nsegs_total + 127) / 128, 128, 0, st>>>(buckets, nsegs_total, A, S);
     const dim3 tree_grid(blocks_x, nout, (unsigned)nb);
     if (TREE_PER_THREAD == 8) fixed_reduce_tree_kernel<8><<<tree_grid, TREE_THREADS, 0, st>>>(A, S, nsegs, part, blocks_x, nout);
+    else if (TREE_PER_THREAD == 2) fixed_reduce_tree_kernel<2><<<tree_grid, TREE_THREADS, 0, st>>>(A, S, nsegs, part, blocks_x, nout);
+    else if (TREE_PER_THREAD == 1) fixed_reduce_tree_kernel<1><<<tree_grid, TREE_THREADS, 0, st>>>(A, S, nsegs, part, blocks_x, nout);
     else fixed_reduce_tree_kernel<4><<<tree_grid, TREE_THREADS, 0, st>>>(A, S, nsegs, part, blocks_x, nout);
     fixed_reduce_final_kernel<<<(unsigned)nb * nout, 32, 0, st>>>(part, blocks_x, out);
     ctx->launches += 12;

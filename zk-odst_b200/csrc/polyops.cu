@@ -242,14 +242,18 @@ sum_partials_kernel(const Fp* __restrict__ partials, uint32_t nblocks, Fp* __res
   Fp total = block_sum(acc, sh);
   if (threadIdx.x == 0) results[blockIdx.x] = total;
 }
+// blockIdx.y selects the pair: <a0, b0> or <a1, b1>
 __global__ void __launch_bounds__(EV_THREADS)
-inner_product_kernel(const Fp* __restrict__ a, const Fp* __restrict__ b, uint64_t n, Fp* __restrict__ partials) {
+inner_product_kernel(const Fp* __restrict__ a0, const Fp* __restrict__ b0, const Fp* __restrict__ a1,
+                     const Fp* __restrict__ b1, uint64_t n, Fp* __restrict__ partials) {
   __shared__ Fp sh[EV_THREADS];
+  const Fp* a = blockIdx.y ? a1 : a0;
+  const Fp* b = blockIdx.y ? b1 : b0;
   Fp acc = Fp::zero();
   for (uint64_t i = blockIdx.x * (uint64_t)EV_THREADS + threadIdx.x; i < n; i += (uint64_t)gridDim.x * EV_THREADS)
     acc = acc + a[i] * b[i];
   Fp total = block_sum(acc, sh);
-  if (threadIdx.x == 0) partials[blockIdx.x] = total;
+  if (threadIdx.x == 0) partials[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = total;
 }
 }  // namespace
 
@@ -296,20 +300,23 @@ int32_t poly_eval_batch(zk_ctx* ctx, const EvalJob* jobs, int njobs, uint64_t n,
   return ZK_OK;
 }
 
-int32_t inner_product(zk_ctx* ctx, const Fp* a, const Fp* b, uint64_t n, Fp* result_host) {
+// results_host[0] = <a0, b0>, results_host[1] = <a1, b1>: one launch pair and one wait for both (the two inner
+// products of an IPA round)
+int32_t inner_product_pair(zk_ctx* ctx, const Fp* a0, const Fp* b0, const Fp* a1, const Fp* b1, uint64_t n,
+                           Fp results_host[2]) {
   cudaStream_t st = ctx->stream;
   uint32_t nblocks = (uint32_t)((n + EV_THREADS * 8 - 1) / (EV_THREADS * 8));
   if (nblocks < 1) nblocks = 1;
   if (nblocks > 1024) nblocks = 1024;
-  int32_t rc = ensure_buf(ctx, ctx->eval_ws, ((size_t)nblocks + 64) * sizeof(Fp));
+  int32_t rc = ensure_buf(ctx, ctx->eval_ws, (2 * (size_t)nblocks + 64) * sizeof(Fp));
   if (rc) return rc;
   Fp* partials = (Fp*)ctx->eval_ws.ptr;
-  Fp* result = partials + nblocks;
-  inner_product_kernel<<<nblocks, EV_THREADS, 0, st>>>(a, b, n, partials);
-  sum_partials_kernel<<<1, EV_THREADS, 0, st>>>(partials, nblocks, result);
+  Fp* result = partials + 2 * (size_t)nblocks;
+  inner_product_kernel<<<dim3(nblocks, 2), EV_THREADS, 0, st>>>(a0, b0, a1, b1, n, partials);
+  sum_partials_kernel<<<2, EV_THREADS, 0, st>>>(partials, nblocks, result);
   ctx->launches += 2;
   ZK_CUDA(ctx, cudaGetLastError());
-  ZK_CUDA(ctx, cudaMemcpyAsync(result_host, result, sizeof(Fp), cudaMemcpyDeviceToHost, st));
+  ZK_CUDA(ctx, cudaMemcpyAsync(results_host, result, 2 * sizeof(Fp), cudaMemcpyDeviceToHost, st));
   ZK_CUDA(ctx, zk_stream_sync(ctx));
   return ZK_OK;
 }

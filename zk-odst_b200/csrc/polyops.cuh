@@ -72,6 +72,7 @@ static inline bool dist_ranges_ok(uint64_t n, int world) { return world > 1 && n
 // In a group (dist_ranges_ok) every rank reads only its own coefficient range of each polynomial.
 int32_t poly_eval_batch(zk_ctx* ctx, const EvalJob* jobs, int njobs, uint64_t n, Fp* results_host);
 // <a, b> over n elements
-int32_t inner_product(zk_ctx* ctx, const Fp* a, const Fp* b, uint64_t n, Fp* result_host);
+int32_t inner_product_pair(zk_ctx* ctx, const Fp* a0, const Fp* b0, const Fp* a1, const Fp* b1, uint64_t n,
+                           Fp results_host[2]);
 
 }  // namespace zkodst

@@ -136,7 +136,8 @@ int32_t get_workspace(zk_ctx* ctx, DeviceKeys& K, ProofWorkspace** out) {
 
 int32_t ensure_fold_workspace(zk_ctx* ctx, ProofWorkspace* W, uint64_t len) {
   if (W->fold_ws) return ZK_OK;
-  const int nwin = (255 + IPA_STAGE2_C - 1) / IPA_STAGE2_C + ((255 % IPA_STAGE2_C) == 0 ? 1 : 0);
+  const int c2 = ipa_stage2_c();
+  const int nwin = (255 + c2 - 1) / c2 + ((255 % c2) == 0 ? 1 : 0);
   const size_t pts = (size_t)nwin * (len + 2);
   ZK_CUDA(ctx, cudaMalloc(&W->fold_ws, ipa_fold_workspace_bytes(len, ctx->dist_world)));
   W->all.push_back(W->fold_ws);
@@ -1053,7 +1054,7 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
         if ((rc = ensure_fold_workspace(ctx, W, base_n))) return rc;
         if ((rc = ipa_fold_generators(ctx, P.fb_g8, us.data(), fold_at, W->fold_ws, W->h_table))) return rc;
         ZK_CUDA(ctx, cudaMemcpyAsync(W->h_table + base_n, P.g + n, 2 * sizeof(Affine), cudaMemcpyDeviceToDevice, st));
-        if ((rc = fixed_base_build_inplace(ctx, base_n, 2, IPA_STAGE2_C, W->h_table, W->h_tmp, &fb_h))) return rc;
+        if ((rc = fixed_base_build_inplace(ctx, base_n, 2, ipa_stage2_c(), W->h_table, W->h_tmp, &fb_h))) return rc;
         fb = &fb_h;
         launch_map(ctx, base_n, [=] __device__(uint64_t m) { svec[m] = Fp::one(); });
         phase.note("ipa: fold + table");
@@ -1063,9 +1064,9 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
         uint64_t i = m & (2 * half - 1);
         cvec[m] = (i < half ? pp[i + half] : pp[i - half]) * svec[m];
       });
-      Fp vl, vr;
-      if ((rc = inner_product(ctx, pp + half, b, half, &vl))) return rc;
-      if ((rc = inner_product(ctx, pp, b + half, half, &vr))) return rc;
+      Fp lr_values[2];
+      if ((rc = inner_product_pair(ctx, pp + half, b, pp, b + half, half, lr_values))) return rc;
+      const Fp vl = lr_values[0], vr = lr_values[1];
       const Fp l_rand = tape.next(), r_rand = tape.next();
       // L and R share the scalar vector and differ in the index bit they keep: one pipeline, 2 jobs
       MsmJob lr[2];
@@ -1086,12 +1087,12 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
       const Fp u = tr.squeeze_challenge();
       const Fp u_inv = u.inv();
       us.push_back(u);
-      launch_map(ctx, half, [=] __device__(uint64_t i) {
-        pp[i] = pp[i] + pp[i + half] * u_inv;
-        b[i] = b[i] + b[i + half] * u;
-      });
-      launch_map(ctx, bn, [=] __device__(uint64_t m) {
-        if (m & half) svec[m] = svec[m] * u;
+      launch_map(ctx, bn > half ? bn : half, [=] __device__(uint64_t m) {
+        if (m < half) {
+          pp[m] = pp[m] + pp[m + half] * u_inv;
+          b[m] = b[m] + b[m + half] * u;
+        }
+        if (m < bn && (m & half)) svec[m] = svec[m] * u;
       });
       f = f + l_rand * u_inv + r_rand * u;
     }

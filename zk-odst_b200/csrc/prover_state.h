@@ -36,7 +36,17 @@ inline int ipa_fold_rounds(int world) {
   }
   return r;
 }
-constexpr int IPA_STAGE2_C = 12;     // window bits of the table over the folded generators
+// Window bits of the table over the folded generators.  13, not 12: 255 = 21 * 12 + 3 leaves a 3-bit top window
+// whose 8,192 digits land in 7 buckets per job, which then take the heavy path of the accumulation in every round
+// (67 us per launch); 255 = 19 * 13 + 8 spreads the top window over 128 buckets.  Rounds on the folded generators of
+// a k = 19 proof: 6.97 -> 6.47 ms (profiles/r02_ipa_stage2_sweep.jsonl).  ZK_IPA_STAGE2_C overrides (8..16).
+inline int ipa_stage2_c() {
+  if (const char* e = getenv("ZK_IPA_STAGE2_C")) {
+    const int v = atoi(e);
+    if (v >= 8 && v <= 16) return v;
+  }
+  return 13;
+}
 
 // halo2 advice column index of each permutation column, in enable_equality order
 static const int PERM_COLUMNS[NUM_PERM] = {8, 9, 1, 2, 0, 3, 4, 5};
