@@ -154,8 +154,9 @@ constexpr int XS_FIELDS_PER_THREAD = 64;        // 1024 stream words per thread
 constexpr int XS_THREAD_SHIFT = 10;             // log2(16 * XS_FIELDS_PER_THREAD)
 
 __global__ void __launch_bounds__(128)
-xorshift_fields_kernel(XsState base, const XsMatrix* __restrict__ pow2, uint64_t n, Fp* __restrict__ out) {
-  const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+xorshift_fields_kernel(XsState base, const XsMatrix* __restrict__ pow2, uint64_t t_lo, uint64_t n,
+                       Fp* __restrict__ out) {
+  const uint64_t t = t_lo + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;  // stream position / 1024 words
   const uint64_t first = t * XS_FIELDS_PER_THREAD;
   if (first >= n) return;
   XsState st = base;
@@ -187,8 +188,12 @@ class ProofRng {
     }
     return Fp::from_u512(w);
   }
-  // the next n field elements of the stream, produced on the device
-  int32_t fill_device(uint64_t n, Fp* out) {
+  // the next n field elements of the stream, produced on the device: out[lo .. lo + cnt) only (a rank of a group
+  // that works by coefficient range needs no more; lo and cnt whole threads' worth), the stream advances by n
+  int32_t fill_device(uint64_t n, Fp* out, uint64_t lo = 0, uint64_t cnt = ~0ull) {
+    if (cnt == ~0ull) cnt = n - lo;
+    if (lo % XS_FIELDS_PER_THREAD || (lo + cnt != n && cnt % XS_FIELDS_PER_THREAD))
+      return set_error(ctx_, ZK_E_INVALID, "fill_device: range not aligned");
     int32_t rc = ensure_buf(ctx_, ctx_->misc_ws, sizeof(XsMatrix) * XS_JUMP_POWERS);
     if (rc) return rc;
     if (!ctx_->xs_table_loaded) {
@@ -196,9 +201,10 @@ class ProofRng {
                                     cudaMemcpyHostToDevice, ctx_->stream));
       ctx_->xs_table_loaded = true;
     }
-    const uint64_t threads = (n + XS_FIELDS_PER_THREAD - 1) / XS_FIELDS_PER_THREAD;
-    xorshift_fields_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, ctx_->stream>>>(
-        st_, (const XsMatrix*)ctx_->misc_ws.ptr, n, out);
+    const uint64_t threads = (cnt + XS_FIELDS_PER_THREAD - 1) / XS_FIELDS_PER_THREAD;
+    if (threads)
+      xorshift_fields_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, ctx_->stream>>>(
+          st_, (const XsMatrix*)ctx_->misc_ws.ptr, lo / XS_FIELDS_PER_THREAD, lo + cnt, out);
     ctx_->launches++;
     ZK_CUDA(ctx_, cudaGetLastError());
     st_ = xs_jump(st_, n * 16);
@@ -639,7 +645,8 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
   }
   phase.mark("lookup product");
   // ---- vanishing argument: random polynomial ----------------------------------------------------------------
-  if ((rc = tape.fill_device(n, W->random_poly))) return rc;
+  // committed by point range, evaluated and opened by coefficient range: a rank of a group needs only its range
+  if ((rc = tape.fill_device(n, W->random_poly, r_lo, r_cnt))) return rc;
   const Fp random_blind = tape.next();
   {
     Affine cm;
@@ -997,7 +1004,7 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
   phase.mark("multiopen");
   // ---- inner product argument (K11) ------------------------------------------------------------------------------
   {
-    if ((rc = tape.fill_device(n, W->s_poly))) return rc;
+    if ((rc = tape.fill_device(n, W->s_poly, r_lo, r_cnt))) return rc;
     Fp* sp = W->s_poly;
     {
       EvalJob j{sp, x3};
