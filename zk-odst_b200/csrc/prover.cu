@@ -1050,7 +1050,13 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
     const FixedBase* fb = &P.fb_g;
     FixedBase fb_h;
     uint64_t base_n = n;  // size of the current generator vector (n, then n >> r)
-    launch_map(ctx, n, [=] __device__(uint64_t m) { svec[m] = Fp::one(); });
+    // the rounds on g read s and c only at the points of this rank's share of the split MSM
+    uint64_t m_lo = 0, m_hi = n;
+    if (ctx->dist_world > 1 && P.fb_g.split) {
+      m_lo = P.fb_g.lo;
+      m_hi = P.fb_g.lo + P.fb_g.nmain;
+    }
+    launch_map_range(ctx, m_lo, m_hi - m_lo, [=] __device__(uint64_t m) { svec[m] = Fp::one(); });
     std::vector<Fp> us;
     phase.note("ipa: p', b, setup");
     for (int j = 0; j < k; j++) {
@@ -1063,11 +1069,13 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
         ZK_CUDA(ctx, cudaMemcpyAsync(W->h_table + base_n, P.g + n, 2 * sizeof(Affine), cudaMemcpyDeviceToDevice, st));
         if ((rc = fixed_base_build_inplace(ctx, base_n, 2, ipa_stage2_c(), W->h_table, W->h_tmp, &fb_h))) return rc;
         fb = &fb_h;
+        m_lo = 0;  // the table over the folded generators is whole on every rank
+        m_hi = base_n;
         launch_map(ctx, base_n, [=] __device__(uint64_t m) { svec[m] = Fp::one(); });
         phase.note("ipa: fold + table");
       }
-      const uint64_t bn = base_n;
-      launch_map(ctx, bn, [=] __device__(uint64_t m) {
+      const uint64_t bn = base_n, lo = m_lo, hi = m_hi;
+      launch_map_range(ctx, lo, hi - lo, [=] __device__(uint64_t m) {
         uint64_t i = m & (2 * half - 1);
         cvec[m] = (i < half ? pp[i + half] : pp[i - half]) * svec[m];
       });
@@ -1094,12 +1102,12 @@ static int32_t create_proof_impl(zk_ctx* ctx, const uint8_t* inputs, bool inputs
       const Fp u = tr.squeeze_challenge();
       const Fp u_inv = u.inv();
       us.push_back(u);
-      launch_map(ctx, bn > half ? bn : half, [=] __device__(uint64_t m) {
+      launch_map(ctx, hi > half ? hi : half, [=] __device__(uint64_t m) {
         if (m < half) {
           pp[m] = pp[m] + pp[m + half] * u_inv;
           b[m] = b[m] + b[m + half] * u;
         }
-        if (m < bn && (m & half)) svec[m] = svec[m] * u;
+        if (m >= lo && m < hi && (m & half)) svec[m] = svec[m] * u;
       });
       f = f + l_rand * u_inv + r_rand * u;
     }
