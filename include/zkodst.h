@@ -166,7 +166,7 @@ int32_t zk_ntt_fp(zk_ctx* ctx, void* data, int32_t log_n, int32_t inverse, int32
  * (create_proof commits the 12 advice columns, the 5 grand products, the 3 pieces of h this way;
  * blake2f-circuit/benches/blake2f.rs:125): out[m] = sum_t scalars[m][t] * base_t + blinds[m] * W.
  * scalars: ncols x 2^k Montgomery Fp, column after column (host, or device when on_device != 0);
- * blinds: ncols Montgomery Fp (host); out_affine: ncols x 64 B (host).  index_mask != 0 restricts the sum
+ * blinds: ncols Montgomery Fp (host); out_affine: ncols x 64 B (host).  index_mask != 0 (one bit) restricts the sum
  * to the terms t with ((t & index_mask) != 0) == (index_select != 0): the support of the vectors L and R of
  * an inner-product round (`best_multiexp(&p_prime[half..], &g_prime[..half])` in poly/commitment/prover.rs).
  *

@@ -226,3 +226,11 @@ def test_k20_proof_accepted_by_oracle_verifier(oracle, zk):
     assert op.verify(bytes(bad))[0] != 0 and not ctx.verify_proof(bytes(bad))
     op.close()
     ctx.close()
+
+
+def test_commit_batch_rejects_a_mask_of_two_bits(setup19, zk):
+    ctx, _, _, _, _ = setup19
+    sc = np.zeros((N, 4), dtype=np.uint64)
+    out = np.zeros((1, 8), dtype=np.uint64)
+    with pytest.raises(zk.ZkError):
+        ctx.commit_batch(0, sc, 1, np.zeros((1, 4), dtype=np.uint64), out, index_mask=6, index_select=1)

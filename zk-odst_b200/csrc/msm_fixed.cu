@@ -70,7 +70,21 @@ struct DevJobs {
   uint32_t side_mask[MSM_MAX_BATCH];
   int32_t side_select[MSM_MAX_BATCH];
   int32_t n_extra[MSM_MAX_BATCH];
+  // Support mask of one index bit (the L / R vectors of an IPA round): the job's threads enumerate only the kept
+  // indices of this rank's range — thread t handles the (kept_before + t)-th kept index of the whole vector —
+  // instead of visiting every index and dropping half.  kept = how many there are in [lo, lo + count).
+  uint64_t kept_before[MSM_MAX_BATCH];
+  uint64_t kept[MSM_MAX_BATCH];
 };
+// indices with ((index & mask) != 0) == select, mask one bit: how many lie below x, and the j-th of them
+__host__ __device__ inline uint64_t kept_below(uint64_t x, uint64_t mask, bool select) {
+  const uint64_t r = x & (2 * mask - 1), start = select ? mask : 0;
+  const uint64_t in_block = r <= start ? 0 : (r - start < mask ? r - start : mask);
+  return (x / (2 * mask)) * mask + in_block;
+}
+__host__ __device__ inline uint64_t kept_index(uint64_t j, uint64_t mask, bool select) {
+  return (j / mask) * 2 * mask + (j & (mask - 1)) + (select ? mask : 0);
+}
 
 // ---- table construction --------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
@@ -110,21 +124,18 @@ __global__ void fixed_digits_kernel(DevJobs jobs, uint64_t count, uint64_t lo, c
                                     uint32_t* __restrict__ ranks_tmp, uint32_t* __restrict__ counts) {
   const int job = blockIdx.y;
   uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  const uint64_t total = count + jobs.n_extra[job];
-  if (t >= total) return;
+  const uint64_t kept = jobs.kept[job];
+  if (t >= kept + jobs.n_extra[job]) return;
   uint64_t s[4];
   bool zero = false;
-  if (t < count) {
-    // optional support mask (IPA rounds): keep index t only if ((t & mask) != 0) == side_select
+  if (t < kept) {
     const uint32_t mask = jobs.side_mask[job];
-    if (mask && ((((lo + t) & mask) != 0) != (jobs.side_select[job] != 0))) zero = true;
-    if (!zero) {
-      Fp v = jobs.scalars[job][lo + t];
-      zero = v.is_zero();
-      if (!zero) v.to_canonical(s);
-    }
+    const uint64_t index = mask ? kept_index(jobs.kept_before[job] + t, mask, jobs.side_select[job] != 0) : lo + t;
+    Fp v = jobs.scalars[job][index];
+    zero = v.is_zero();
+    if (!zero) v.to_canonical(s);
   } else {
-    extra[job * 4 + (t - count)].to_canonical(s);
+    extra[job * 4 + (t - kept)].to_canonical(s);
   }
   uint32_t* my_counts = counts + (size_t)job * B;
   uint32_t* my_tmp = entries_tmp + (size_t)job * nwin * stride + t;
@@ -240,15 +251,19 @@ __global__ void fscan_add_kernel(uint32_t* __restrict__ out, const uint32_t* __r
 
 // scatter: sorted[pos] = table entry index (w * npoints + point) | sign << 31
 __global__ void fixed_scatter_kernel(DevJobs jobs, const uint32_t* __restrict__ entries_tmp,
-                                     const uint32_t* __restrict__ ranks_tmp, uint64_t count,
+                                     const uint32_t* __restrict__ ranks_tmp, uint64_t lo,
                                      const uint32_t* __restrict__ extra_index, int nwin, uint64_t stride,
                                      uint64_t npoints, uint32_t B, const uint32_t* __restrict__ offsets,
                                      uint32_t* __restrict__ sorted) {
   const int job = blockIdx.y;
   uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  const uint64_t total = count + jobs.n_extra[job];
-  if (t >= total) return;
-  const uint32_t point = t < count ? (uint32_t)t : extra_index[job * 4 + (t - count)];  // local indices
+  const uint64_t kept = jobs.kept[job];
+  if (t >= kept + jobs.n_extra[job]) return;
+  const uint32_t mask = jobs.side_mask[job];
+  // local indices (table rows of this rank's range)
+  const uint32_t point = t >= kept ? extra_index[job * 4 + (t - kept)]
+                         : mask    ? (uint32_t)(kept_index(jobs.kept_before[job] + t, mask, jobs.side_select[job] != 0) - lo)
+                                   : (uint32_t)t;
   const uint32_t* my_tmp = entries_tmp + (size_t)job * nwin * stride + t;
   const uint32_t* my_rank = ranks_tmp + (size_t)job * nwin * stride + t;
   const uint32_t* my_offsets = offsets + (size_t)job * B;
@@ -602,6 +617,8 @@ int32_t msm_fixed_batch(zk_ctx* ctx, const FixedBase& fb, const MsmJob* jobs, in
     return set_error(ctx, ZK_E_INVALID, "msm_fixed: bad sizes");
   for (int m = 0; m < nb; m++) {
     if (jobs[m].n_extra < 0 || jobs[m].n_extra > 4) return set_error(ctx, ZK_E_INVALID, "msm_fixed: bad extras");
+    if (jobs[m].side_mask & (jobs[m].side_mask - 1))
+      return set_error(ctx, ZK_E_INVALID, "msm_fixed: the index mask must be one bit");
     for (int e = 0; e < jobs[m].n_extra; e++)
       if (jobs[m].extra_index[e] < fb.total_main) return set_error(ctx, ZK_E_INVALID, "msm_fixed: extra index");
   }
@@ -697,11 +714,15 @@ int32_t msm_fixed_batch(zk_ctx* ctx, const FixedBase& fb, const MsmJob* jobs, in
   Fp h_extra[MSM_MAX_BATCH * 4];
   uint32_t h_eidx[MSM_MAX_BATCH * 4];
   bool any_extra = false;
+  uint64_t most = 4;  // threads of the widest job: digits and scatter grids
   for (int m = 0; m < MSM_MAX_BATCH; m++) {
     const MsmJob& j = jobs[m < nb ? m : 0];
     dj.scalars[m] = j.scalars;
     dj.side_mask[m] = j.side_mask;
     dj.side_select[m] = j.side_select;
+    dj.kept_before[m] = j.side_mask ? kept_below(fb.lo, j.side_mask, j.side_select != 0) : 0;
+    dj.kept[m] = j.side_mask ? kept_below(fb.lo + count, j.side_mask, j.side_select != 0) - dj.kept_before[m] : count;
+    if (m < nb && dj.kept[m] + 4 > most) most = dj.kept[m] + 4;
     const int ne = (m < nb && fb.nextra) ? j.n_extra : 0;  // extras live on rank 0 only
     dj.n_extra[m] = ne;
     for (int e = 0; e < 4; e++) {
@@ -719,12 +740,12 @@ int32_t msm_fixed_batch(zk_ctx* ctx, const FixedBase& fb, const MsmJob* jobs, in
   {
     KernelTimer timer(ctx, KC_MSM);
     const int T = 256;
-    const dim3 gt((unsigned)((stride + T - 1) / T), (unsigned)nb);
+    const dim3 gt((unsigned)((most + T - 1) / T), (unsigned)nb);
     fixed_digits_kernel<<<gt, T, 0, st>>>(dj, count, fb.lo, d_extra, c, nwin, stride, B, tmp, ranks, counts);
     fscan_tiles_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(counts, offsets, tiles, NB);
     fscan_sums_kernel<<<1, 1024, 0, st>>>(tiles, ntiles);
     fscan_add_kernel<<<(NB + T - 1) / T, T, 0, st>>>(offsets, tiles, counts, NB, resident, min_chunk, plan);
-    fixed_scatter_kernel<<<gt, T, 0, st>>>(dj, tmp, ranks, count, eidx, nwin, stride, fb.npoints, B, offsets, sorted);
+    fixed_scatter_kernel<<<gt, T, 0, st>>>(dj, tmp, ranks, fb.lo, eidx, nwin, stride, fb.npoints, B, offsets, sorted);
     {
       KernelTimer acc_timer(ctx, KC_MSM_ACC);
       acc_kernel<<<acc_grid, ACC_THREADS, 0, st>>>(fb.table, sorted, offsets, NB, plan, heads, buckets);
