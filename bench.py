@@ -330,7 +330,7 @@ def main():
                     help="skip the CPU oracle legs (cpu_baseline and the parity gates that need it)")
     ap.add_argument("--no-one-thread", action="store_true", help="reference arm: skip the single-thread figure")
     ap.add_argument("--compressions", type=int, default=N_COMPRESSIONS)
-    ap.add_argument("--streams", type=int, default=4,
+    ap.add_argument("--streams", type=int, default=8,
                     help="concurrent proof streams per GPU (one context and host thread each)")
     ap.add_argument("--blocking-sync", type=int, default=-1,
                     help="1: host threads sleep while waiting for the device, 0: spin, -1: sleep only "
