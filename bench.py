@@ -507,10 +507,17 @@ def main():
         R = ROWS_PER_COMPRESSION
         # dominant kernel: MSM bucket accumulation
         # terms the accumulate launches process per proof: 13 full-width commitments (2 lookup, 5 grand
-        # products, random, 3 h pieces, q', s), 12 advice columns (<= 32-bit cells), and the IPA: 5 rounds
-        # of n terms on the original generators, then k - 5 rounds of n / 32 terms on the folded ones
+        # products, random, 3 h pieces, q', s), 12 advice columns (<= 32-bit cells), and the IPA: `fold` rounds
+        # of n terms on the original generators, then k - fold rounds of n / 2^fold terms on the folded ones
         # (halo2's schedule would be 2n MSM terms plus n generator-folding scalar multiplications)
-        fold = 5 if (k > 13 and (not split or 32 % world == 0)) else k
+        # (a group of 2^e ranks keeps e more rounds on the original generators: prover_state.h ipa_fold_rounds)
+        fold = 5
+        if split:
+            w = world
+            while w > 1 and fold < 8:
+                fold, w = fold + 1, w >> 1
+        if not (k > fold + 8 and (not split or (1 << fold) % world == 0)):
+            fold = k
         ipa_terms = fold + (k - fold) / float(1 << fold)
         full_terms = 13 + ipa_terms
         # (MSM-split group: the timed launches are rank 0's, which process 1 / world of every MSM's terms)
