@@ -372,6 +372,9 @@ def main():
     seed = zk.REFERENCE_SEED
     split = args.msm_split and world > 1
     S = 1 if split else max(1, args.streams)   # concurrent proof streams per GPU (one context each)
+    # a context holds the window tables of g / g_lagrange, the keys' coset forms and a proof's workspace:
+    # about 9.5 KB per row (k = 23: ~80 GB); larger circuits get fewer concurrent contexts instead of an OOM
+    S = max(1, min(S, int(0.8 * torch.cuda.get_device_properties(local_rank).total_memory // (nrows * 9728))))
     inputs = zk.synthetic_inputs(n, stream=0 if split else rank)  # independent batch per rank
     ev_stream = torch.cuda.Stream()  # carries only the timing events
     torch.cuda.set_stream(ev_stream)
