@@ -31,6 +31,7 @@ UNIT = "compressions/s"
 # SURVEY.md §8d accounting: a full-width MSM term = 16 bucket additions x 11 Fq mults x 136 MAC,
 # a <= 32-bit advice term = 2 windows.
 MAC_FULL, MAC_SMALL = 16 * 11 * 136, 2 * 11 * 136
+EXECUTED_PER_ALGORITHMIC = (10 * 97) / (11 * 136.0)   # IMAD.WIDE the accumulation issues per algorithmic MAC
 MAC_PER_FP_MUL = 136
 ROWS_PER_COMPRESSION = 292 + 392 * ROUNDS
 # dram__bytes_read.sum + dram__bytes_write.sum of one full-width accumulation launch (k = 19), from the
@@ -537,10 +538,14 @@ def main():
             "traffic_source": TRAFFIC_CAPTURE["source"],
             "peak_source": "zk_bench_int_pipe mode 1 (mad.wide.u32) measured in this run; "
                            "MEASURED_PEAKS.json has no integer peak",
-            # for information: the same achieved rate against the carry-chained MAC rate (mode 2) — the rate a
-            # multi-limb product can actually issue at; `frac` above stays against the plain mad.wide peak
+            # for information: the MACs the kernel EXECUTES (10 products of 97 carry-chained IMAD.WIDE per mixed
+            # addition, tools/gen_mont_ptx.py, against the 11 x 136 of the algorithmic count above) against the
+            # carry-chained MAC rate (mode 2) — the rate a multi-limb product can actually issue at; `frac` above
+            # stays algorithmic MACs against the plain mad.wide peak
             "peak_carry_chained_tmacs": chain_peak / 1e12,
-            "frac_of_carry_chained_peak": achieved / (chain_peak / 1e12) if achieved else None,
+            "executed_tmacs": achieved * EXECUTED_PER_ALGORITHMIC if achieved else None,
+            "frac_of_carry_chained_peak": (achieved * EXECUTED_PER_ALGORITHMIC / (chain_peak / 1e12)
+                                           if achieved else None),
             "launches_per_proof": acc_launches, "avg_launch_ms": acc_ms / acc_launches if acc_launches else None,
             "algorithmic_mac_per_proof": mac_per_proof,
             "accounting": "SURVEY.md 8d per-term figures (23936 MAC full-width, 2992 MAC advice) x the "
